@@ -1,0 +1,251 @@
+/*
+ * mmtpsm_b200.h — C ABI of libmmtpsm_b200.so
+ *
+ * The B200 (sm_100a) replacement for the native side of the MMT-PSM mean-teacher training hot
+ * path.  Every entry point takes raw DEVICE pointers, sizes and a CUDA stream (passed as void*,
+ * i.e. a cudaStream_t), returns an int status (0 = ok) and never allocates, frees or synchronises:
+ * the caller owns every output and workspace buffer.  No torch types appear in this file.
+ *
+ * Each block cites the reference interface it replaces (paths relative to the reference root).
+ * The reference-side binding a maintainer adds is shown in INTEGRATION.md.
+ */
+#ifndef MMTPSM_B200_H_
+#define MMTPSM_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MMT_OK 0
+#define MMT_ERR_INVALID_ARGUMENT 1
+#define MMT_ERR_WORKSPACE_TOO_SMALL 2
+#define MMT_ERR_CUDA 3
+#define MMT_ERR_UNSUPPORTED 4
+
+/* Thread-local text of the last error raised by a call on this thread ("" if none). */
+const char* mmt_last_error(void);
+/* Library version string, e.g. "mmtpsm_b200 0.1 (sm_100a)". */
+const char* mmt_version(void);
+/* Number of kernels this library has launched on this process since load / last reset
+ * (used by bench.py for the "gpu_launches" claim). */
+int64_t mmt_launch_count(void);
+void mmt_reset_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * NMS — replaces maskrcnn_benchmark/csrc/nms.h:10-28 (`_C.nms`) and csrc/cuda/nms.cu:23-131.
+ * Semantics are those of the CUDA flavour (the one the reference's live path always takes,
+ * structures/boxlist_ops.py:28-30): legacy "+1" areas (nms.cu:13-21), suppress when IoU > thr
+ * (nms.cu:60), boxes visited in descending score order, kept ORIGINAL indices returned in
+ * ascending order (nms.cu:127-130).  Ties in score are broken towards the lower original index.
+ * Unlike the reference there is no device->host copy, no malloc and no legacy-stream launch.
+ *
+ * Segmented form: `n_segments` independent problems laid out back to back; segment s owns boxes
+ * [seg_offsets[s], seg_offsets[s+1]).  `seg_offsets` is a HOST array of n_segments+1 ints.
+ * keep_out   [total]      int64, per segment the kept indices RELATIVE to the segment start,
+ *                         ascending, written at keep_out + seg_offsets[s]
+ * n_keep_out [n_segments] int32 (device) number kept per segment
+ * ------------------------------------------------------------------------------------------ */
+size_t mmt_nms_workspace_bytes(int total_boxes, int n_segments, int max_segment_boxes);
+int mmt_nms_segmented_f32(const float* boxes_xyxy, const float* scores, const int* seg_offsets_host,
+                          int n_segments, float iou_threshold, int64_t* keep_out, int* n_keep_out,
+                          void* workspace, size_t workspace_bytes, void* stream);
+/* Single problem convenience form (exactly `_C.nms(dets, scores, thr)` minus the tensor plumbing). */
+int mmt_nms_f32(const float* boxes_xyxy, const float* scores, int n, float iou_threshold,
+                int64_t* keep_out, int* n_keep_out, void* workspace, size_t workspace_bytes,
+                void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * ROIAlign — replaces csrc/ROIAlign.h:11-45 (`_C.roi_align_forward/backward`) and
+ * csrc/cuda/ROIAlign_cuda.cu:65-122,178-254.  "aligned=False" Caffe2 semantics: no coordinate
+ * rounding, ROI extent clamped to >= 1, sampling grid = sampling_ratio (or ceil(roi/pooled) when
+ * <= 0), out-of-bounds rule y < -1 || y > H -> 0.
+ *
+ * Feature maps and outputs are addressed through explicit ELEMENT strides so the same kernel
+ * serves NCHW (the reference's layout) and NHWC/channels_last (the layout this library's conv
+ * engine produces; channel stride 1 gives 128-byte coalesced, float4-vectorised accesses).
+ * rois [n_rois,5] = (batch_index as float, x1, y1, x2, y2), contiguous.
+ * Backward ACCUMULATES into grad_input (caller zero-fills it once; several levels / poolers can
+ * share one buffer).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  int64_t n, c, h, w; /* element strides of the batch, channel, row and column axes */
+} mmt_strides4;
+
+int mmt_roi_align_forward_f32(const float* input, mmt_strides4 input_strides, int batch, int channels,
+                              int height, int width, const float* rois, int n_rois,
+                              float spatial_scale, int pooled_h, int pooled_w, int sampling_ratio,
+                              float* output, mmt_strides4 output_strides, void* stream);
+int mmt_roi_align_backward_f32(const float* grad_output, mmt_strides4 grad_output_strides,
+                               const float* rois, int n_rois, float spatial_scale, int pooled_h,
+                               int pooled_w, int sampling_ratio, float* grad_input,
+                               mmt_strides4 grad_input_strides, int batch, int channels, int height,
+                               int width, void* stream);
+
+/* ROIPool — replaces csrc/ROIPool.h:10-45 / csrc/cuda/ROIPool_cuda.cu:17-108 (kept for ABI
+ * completeness; the FPN configuration on the hot path only uses ROIAlign). NCHW contiguous. */
+int mmt_roi_pool_forward_f32(const float* input, int batch, int channels, int height, int width,
+                             const float* rois, int n_rois, float spatial_scale, int pooled_h,
+                             int pooled_w, float* output, int* argmax, void* stream);
+int mmt_roi_pool_backward_f32(const float* grad_output, const int* argmax, const float* rois,
+                              int n_rois, int pooled_h, int pooled_w, float* grad_input, int batch,
+                              int channels, int height, int width, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * SigmoidFocalLoss — ABSENT from this reference tree; semantics are those of
+ * upstream facebookresearch/maskrcnn-benchmark csrc/cuda/SigmoidFocalLoss_cuda.cu:
+ *   p = sigmoid(x); t = targets[n] (1-based class, 0 = background, < 0 = ignore)
+ *   L[n,c] = -[t==c+1] a (1-p)^g log(max(p,FLT_MIN))
+ *            -[t!=c+1 && t>=0] (1-a) p^g (-x [x>=0] - log(1+exp(x-2x[x>=0])))
+ * losses/grad_logits are [n, num_classes]; backward multiplies by grad_losses[n,c].
+ * ------------------------------------------------------------------------------------------ */
+int mmt_sigmoid_focal_loss_forward_f32(const float* logits, const int* targets, int n,
+                                       int num_classes, float gamma, float alpha, float* losses,
+                                       void* stream);
+int mmt_sigmoid_focal_loss_backward_f32(const float* logits, const int* targets,
+                                        const float* grad_losses, int n, int num_classes,
+                                        float gamma, float alpha, float* grad_logits, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * PSM consistency loss — replaces the ~40-kernel chain of
+ * modeling/roi_heads/box_head/loss.py:164-237 (`_mean_var_logits`, `evaluatePSM`),
+ * :267-287 (`cls_loss`, 'bce' -> soft-target CE branch) and :311-315 (`sharpen`).
+ *   student_logits [n,C], teacher_logits [n_views][n,C] (view-major, contiguous), labels [n] int64
+ *   positives = labels > 0, negatives = labels == 0 (labels < 0 ignored)
+ *   v[i]  = sum_c std_k(softmax(z_k[i]))[c]   (unbiased std over views)
+ *   keep m = min(#neg, floor(#pos/2)) negatives of largest v (ties: lower index first);
+ *            hard_negative == 0 keeps the first m negatives of the order given in `neg_order`
+ *   q = softmax(mean_k z_k), sharpened q^(1/T)/sum when sharpen != 0
+ *   loss = sum_c mean_rows(-q log_softmax(s) w) / 3, w = 1 (pos) / neg_weight (kept neg)
+ * (the literal 3 is the reference's, loss.py:284,287, independent of C).
+ * Outputs: loss_out[1]; grad_student [n,C] = d loss / d student_logits (zero on unused rows);
+ * selected_out [n] int32 (1 = positive row, 2 = kept negative, 0 = unused) for exact-index parity.
+ * Workspace: mmt_psm_workspace_bytes(n).
+ * ------------------------------------------------------------------------------------------ */
+size_t mmt_psm_workspace_bytes(int n);
+int mmt_psm_loss_f32(const float* student_logits, const float* teacher_logits, int n_views,
+                     const int64_t* labels, int n, int num_classes, float temperature, int sharpen,
+                     int hard_negative, float neg_weight, const int* neg_order, float* loss_out,
+                     float* grad_student, int* selected_out, void* workspace,
+                     size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * MGD (mask-guided feature distillation) — replaces `fg_hint_loss`
+ * (modeling/detector/generalized_rcnn.py:243-282), ~160 launches per iteration.
+ *
+ * mmt_mgd_masks: integral foreground map M [batch, H, W] (float) -> per-level binary masks
+ *   m_l = 1[adaptive_avg_pool2d(M, (h_l, w_l)) > 0.5] (generalized_rcnn.py:259-264) and their
+ *   sums.  masks_out is the concatenation over levels of [batch, h_l, w_l] uint8;
+ *   mask_sums_out [n_levels] float.
+ * mmt_mgd_level: one pyramid level, all teacher views in one pass (student read once):
+ *   num[k] = sum_{b,y,x,c} (S - T_k')^2 m  with T_k' = T_k flipped along x when flip_mask bit k
+ *   is set (generalized_rcnn.py:246-249).  Features are NHWC-addressed through strides.
+ *   partial_out [n_views] float is ACCUMULATED (caller zero-fills).
+ *   grad_student (nullable) receives sum_k coeff[k] * 2 (S - T_k') m, coeff = term_weight /
+ *   (mask_sum * C + 1e-7) read from device (so no host sync is needed).
+ * mmt_mgd_finalize: loss = mean over (view, level) of num / (mask_sum * C + 1e-7)
+ *   (generalized_rcnn.py:267-281).
+ * ------------------------------------------------------------------------------------------ */
+int mmt_mgd_masks_f32(const float* integral_mask, int batch, int height, int width,
+                      const int* level_h_host, const int* level_w_host, int n_levels,
+                      uint8_t* masks_out, float* mask_sums_out, void* stream);
+int mmt_mgd_level_f32(const float* student, mmt_strides4 student_strides,
+                      const float* const* teacher_views_host, mmt_strides4 teacher_strides,
+                      int n_views, unsigned flip_mask, const uint8_t* level_mask,
+                      const float* level_mask_sum, int batch, int channels, int height, int width,
+                      float term_weight, float* partial_out, float* grad_student,
+                      mmt_strides4 grad_strides, void* stream);
+int mmt_mgd_finalize_f32(const float* partials /*[n_levels][n_views]*/,
+                         const float* mask_sums /*[n_levels]*/, int n_levels, int n_views,
+                         int channels, float* loss_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Teacher EMA + student SGD — replaces `MTtrainer.update_teacher`
+ * (engine/MTtrainer.py:277-281; 264 launches) and torch.optim.SGD as configured by
+ * solver/build.py:5-23 (one param group per tensor; bias lr x2, weight decay 0).
+ * Parameters live in flat fp32 arenas; `segments` (DEVICE array) gives per-tensor hyper-params.
+ *   SGD:  g = grad + wd * p;  buf = first_step ? g : momentum * buf + g;  p -= lr * buf
+ *   EMA:  t = alpha * t + (1 - alpha) * p      (with the updated p, as the reference orders it)
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  int64_t begin, end; /* element range in the arena; begin must be a multiple of 4 */
+  float lr, weight_decay;
+  int trainable; /* 0: SGD skipped (frozen tensor), EMA still applied */
+  int reserved;
+} mmt_param_segment;
+
+int mmt_ema_f32(float* teacher, const float* student, int64_t n, float alpha, void* stream);
+int mmt_sgd_ema_f32(float* student, float* teacher /*nullable: no EMA*/, const float* grad,
+                    float* momentum_buf, int64_t n, const mmt_param_segment* segments_dev,
+                    int n_segments, float momentum, float alpha, int first_step,
+                    float grad_scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Convolution engine — replaces torch.nn.Conv2d + FrozenBatchNorm2d + ReLU as used by
+ * layers/misc.py:30-43, layers/batch_norm.py:6-24, modeling/backbone/resnet.py:254-275,
+ * modeling/backbone/fpn.py:43-69, modeling/rpn/rpn.py:39-46 (cuDNN in the reference).
+ * Activations are NHWC fp32; weights are [out_c][k_h][k_w][in_c] ("OHWI") fp32.  The tensor
+ * cores consume the fp32 operands as TF32 (kind::tf32, fp32 accumulate in TMEM) — the same
+ * arithmetic cuDNN applies to the reference's fp32 convs on Ampere-and-later GPUs.
+ *   y = act( conv(x, w) * scale[c] + bias[c] + residual )
+ * `impl` selects the kernel: MMT_CONV_TCGEN05 (TMA + tcgen05 implicit GEMM; needs in_c % 32 == 0
+ * and out_c % 16 == 0) or MMT_CONV_SIMT (plain fp32 FFMA kernel, any shape; used for the 7x7
+ * stem (in_c = 3), the skinny heads, and as the on-device cross-check of the tensor-core path).
+ * MMT_CONV_AUTO picks tcgen05 whenever the shape allows.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  int batch, in_h, in_w, in_c;
+  int out_c, k_h, k_w;
+  int stride, pad;
+  int out_h, out_w;
+} mmt_conv_shape;
+
+#define MMT_CONV_AUTO 0
+#define MMT_CONV_TCGEN05 1
+#define MMT_CONV_SIMT 2
+
+#define MMT_EPI_RELU 1
+
+size_t mmt_conv_workspace_bytes(const mmt_conv_shape* shape);
+int mmt_conv_fprop_f32(const float* x_nhwc, const float* w_ohwi, const float* scale /*nullable*/,
+                       const float* bias /*nullable*/, const float* residual_nhwc /*nullable*/,
+                       float* y_nhwc, const mmt_conv_shape* shape, int epilogue_flags, int impl,
+                       void* stream);
+/* dx = conv_transpose(dy, w): data gradient.  dx is fully overwritten. */
+int mmt_conv_dgrad_f32(const float* dy_nhwc, const float* w_ohwi, float* dx_nhwc,
+                       const mmt_conv_shape* shape, int impl, void* workspace,
+                       size_t workspace_bytes, void* stream);
+/* dw[o][r][s][i] = sum_pixels dy[p][o] x[p + (r,s)][i]; dbias[o] = sum dy (nullable).
+ * dw/dbias are fully overwritten. */
+int mmt_conv_wgrad_f32(const float* x_nhwc, const float* dy_nhwc, float* dw_ohwi,
+                       float* dbias /*nullable*/, const mmt_conv_shape* shape, int impl,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* Fused elementwise helpers around the convs (all NHWC fp32, contiguous) ------------------- */
+/* g_out = g_in * (y > 0) * scale[c]  (ReLU + FrozenBN backward; scale nullable, relu optional) */
+int mmt_bn_relu_backward_f32(const float* grad_y, const float* y, const float* scale, float* grad_z,
+                             int64_t pixels, int channels, int apply_relu_mask, void* stream);
+/* 3x3/s2/p1 max-pool forward + backward (resnet.py:292 stem) and 1x1/s2 subsample (fpn.py:74). */
+int mmt_maxpool3x3s2_forward_f32(const float* x, float* y, int batch, int in_h, int in_w,
+                                 int channels, void* stream);
+int mmt_subsample2_forward_f32(const float* x, float* y, int batch, int in_h, int in_w,
+                               int channels, void* stream);
+/* grad_x[2oy][2ox] += grad_y[oy][ox] (grad_x is accumulated into, in_h/in_w are x's extent). */
+int mmt_subsample2_backward_f32(const float* grad_y, float* grad_x, int batch, int in_h, int in_w,
+                                int channels, void* stream);
+/* FPN top-down: out = lateral + nearest_upsample_x2(top)  (fpn.py:57-62), and its backward
+ * (grad_top[y/2][x/2] += grad_out[y][x]).  lateral/out [b,h,w,c], top [b,th,tw,c]. */
+int mmt_upsample2_add_f32(const float* lateral, const float* top, float* out, int batch, int h,
+                          int w, int top_h, int top_w, int channels, void* stream);
+int mmt_upsample2_backward_f32(const float* grad_out, float* grad_top, int batch, int h, int w,
+                               int top_h, int top_w, int channels, void* stream);
+/* Layout transforms between the reference's NCHW/OIHW and this library's NHWC/OHWI. */
+int mmt_nchw_to_nhwc_f32(const float* src, float* dst, int n, int c, int h, int w, void* stream);
+int mmt_nhwc_to_nchw_f32(const float* src, float* dst, int n, int c, int h, int w, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMTPSM_B200_H_ */

@@ -1,0 +1,35 @@
+// Internal interface between the conv dispatch (conv_api.cu) and the two kernel families.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "mmtpsm_b200.h"
+
+namespace mmt {
+
+// fp32 FFMA kernels (conv_simt.cu)
+int conv_fprop_simt(const float* x, const float* w, const float* scale, const float* bias,
+                    const float* residual, float* y, const mmt_conv_shape& s, int flags,
+                    cudaStream_t stream);
+int conv_dgrad_simt(const float* dy, const float* w, float* dx, const mmt_conv_shape& s,
+                    cudaStream_t stream);
+int conv_wgrad_simt(const float* x, const float* dy, float* dw, float* dbias, const mmt_conv_shape& s,
+                    cudaStream_t stream);
+// dbias[c] = sum over pixels of dy[p][c] (dbias is overwritten)
+int conv_bias_grad(const float* dy, long long pixels, int out_c, float* dbias, cudaStream_t stream);
+
+// TMA + tcgen05 (TF32) kernels (conv_tc.cu)
+bool conv_tc_supported_fprop(const mmt_conv_shape& s);
+bool conv_tc_supported_dgrad(const mmt_conv_shape& s);
+bool conv_tc_supported_wgrad(const mmt_conv_shape& s);
+int conv_fprop_tc(const float* x, const float* w, const float* scale, const float* bias,
+                  const float* residual, float* y, const mmt_conv_shape& s, int flags,
+                  cudaStream_t stream);
+// w_t must hold the dgrad-transformed filter [in_c][k_h][k_w][out_c] (rotated 180 degrees)
+int conv_dgrad_tc(const float* dy, const float* w_t, float* dx, const mmt_conv_shape& s,
+                  cudaStream_t stream);
+int conv_wgrad_tc(const float* x, const float* dy, float* dw, float* dbias, const mmt_conv_shape& s,
+                  void* workspace, size_t workspace_bytes, cudaStream_t stream);
+// [out_c][k_h][k_w][in_c] -> [in_c][k_h][k_w][out_c] with the taps rotated by 180 degrees
+int conv_filter_for_dgrad(const float* w, float* w_t, const mmt_conv_shape& s, cudaStream_t stream);
+
+}  // namespace mmt

@@ -1,0 +1,729 @@
+// TMA + tcgen05 (TF32, fp32 accumulate in TMEM) implicit-GEMM convolution engine for sm_100a.
+//
+// Replaces cuDNN behind torch.nn.Conv2d (+ FrozenBatchNorm2d + ReLU + residual add) on the path
+//   maskrcnn_benchmark/layers/misc.py:30-43, layers/batch_norm.py:19-24,
+//   modeling/backbone/resnet.py:254-275, modeling/backbone/fpn.py:43-69, modeling/rpn/rpn.py:39-46,
+//   modeling/roi_heads/mask_head/roi_mask_feature_extractors.py:131-146 and the box-head FCs.
+//
+// Data layout: activations NHWC fp32, filters [out_c][k_h][k_w][in_c] fp32 (K contiguous).
+//
+// forward / data-gradient kernel (conv_tc_kernel)
+//   GEMM view  D[128 pixels][BN out channels] += A[128 pixels][32 ch of one tap] * B[BN][32]
+//   * the 128 pixels of a tile are a TW x TH spatial patch of ONE image; the A tile of filter tap
+//     (r,s) is the same patch shifted by (r-pad, s-pad), fetched by ONE 4-D TMA box load whose
+//     out-of-bounds elements are zero-filled by the hardware — the implicit-GEMM "im2col" costs
+//     no instructions and no extra traffic.  1x1 convs flatten (n,h,w) into one axis (no tile
+//     waste); 1x1/stride-2 convs read through a strided tensor map.
+//   * warp roles: warp 0 = TMA producer, warp 1 = tcgen05.mma issuer (one elected lane) + TMEM
+//     allocator, warps 2-5 = epilogue (TMEM -> registers -> scale/bias/residual/ReLU -> swizzled
+//     smem -> TMA store).  smem ring of STAGES (A 16 KB + B BN*128 B) slots with full/empty
+//     mbarriers; the accumulator is double-buffered in TMEM (2*BN columns) so the epilogue of
+//     tile i overlaps the main loop of tile i+1; persistent CTAs, one per SM.
+// weight-gradient kernel (wgrad_tc_kernel)
+//   D[128 out_c][BN in_c] (one filter tap) += dy^T * x over 32-pixel patches; both operands are
+//   MN-major (pixels are the GEMM K axis), split-K over pixel ranges, partial tiles are summed
+//   into dw by TMA reduce-add (cp.reduce.async.bulk.tensor ... .add) — no atomics in SM code.
+#include <cuda.h>
+#include <mutex>
+
+#include "common.cuh"
+#include "conv_common.cuh"
+#include "tc_ptx.cuh"
+
+namespace {
+
+using namespace tc;
+
+constexpr int kThreads = 192;
+constexpr int kTileM = 128;
+constexpr int kABytes = kTileM * 128;  // 128 rows x 32 fp32
+constexpr int kStagingBytes = kTileM * 128;
+constexpr int kSmemLimit = 232448;  // 227 KB
+
+template <int BN>
+struct Cfg {
+  static constexpr int kBBytes = BN * 128;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStagesRaw = (kSmemLimit - 2 * kStagingBytes - 2048) / kStageBytes;
+  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static constexpr int kTmemCols = 2 * BN;  // 128 / 256 / 512: powers of two >= 32
+  static constexpr int kSmemBytes = kStages * kStageBytes + 2 * kStagingBytes + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+struct FpropParams {
+  int tiles_w, tiles_h, tiles_b;  // spatial tiles per image and images
+  int n_tiles;                    // out channels / BN
+  int TW, TH;
+  int kh, kw, cblocks;  // cblocks = channels of A / 32
+  int pad_h, pad_w;
+  int y_w, y_h;  // output extent (residual bounds)
+  long long r_sb, r_sh, r_sw;
+  const float* scale;
+  const float* bias;
+  const float* residual;
+  int relu;
+  int total_tiles;
+};
+
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+struct SmemLayout {
+  uint32_t a[8], b[8];
+  uint32_t staging[2];
+  uint32_t full[8], empty[8], tfull[2], tempty[2];
+  uint32_t tmem_slot;
+};
+
+template <int STAGES, int A_BYTES, int B_BYTES>
+__device__ __forceinline__ SmemLayout carve(uint8_t* raw) {
+  SmemLayout L;
+  uint32_t base = smem_u32(raw);
+  base = (base + 1023u) & ~1023u;
+#pragma unroll
+  for (int s = 0; s < 8; ++s) {
+    L.a[s] = base + (s < STAGES ? s : 0) * (A_BYTES + B_BYTES);
+    L.b[s] = L.a[s] + A_BYTES;
+  }
+  uint32_t p = base + STAGES * (A_BYTES + B_BYTES);
+  L.staging[0] = p;
+  L.staging[1] = p + kStagingBytes;
+  p += 2 * kStagingBytes;
+#pragma unroll
+  for (int s = 0; s < 8; ++s) {
+    L.full[s] = p + 8 * s;
+    L.empty[s] = p + 64 + 8 * s;
+  }
+  L.tfull[0] = p + 128;
+  L.tfull[1] = p + 136;
+  L.tempty[0] = p + 144;
+  L.tempty[1] = p + 152;
+  L.tmem_slot = p + 160;
+  return L;
+}
+
+__device__ __forceinline__ uint32_t ld_shared_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, float x, float y, float z, float w) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmY, const FpropParams p) {
+  using C = Cfg<BN>;
+  constexpr int STAGES = C::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  const SmemLayout L = carve<STAGES, kABytes, C::kBBytes>(smem_raw);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&tmA);
+    prefetch_tensormap(&tmB);
+    prefetch_tensormap(&tmY);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < STAGES; ++s) {
+        mbar_init(L.full[s], 1);
+        mbar_init(L.empty[s], 1);
+      }
+      mbar_init(L.tfull[0], 1);
+      mbar_init(L.tfull[1], 1);
+      mbar_init(L.tempty[0], 1);
+      mbar_init(L.tempty[1], 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(L.tmem_slot, C::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = ld_shared_u32(L.tmem_slot);
+
+  const int kblocks = p.kh * p.kw * p.cblocks;
+  const int tiles_per_img = p.tiles_w * p.tiles_h;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        const int nt = t % p.n_tiles, mt = t / p.n_tiles;
+        const int b = mt / tiles_per_img, rem = mt % tiles_per_img;
+        const int h0 = (rem / p.tiles_w) * p.TH, w0 = (rem % p.tiles_w) * p.TW;
+        int kb = 0;
+        for (int r = 0; r < p.kh; ++r)
+          for (int s = 0; s < p.kw; ++s)
+            for (int cb = 0; cb < p.cblocks; ++cb, ++kb) {
+              mbar_wait(L.empty[stage], phase ^ 1u);
+              mbar_arrive_expect_tx(L.full[stage], (uint32_t)C::kStageBytes);
+              tma_load_4d(L.a[stage], &tmA, L.full[stage], cb * 32, w0 + s - p.pad_w, h0 + r - p.pad_h, b);
+              tma_load_2d(L.b[stage], &tmB, L.full[stage], kb * 32, nt * BN);
+              if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+            }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_tf32(kTileM, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+        mbar_wait(L.tempty[acc], acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(L.full[stage], phase);
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t da = umma_desc_kmajor_sw128(L.a[stage] + k * 32);
+            const uint64_t db = umma_desc_kmajor_sw128(L.b[stage] + k * 32);
+            mma_tf32_ss(d_tmem, da, db, idesc, (kb | k) ? 1u : 0u);
+          }
+          mma_commit(L.empty[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        mma_commit(L.tfull[acc]);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    const int q = warp & 3;            // TMEM lane quadrant this warp may access
+    const int row = q * 32 + lane;     // pixel index inside the tile
+    const int epi_tid = threadIdx.x - 64;
+    const int tw = row % p.TW, th = row / p.TW;
+    int it = 0;
+    uint32_t chunk_counter = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+      const int nt = t % p.n_tiles, mt = t / p.n_tiles;
+      const int b = mt / tiles_per_img, rem = mt % tiles_per_img;
+      const int h0 = (rem / p.tiles_w) * p.TH, w0 = (rem % p.tiles_w) * p.TW;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+      mbar_wait(L.tfull[acc], acc_phase);
+      tc_fence_after();
+      const bool pix_ok = (w0 + tw < p.y_w) && (h0 + th < p.y_h);
+      const float* res_row = p.residual
+                                 ? p.residual + b * p.r_sb + (long long)(h0 + th) * p.r_sh + (long long)(w0 + tw) * p.r_sw
+                                 : nullptr;
+#pragma unroll 1
+      for (int j = 0; j < BN / 32; ++j, ++chunk_counter) {
+        const uint32_t buf = L.staging[chunk_counter & 1u];
+        if (epi_tid == 0) tma_wait_group_read<1>();  // the buffer used two chunks ago has been read
+        named_bar_sync(1, 128);
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + j * 32), v);
+        tmem_ld_wait();
+        tc_fence_before();
+        const int c0 = nt * BN + j * 32;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          float o[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float x = __uint_as_float(v[g * 4 + e]);
+            const int c = c0 + g * 4 + e;
+            if (p.scale) x *= __ldg(p.scale + c);
+            if (p.bias) x += __ldg(p.bias + c);
+            o[e] = x;
+          }
+          if (res_row != nullptr && pix_ok) {
+            const float4 rr = __ldg(reinterpret_cast<const float4*>(res_row + c0 + g * 4));
+            o[0] += rr.x; o[1] += rr.y; o[2] += rr.z; o[3] += rr.w;
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) o[e] = fmaxf(o[e], 0.f);
+          }
+          st_shared_v4(buf + row * 128 + ((g ^ (row & 7)) << 4), o[0], o[1], o[2], o[3]);
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(1, 128);
+        if (epi_tid == 0) {
+          tma_store_4d(&tmY, buf, c0, w0, h0, b);
+          tma_commit_group();
+        }
+      }
+      // every epilogue thread has finished its tcgen05.ld of this accumulator (barrier above)
+      if (epi_tid == 0) mbar_arrive(L.tempty[acc]);
+    }
+    if (epi_tid == 0) tma_wait_group<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------ wgrad
+struct WgradParams {
+  int tiles_w, tiles_h, tiles_b;  // 32-pixel patches per image, images
+  int TW, TH;
+  int kh, kw, pad_h, pad_w;
+  int co_tiles, ci_tiles, splits;
+  int pixel_tiles, tiles_per_split;
+  int cin;
+  int total_items;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX,
+                const __grid_constant__ CUtensorMap tmDW, const WgradParams p) {
+  using C = Cfg<BN>;
+  constexpr int STAGES = C::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  const SmemLayout L = carve<STAGES, kABytes, C::kBBytes>(smem_raw);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&tmDY);
+    prefetch_tensormap(&tmX);
+    prefetch_tensormap(&tmDW);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < STAGES; ++s) {
+        mbar_init(L.full[s], 1);
+        mbar_init(L.empty[s], 1);
+      }
+      mbar_init(L.tfull[0], 1);
+      mbar_init(L.tfull[1], 1);
+      mbar_init(L.tempty[0], 1);
+      mbar_init(L.tempty[1], 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(L.tmem_slot, C::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = ld_shared_u32(L.tmem_slot);
+  const int tiles_per_img = p.tiles_w * p.tiles_h;
+  const int taps = p.kh * p.kw;
+
+  // work item -> (co tile, tap, ci tile, split)
+  auto decode = [&](int item, int& co_t, int& tap, int& ci_t, int& pt_begin, int& pt_end) {
+    const int split = item % p.splits;
+    int r = item / p.splits;
+    ci_t = r % p.ci_tiles; r /= p.ci_tiles;
+    tap = r % taps;
+    co_t = r / taps;
+    pt_begin = split * p.tiles_per_split;
+    pt_end = min(p.pixel_tiles, pt_begin + p.tiles_per_split);
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+        int co_t, tap, ci_t, pb, pe;
+        decode(item, co_t, tap, ci_t, pb, pe);
+        const int r = tap / p.kw, s = tap % p.kw;
+        for (int pt = pb; pt < pe; ++pt) {
+          const int b = pt / tiles_per_img, rem = pt % tiles_per_img;
+          const int h0 = (rem / p.tiles_w) * p.TH, w0 = (rem % p.tiles_w) * p.TW;
+          mbar_wait(L.empty[stage], phase ^ 1u);
+          mbar_arrive_expect_tx(L.full[stage], (uint32_t)C::kStageBytes);
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+            tma_load_4d(L.a[stage] + g * 4096, &tmDY, L.full[stage], co_t * 128 + g * 32, w0, h0, b);
+#pragma unroll
+          for (int g = 0; g < BN / 32; ++g)
+            tma_load_4d(L.b[stage] + g * 4096, &tmX, L.full[stage], ci_t * BN + g * 32,
+                        w0 + s - p.pad_w, h0 + r - p.pad_h, b);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_tf32(kTileM, BN, 1, 1);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++it) {
+        int co_t, tap, ci_t, pb, pe;
+        decode(item, co_t, tap, ci_t, pb, pe);
+        const int acc = it & 1;
+        const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+        mbar_wait(L.tempty[acc], acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int pt = pb; pt < pe; ++pt) {
+          mbar_wait(L.full[stage], phase);
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {  // 4 x 8 pixels
+            const uint64_t da = umma_desc_mnmajor_sw128(L.a[stage] + k * 1024, 4096);
+            const uint64_t db = umma_desc_mnmajor_sw128(L.b[stage] + k * 1024, 4096);
+            mma_tf32_ss(d_tmem, da, db, idesc, (pt > pb || k) ? 1u : 0u);
+          }
+          mma_commit(L.empty[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        mma_commit(L.tfull[acc]);
+      }
+    }
+    __syncwarp();
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;  // out channel inside the 128-row tile
+    const int epi_tid = threadIdx.x - 64;
+    int it = 0;
+    uint32_t chunk_counter = 0;
+    for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++it) {
+      int co_t, tap, ci_t, pb, pe;
+      decode(item, co_t, tap, ci_t, pb, pe);
+      const int acc = it & 1;
+      const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+      const bool empty_range = pe <= pb;  // nothing accumulated: MMA warp still commits, D undefined
+      mbar_wait(L.tfull[acc], acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int j = 0; j < BN / 32; ++j, ++chunk_counter) {
+        const uint32_t buf = L.staging[chunk_counter & 1u];
+        if (epi_tid == 0) tma_wait_group_read<1>();
+        named_bar_sync(1, 128);
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + j * 32), v);
+        tmem_ld_wait();
+        tc_fence_before();
+#pragma unroll
+        for (int g = 0; g < 8; ++g)
+          st_shared_v4(buf + row * 128 + ((g ^ (row & 7)) << 4),
+                       empty_range ? 0.f : __uint_as_float(v[g * 4 + 0]),
+                       empty_range ? 0.f : __uint_as_float(v[g * 4 + 1]),
+                       empty_range ? 0.f : __uint_as_float(v[g * 4 + 2]),
+                       empty_range ? 0.f : __uint_as_float(v[g * 4 + 3]));
+        fence_proxy_async_smem();
+        named_bar_sync(1, 128);
+        if (epi_tid == 0) {
+          tma_reduce_add_2d(&tmDW, buf, tap * p.cin + ci_t * BN + j * 32, co_t * 128);
+          tma_commit_group();
+        }
+      }
+      if (epi_tid == 0) mbar_arrive(L.tempty[acc]);
+    }
+    if (epi_tid == 0) tma_wait_group<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::kTmemCols);
+  }
+}
+
+// [out_c][kh][kw][in_c] -> [in_c][kh][kw][out_c], taps rotated 180 degrees
+__global__ void __launch_bounds__(256) filter_dgrad_kernel(const float* __restrict__ w, float* __restrict__ wt,
+                                                           int out_c, int taps, int in_c) {
+  __shared__ float tile[32][33];
+  // per tap: transpose the [out_c][in_c] matrix (row stride taps*in_c) into [in_c][out_c]
+  const int tap = blockIdx.z;
+  const int rtap = taps - 1 - tap;
+  const int i0 = blockIdx.x * 32, o0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int k = ty; k < 32; k += 8) {
+    const int o = o0 + k, i = i0 + tx;
+    if (o < out_c && i < in_c) tile[k][tx] = w[((long long)o * taps + tap) * in_c + i];
+  }
+  __syncthreads();
+  for (int k = ty; k < 32; k += 8) {
+    const int i = i0 + k, o = o0 + tx;
+    if (o < out_c && i < in_c) wt[((long long)i * taps + rtap) * out_c + o] = tile[tx][k];
+  }
+}
+
+// ------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  });
+  return fn;
+}
+
+struct View4 {  // channels-innermost view: dims (c, w, h, n), element strides of w, h, n (c stride 1)
+  const void* base;
+  long long c, w, h, n;
+  long long sw, sh, sn;
+};
+
+int make_map(CUtensorMap* m, const View4& v, int box_c, int box_w, int box_h, const char* what) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return mmt::fail(MMT_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[4] = {(cuuint64_t)v.c, (cuuint64_t)v.w, (cuuint64_t)v.h, (cuuint64_t)v.n};
+  cuuint64_t strides[3] = {(cuuint64_t)v.sw * 4, (cuuint64_t)v.sh * 4, (cuuint64_t)v.sn * 4};
+  cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  if (((uintptr_t)v.base & 15) || (strides[0] & 15) || (strides[1] & 15) || (strides[2] & 15))
+    return mmt::fail(MMT_ERR_INVALID_ARGUMENT, "%s: tensor must be 16-byte aligned with 16-byte strides", what);
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(v.base), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return mmt::fail(MMT_ERR_CUDA, "%s: cuTensorMapEncodeTiled failed (%d)", what, (int)r);
+  return MMT_OK;
+}
+
+int make_map_2d(CUtensorMap* m, const void* base, long long inner, long long outer, long long row_stride,
+                int box_inner, int box_outer, const char* what) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return mmt::fail(MMT_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  cuuint64_t strides[1] = {(cuuint64_t)row_stride * 4};
+  cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
+  cuuint32_t es[2] = {1, 1};
+  if (((uintptr_t)base & 15) || (strides[0] & 15))
+    return mmt::fail(MMT_ERR_INVALID_ARGUMENT, "%s: matrix must be 16-byte aligned with 16-byte row stride", what);
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return mmt::fail(MMT_ERR_CUDA, "%s: cuTensorMapEncodeTiled failed (%d)", what, (int)r);
+  return MMT_OK;
+}
+
+// choose the TW x TH (= pixels) patch that wastes the least area on a w x h map
+void pick_patch(long long w, long long h, int pixels, int& TW, int& TH) {
+  long long best = -1;
+  for (int tw = pixels; tw >= 8; tw >>= 1) {
+    const int th = pixels / tw;
+    const long long area = mmt::ceil_div<long long>(w, tw) * tw * mmt::ceil_div<long long>(h, th) * th;
+    if (best < 0 || area < best) { best = area; TW = tw; TH = th; }
+  }
+}
+
+struct GemmProblem {
+  View4 a;          // activations feeding the GEMM A operand (a.c = channels per tap)
+  const float* b;   // [n_out][kh*kw*a.c]
+  int n_out;
+  int kh, kw, pad_h, pad_w;
+  View4 y;          // output view, y.c == n_out
+  const float* scale;
+  const float* bias;
+  const float* residual;  // addressed like y with strides r_*
+  long long r_sw, r_sh, r_sn;
+  int relu;
+};
+
+template <int BN>
+int launch_gemm(const GemmProblem& g, cudaStream_t stream) {
+  using C = Cfg<BN>;
+  int TW, TH;
+  pick_patch(g.y.w, g.y.h, kTileM, TW, TH);
+  CUtensorMap tmA, tmB, tmY;
+  if (int rc = make_map(&tmA, g.a, 32, TW, TH, "conv A operand")) return rc;
+  const long long Ktot = (long long)g.kh * g.kw * g.a.c;
+  if (int rc = make_map_2d(&tmB, g.b, Ktot, g.n_out, Ktot, 32, BN, "conv filter")) return rc;
+  if (int rc = make_map(&tmY, g.y, 32, TW, TH, "conv output")) return rc;
+  FpropParams p;
+  p.tiles_w = (int)mmt::ceil_div<long long>(g.y.w, TW);
+  p.tiles_h = (int)mmt::ceil_div<long long>(g.y.h, TH);
+  p.tiles_b = (int)g.y.n;
+  p.n_tiles = g.n_out / BN;
+  p.TW = TW; p.TH = TH;
+  p.kh = g.kh; p.kw = g.kw; p.cblocks = (int)(g.a.c / 32);
+  p.pad_h = g.pad_h; p.pad_w = g.pad_w;
+  p.y_w = (int)g.y.w; p.y_h = (int)g.y.h;
+  p.r_sb = g.r_sn; p.r_sh = g.r_sh; p.r_sw = g.r_sw;
+  p.scale = g.scale; p.bias = g.bias; p.residual = g.residual; p.relu = g.relu;
+  const long long total = (long long)p.tiles_w * p.tiles_h * p.tiles_b * p.n_tiles;
+  if (total > 0x7fffffffll) return mmt::fail(MMT_ERR_UNSUPPORTED, "conv: too many tiles");
+  p.total_tiles = (int)total;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MMT_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+    attr_set = true;
+  }
+  const int grid = (int)std::min<long long>(total, mmt::kNumSMs);
+  conv_tc_kernel<BN><<<grid, kThreads, C::kSmemBytes, stream>>>(tmA, tmB, tmY, p);
+  return mmt::check_launch("conv_tc_kernel");
+}
+
+int dispatch_gemm(const GemmProblem& g, cudaStream_t stream) {
+  if (g.n_out % 256 == 0) return launch_gemm<256>(g, stream);
+  if (g.n_out % 128 == 0) return launch_gemm<128>(g, stream);
+  if (g.n_out % 64 == 0) return launch_gemm<64>(g, stream);
+  return mmt::fail(MMT_ERR_UNSUPPORTED, "conv_tc: out channels %d not a multiple of 64", g.n_out);
+}
+
+View4 dense_nhwc(const float* base, long long n, long long h, long long w, long long c) {
+  return View4{base, c, w, h, n, c, w * c, h * w * c};
+}
+View4 flat_pixels(const float* base, long long pixels, long long c) {
+  return View4{base, c, pixels, 1, 1, c, pixels * c, pixels * c};
+}
+
+template <int BN>
+int launch_wgrad(const CUtensorMap& tmDY, const CUtensorMap& tmX, const CUtensorMap& tmDW,
+                 const WgradParams& p, cudaStream_t stream) {
+  using C = Cfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MMT_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+    attr_set = true;
+  }
+  const int grid = std::min(p.total_items, mmt::kNumSMs);
+  wgrad_tc_kernel<BN><<<grid, kThreads, C::kSmemBytes, stream>>>(tmDY, tmX, tmDW, p);
+  return mmt::check_launch("wgrad_tc_kernel");
+}
+
+}  // namespace
+
+namespace mmt {
+
+bool conv_tc_supported_fprop(const mmt_conv_shape& s) {
+  if (s.in_c % 32 || s.out_c % 64) return false;
+  if (s.stride == 1) return s.out_h == s.in_h + 2 * s.pad - s.k_h + 1 && s.out_w == s.in_w + 2 * s.pad - s.k_w + 1;
+  return s.stride == 2 && s.k_h == 1 && s.k_w == 1 && s.pad == 0;
+}
+bool conv_tc_supported_dgrad(const mmt_conv_shape& s) {
+  if (s.out_c % 32 || s.in_c % 64) return false;
+  if (s.stride == 1) return s.k_h - 1 - s.pad >= 0 && s.k_w - 1 - s.pad >= 0;
+  return s.stride == 2 && s.k_h == 1 && s.k_w == 1 && s.pad == 0;
+}
+bool conv_tc_supported_wgrad(const mmt_conv_shape& s) {
+  if (s.out_c % 128 || s.in_c % 64) return false;
+  if (s.stride == 1) return true;
+  return s.stride == 2 && s.k_h == 1 && s.k_w == 1 && s.pad == 0;
+}
+
+int conv_fprop_tc(const float* x, const float* w, const float* scale, const float* bias,
+                  const float* residual, float* y, const mmt_conv_shape& s, int flags, cudaStream_t stream) {
+  GemmProblem g;
+  const bool pointwise = s.k_h == 1 && s.k_w == 1 && s.pad == 0;
+  if (pointwise && s.stride == 1) {
+    const long long P = (long long)s.batch * s.in_h * s.in_w;
+    g.a = flat_pixels(x, P, s.in_c);
+    g.y = flat_pixels(y, P, s.out_c);
+    g.r_sw = s.out_c; g.r_sh = P * s.out_c; g.r_sn = P * s.out_c;
+  } else if (pointwise && s.stride == 2) {
+    g.a = View4{x, s.in_c, s.out_w, s.out_h, s.batch, 2ll * s.in_c, 2ll * s.in_w * s.in_c,
+                (long long)s.in_h * s.in_w * s.in_c};
+    g.y = dense_nhwc(y, s.batch, s.out_h, s.out_w, s.out_c);
+    g.r_sw = s.out_c; g.r_sh = (long long)s.out_w * s.out_c; g.r_sn = (long long)s.out_h * s.out_w * s.out_c;
+  } else {
+    g.a = dense_nhwc(x, s.batch, s.in_h, s.in_w, s.in_c);
+    g.y = dense_nhwc(y, s.batch, s.out_h, s.out_w, s.out_c);
+    g.r_sw = s.out_c; g.r_sh = (long long)s.out_w * s.out_c; g.r_sn = (long long)s.out_h * s.out_w * s.out_c;
+  }
+  g.b = w; g.n_out = s.out_c;
+  g.kh = s.k_h; g.kw = s.k_w; g.pad_h = s.pad; g.pad_w = s.pad;
+  g.scale = scale; g.bias = bias; g.residual = residual;
+  g.relu = (flags & MMT_EPI_RELU) ? 1 : 0;
+  return dispatch_gemm(g, stream);
+}
+
+int conv_dgrad_tc(const float* dy, const float* w_t, float* dx, const mmt_conv_shape& s, cudaStream_t stream) {
+  GemmProblem g;
+  const bool pointwise = s.k_h == 1 && s.k_w == 1 && s.pad == 0;
+  if (pointwise && s.stride == 1) {
+    const long long P = (long long)s.batch * s.in_h * s.in_w;
+    g.a = flat_pixels(dy, P, s.out_c);
+    g.y = flat_pixels(dx, P, s.in_c);
+  } else if (pointwise && s.stride == 2) {
+    // dx is zero except at the even positions, which receive the GEMM result through a strided map
+    MMT_CUDA(cudaMemsetAsync(dx, 0, sizeof(float) * (size_t)s.batch * s.in_h * s.in_w * s.in_c, stream));
+    g.a = dense_nhwc(dy, s.batch, s.out_h, s.out_w, s.out_c);
+    g.y = View4{dx, s.in_c, s.out_w, s.out_h, s.batch, 2ll * s.in_c, 2ll * s.in_w * s.in_c,
+                (long long)s.in_h * s.in_w * s.in_c};
+  } else {
+    g.a = dense_nhwc(dy, s.batch, s.out_h, s.out_w, s.out_c);
+    g.y = dense_nhwc(dx, s.batch, s.in_h, s.in_w, s.in_c);
+  }
+  g.r_sw = g.r_sh = g.r_sn = 0;
+  g.b = w_t; g.n_out = s.in_c;
+  g.kh = s.k_h; g.kw = s.k_w; g.pad_h = s.k_h - 1 - s.pad; g.pad_w = s.k_w - 1 - s.pad;
+  g.scale = nullptr; g.bias = nullptr; g.residual = nullptr; g.relu = 0;
+  return dispatch_gemm(g, stream);
+}
+
+int conv_filter_for_dgrad(const float* w, float* w_t, const mmt_conv_shape& s, cudaStream_t stream) {
+  const int taps = s.k_h * s.k_w;
+  dim3 grid((unsigned)ceil_div(s.in_c, 32), (unsigned)ceil_div(s.out_c, 32), (unsigned)taps);
+  filter_dgrad_kernel<<<grid, 256, 0, stream>>>(w, w_t, s.out_c, taps, s.in_c);
+  return check_launch("filter_dgrad");
+}
+
+int conv_wgrad_tc(const float* x, const float* dy, float* dw, float* dbias, const mmt_conv_shape& s,
+                  void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  (void)workspace; (void)workspace_bytes; (void)dbias;
+  const bool pointwise = s.k_h == 1 && s.k_w == 1 && s.pad == 0;
+  View4 vdy, vx;
+  if (pointwise && s.stride == 1) {
+    const long long P = (long long)s.batch * s.in_h * s.in_w;
+    vdy = flat_pixels(dy, P, s.out_c);
+    vx = flat_pixels(x, P, s.in_c);
+  } else if (pointwise && s.stride == 2) {
+    vdy = dense_nhwc(dy, s.batch, s.out_h, s.out_w, s.out_c);
+    vx = View4{x, s.in_c, s.out_w, s.out_h, s.batch, 2ll * s.in_c, 2ll * s.in_w * s.in_c,
+               (long long)s.in_h * s.in_w * s.in_c};
+  } else {
+    vdy = dense_nhwc(dy, s.batch, s.out_h, s.out_w, s.out_c);
+    vx = dense_nhwc(x, s.batch, s.in_h, s.in_w, s.in_c);
+  }
+  const int BN = s.in_c % 256 == 0 ? 256 : (s.in_c % 128 == 0 ? 128 : 64);
+  int TW, TH;
+  pick_patch(vdy.w, vdy.h, 32, TW, TH);
+  CUtensorMap tmDY, tmX, tmDW;
+  if (int rc = make_map(&tmDY, vdy, 32, TW, TH, "wgrad dy")) return rc;
+  if (int rc = make_map(&tmX, vx, 32, TW, TH, "wgrad x")) return rc;
+  const long long Ktot = (long long)s.k_h * s.k_w * s.in_c;
+  if (int rc = make_map_2d(&tmDW, dw, Ktot, s.out_c, Ktot, 32, 128, "wgrad dw")) return rc;
+  MMT_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)s.out_c * Ktot, stream));
+  WgradParams p;
+  p.tiles_w = (int)ceil_div<long long>(vdy.w, TW);
+  p.tiles_h = (int)ceil_div<long long>(vdy.h, TH);
+  p.tiles_b = (int)vdy.n;
+  p.TW = TW; p.TH = TH;
+  p.kh = s.k_h; p.kw = s.k_w; p.pad_h = s.pad; p.pad_w = s.pad;
+  p.co_tiles = s.out_c / 128;
+  p.ci_tiles = s.in_c / BN;
+  p.cin = s.in_c;
+  const long long ptiles = (long long)p.tiles_w * p.tiles_h * p.tiles_b;
+  if (ptiles > 0x7fffffffll) return fail(MMT_ERR_UNSUPPORTED, "wgrad: too many pixel tiles");
+  p.pixel_tiles = (int)ptiles;
+  const int base_items = p.co_tiles * s.k_h * s.k_w * p.ci_tiles;
+  int splits = std::max(1, (2 * kNumSMs) / base_items);
+  splits = (int)std::min<long long>(splits, std::max<long long>(1, ptiles / 16));  // >= 16 K-steps per item
+  p.tiles_per_split = (int)ceil_div<long long>(ptiles, splits);
+  p.splits = (int)ceil_div<long long>(ptiles, p.tiles_per_split);
+  p.total_items = base_items * p.splits;
+  if (BN == 256) return launch_wgrad<256>(tmDY, tmX, tmDW, p, stream);
+  if (BN == 128) return launch_wgrad<128>(tmDY, tmX, tmDW, p, stream);
+  return launch_wgrad<64>(tmDY, tmX, tmDW, p, stream);
+}
+
+}  // namespace mmt

@@ -84,6 +84,25 @@ int mmt_roi_align_backward_f32(const float* grad_output, mmt_strides4 grad_outpu
                                mmt_strides4 grad_input_strides, int batch, int channels, int height,
                                int width, void* stream);
 
+/* Fused FPN pooler — replaces the per-level loop of modeling/poolers.py:91-121 (`Pooler.forward`:
+ * per level one `nonzero`, one ROIAlign launch and one index_put scatter).  All levels in ONE
+ * launch: ROI n samples level roi_levels[n] (int32, DEVICE; computed by the caller with the
+ * reference's LevelMapper formula, poolers.py:31-42) and writes row n of the dense NHWC output
+ * [n_rois, pooled_h, pooled_w, channels].  Level feature maps are dense NHWC [batch, h_l, w_l,
+ * channels]; the pointer / size / scale tables are HOST arrays of n_levels (<= 8) entries.
+ * Backward ACCUMULATES into the per-level gradient maps (caller zero-fills them). */
+int mmt_roi_align_fpn_forward_f32(const float* const* level_feats_host, const int* level_h_host,
+                                  const int* level_w_host, const float* level_scale_host,
+                                  int n_levels, int batch, int channels, const float* rois,
+                                  int n_rois, int pooled_h, int pooled_w, int sampling_ratio,
+                                  const int* roi_levels, float* output, void* stream);
+int mmt_roi_align_fpn_backward_f32(const float* grad_output, const float* rois,
+                                   const int* roi_levels, int n_rois, int pooled_h, int pooled_w,
+                                   int sampling_ratio, float* const* level_grads_host,
+                                   const int* level_h_host, const int* level_w_host,
+                                   const float* level_scale_host, int n_levels, int batch,
+                                   int channels, void* stream);
+
 /* ROIPool — replaces csrc/ROIPool.h:10-45 / csrc/cuda/ROIPool_cuda.cu:17-108 (kept for ABI
  * completeness; the FPN configuration on the hot path only uses ROIAlign). NCHW contiguous. */
 int mmt_roi_pool_forward_f32(const float* input, int batch, int channels, int height, int width,

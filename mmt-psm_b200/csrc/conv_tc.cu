@@ -52,7 +52,8 @@ struct Cfg {
 
 struct FpropParams {
   int tiles_w, tiles_h, tiles_b;  // spatial tiles per image and images
-  int n_tiles;                    // out channels / BN
+  int n_tiles;                    // ceil(out channels / BN)
+  int n_out;                      // out channels (epilogue guard; the TMA store clips)
   int TW, TH;
   int kh, kw, cblocks;  // cblocks = channels of A / 32
   int pad_h, pad_w;
@@ -237,11 +238,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int e = 0; e < 4; ++e) {
             float x = __uint_as_float(v[g * 4 + e]);
             const int c = c0 + g * 4 + e;
-            if (p.scale) x *= __ldg(p.scale + c);
-            if (p.bias) x += __ldg(p.bias + c);
+            if (c < p.n_out) {
+              if (p.scale) x *= __ldg(p.scale + c);
+              if (p.bias) x += __ldg(p.bias + c);
+            }
             o[e] = x;
           }
-          if (res_row != nullptr && pix_ok) {
+          if (res_row != nullptr && pix_ok && c0 + g * 4 < p.n_out) {
             const float4 rr = __ldg(reinterpret_cast<const float4*>(res_row + c0 + g * 4));
             o[0] += rr.x; o[1] += rr.y; o[2] += rr.z; o[3] += rr.w;
           }
@@ -552,7 +555,8 @@ int launch_gemm(const GemmProblem& g, cudaStream_t stream) {
   p.tiles_w = (int)mmt::ceil_div<long long>(g.y.w, TW);
   p.tiles_h = (int)mmt::ceil_div<long long>(g.y.h, TH);
   p.tiles_b = (int)g.y.n;
-  p.n_tiles = g.n_out / BN;
+  p.n_tiles = (g.n_out + BN - 1) / BN;
+  p.n_out = g.n_out;
   p.TW = TW; p.TH = TH;
   p.kh = g.kh; p.kw = g.kw; p.cblocks = (int)(g.a.c / 32);
   p.pad_h = g.pad_h; p.pad_w = g.pad_w;
@@ -573,10 +577,11 @@ int launch_gemm(const GemmProblem& g, cudaStream_t stream) {
 }
 
 int dispatch_gemm(const GemmProblem& g, cudaStream_t stream) {
+  // out channels beyond n_out are zero-filled on load (weights) and clipped on store by TMA
   if (g.n_out % 256 == 0) return launch_gemm<256>(g, stream);
   if (g.n_out % 128 == 0) return launch_gemm<128>(g, stream);
-  if (g.n_out % 64 == 0) return launch_gemm<64>(g, stream);
-  return mmt::fail(MMT_ERR_UNSUPPORTED, "conv_tc: out channels %d not a multiple of 64", g.n_out);
+  if (g.n_out <= 32) return launch_gemm<32>(g, stream);
+  return launch_gemm<64>(g, stream);
 }
 
 View4 dense_nhwc(const float* base, long long n, long long h, long long w, long long c) {
@@ -605,17 +610,17 @@ int launch_wgrad(const CUtensorMap& tmDY, const CUtensorMap& tmX, const CUtensor
 namespace mmt {
 
 bool conv_tc_supported_fprop(const mmt_conv_shape& s) {
-  if (s.in_c % 32 || s.out_c % 64) return false;
+  if (s.in_c % 32 || s.out_c % 4) return false;
   if (s.stride == 1) return s.out_h == s.in_h + 2 * s.pad - s.k_h + 1 && s.out_w == s.in_w + 2 * s.pad - s.k_w + 1;
   return s.stride == 2 && s.k_h == 1 && s.k_w == 1 && s.pad == 0;
 }
 bool conv_tc_supported_dgrad(const mmt_conv_shape& s) {
-  if (s.out_c % 32 || s.in_c % 64) return false;
+  if (s.out_c % 32 || s.in_c % 4) return false;
   if (s.stride == 1) return s.k_h - 1 - s.pad >= 0 && s.k_w - 1 - s.pad >= 0;
   return s.stride == 2 && s.k_h == 1 && s.k_w == 1 && s.pad == 0;
 }
 bool conv_tc_supported_wgrad(const mmt_conv_shape& s) {
-  if (s.out_c % 128 || s.in_c % 64) return false;
+  if (s.out_c % 4 || s.in_c % 4) return false;  // partial tiles: TMA zero-fills loads, clips the reduce-add
   if (s.stride == 1) return true;
   return s.stride == 2 && s.k_h == 1 && s.k_w == 1 && s.pad == 0;
 }
@@ -694,7 +699,7 @@ int conv_wgrad_tc(const float* x, const float* dy, float* dw, float* dbias, cons
     vdy = dense_nhwc(dy, s.batch, s.out_h, s.out_w, s.out_c);
     vx = dense_nhwc(x, s.batch, s.in_h, s.in_w, s.in_c);
   }
-  const int BN = s.in_c % 256 == 0 ? 256 : (s.in_c % 128 == 0 ? 128 : 64);
+  const int BN = s.in_c % 256 == 0 ? 256 : (s.in_c % 128 == 0 ? 128 : 64);  // ci tiles may be partial
   int TW, TH;
   pick_patch(vdy.w, vdy.h, 32, TW, TH);
   CUtensorMap tmDY, tmX, tmDW;
@@ -709,8 +714,8 @@ int conv_wgrad_tc(const float* x, const float* dy, float* dw, float* dbias, cons
   p.tiles_b = (int)vdy.n;
   p.TW = TW; p.TH = TH;
   p.kh = s.k_h; p.kw = s.k_w; p.pad_h = s.pad; p.pad_w = s.pad;
-  p.co_tiles = s.out_c / 128;
-  p.ci_tiles = s.in_c / BN;
+  p.co_tiles = (s.out_c + 127) / 128;
+  p.ci_tiles = (s.in_c + BN - 1) / BN;
   p.cin = s.in_c;
   const long long ptiles = (long long)p.tiles_w * p.tiles_h * p.tiles_b;
   if (ptiles > 0x7fffffffll) return fail(MMT_ERR_UNSUPPORTED, "wgrad: too many pixel tiles");

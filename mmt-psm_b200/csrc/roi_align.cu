@@ -232,6 +232,93 @@ __global__ void __launch_bounds__(256) roi_align_bwd_kernel(
   }
 }
 
+// ---------------------------------------------------------------- fused FPN pooler (all levels)
+// Replaces the per-level loop of maskrcnn_benchmark/modeling/poolers.py:91-121 (4 nonzero syncs, 4
+// ROIAlign launches and 4 index_put scatters per call): each ROI carries its level id (computed by
+// the caller with the reference's LevelMapper formula, poolers.py:31-42) and samples that level's
+// NHWC map; the result lands directly at row n of the [n_rois, ph, pw, C] output.
+constexpr int kMaxLevels = 8;
+struct LevelTab {
+  const float* feat[kMaxLevels];
+  float* grad[kMaxLevels];
+  int h[kMaxLevels], w[kMaxLevels];
+  float scale[kMaxLevels];
+};
+
+__global__ void __launch_bounds__(256) roi_align_fpn_fwd_kernel(
+    LevelTab tab, int channels, const float* __restrict__ rois, const int* __restrict__ levels,
+    int pooled_h, int pooled_w, int sampling_ratio, float* __restrict__ out, long long total) {
+  const int cvecs = channels >> 2;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    int n, cv, ph, pw;
+    decompose<true>(idx, cvecs, pooled_h, pooled_w, n, cv, ph, pw);
+    const int l = levels[n];
+    const int height = tab.h[l], width = tab.w[l];
+    const RoiGeom g = roi_geometry(rois + (long long)n * 5, tab.scale[l], pooled_h, pooled_w, sampling_ratio);
+    const long long sw = channels, sh = (long long)width * channels, sn = (long long)height * sh;
+    const float* base = tab.feat[l] + g.batch_ind * sn + cv * 4;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    for (int iy = 0; iy < g.grid_h; ++iy) {
+      const float y = sample_coord(g.start_h, ph, g.bin_h, iy, g.grid_h);
+      for (int ix = 0; ix < g.grid_w; ++ix) {
+        const float x = sample_coord(g.start_w, pw, g.bin_w, ix, g.grid_w);
+        const Taps t = bilinear_taps(y, x, height, width);
+        if (!t.valid) continue;
+        const float4 a = __ldg(reinterpret_cast<const float4*>(base + t.y_low * sh + t.x_low * sw));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(base + t.y_low * sh + t.x_high * sw));
+        const float4 c = __ldg(reinterpret_cast<const float4*>(base + t.y_high * sh + t.x_low * sw));
+        const float4 d = __ldg(reinterpret_cast<const float4*>(base + t.y_high * sh + t.x_high * sw));
+        a0 = __fadd_rn(a0, blend(t, a.x, b.x, c.x, d.x));
+        a1 = __fadd_rn(a1, blend(t, a.y, b.y, c.y, d.y));
+        a2 = __fadd_rn(a2, blend(t, a.z, b.z, c.z, d.z));
+        a3 = __fadd_rn(a3, blend(t, a.w, b.w, c.w, d.w));
+      }
+    }
+    float4 r;
+    r.x = __fdiv_rn(a0, g.count); r.y = __fdiv_rn(a1, g.count);
+    r.z = __fdiv_rn(a2, g.count); r.w = __fdiv_rn(a3, g.count);
+    reinterpret_cast<float4*>(out)[idx] = r;  // idx enumerates [n][ph][pw][cvec] == NHWC order
+  }
+}
+
+__global__ void __launch_bounds__(256) roi_align_fpn_bwd_kernel(
+    LevelTab tab, int channels, const float* __restrict__ gout, const float* __restrict__ rois,
+    const int* __restrict__ levels, int pooled_h, int pooled_w, int sampling_ratio, long long total) {
+  const int cvecs = channels >> 2;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    int n, cv, ph, pw;
+    decompose<true>(idx, cvecs, pooled_h, pooled_w, n, cv, ph, pw);
+    const int l = levels[n];
+    const int height = tab.h[l], width = tab.w[l];
+    const RoiGeom g = roi_geometry(rois + (long long)n * 5, tab.scale[l], pooled_h, pooled_w, sampling_ratio);
+    const long long sw = channels, sh = (long long)width * channels, sn = (long long)height * sh;
+    float* base = tab.grad[l] + g.batch_ind * sn + cv * 4;
+    const float4 go = __ldg(reinterpret_cast<const float4*>(gout) + idx);
+    for (int iy = 0; iy < g.grid_h; ++iy) {
+      const float y = sample_coord(g.start_h, ph, g.bin_h, iy, g.grid_h);
+      for (int ix = 0; ix < g.grid_w; ++ix) {
+        const float x = sample_coord(g.start_w, pw, g.bin_w, ix, g.grid_w);
+        const Taps t = bilinear_taps(y, x, height, width);
+        if (!t.valid) continue;
+        const float ws[4] = {t.w1, t.w2, t.w3, t.w4};
+        float* ps[4] = {base + t.y_low * sh + t.x_low * sw, base + t.y_low * sh + t.x_high * sw,
+                        base + t.y_high * sh + t.x_low * sw, base + t.y_high * sh + t.x_high * sw};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float4 v;
+          v.x = __fdiv_rn(__fmul_rn(go.x, ws[k]), g.count);
+          v.y = __fdiv_rn(__fmul_rn(go.y, ws[k]), g.count);
+          v.z = __fdiv_rn(__fmul_rn(go.z, ws[k]), g.count);
+          v.w = __fdiv_rn(__fmul_rn(go.w, ws[k]), g.count);
+          mmt::red_add_v4(ps[k], v);
+        }
+      }
+    }
+  }
+}
+
 inline int grid_for(long long total, int block) {
   long long blocks = (total + block - 1) / block;
   const long long cap = (long long)mmt::kNumSMs * 8 * 4;  // 8 CTAs of 256 thr/SM resident, 4 waves
@@ -378,4 +465,61 @@ extern "C" int mmt_roi_pool_backward_f32(const float* grad_output, const int* ar
                                                                 height, width, pooled_h, pooled_w,
                                                                 grad_input, total);
   return mmt::check_launch("roi_pool_backward");
+}
+
+static int fill_level_tab(LevelTab& tab, const float* const* feats, float* const* grads, const int* hs,
+                          const int* ws, const float* scales, int n_levels, const char* who) {
+  MMT_REQUIRE(n_levels >= 1 && n_levels <= kMaxLevels, "%s: n_levels must be in [1,%d]", who, kMaxLevels);
+  MMT_REQUIRE(hs && ws && scales, "%s: null level table", who);
+  for (int l = 0; l < kMaxLevels; ++l) {
+    tab.feat[l] = nullptr; tab.grad[l] = nullptr; tab.h[l] = tab.w[l] = 1; tab.scale[l] = 1.f;
+  }
+  for (int l = 0; l < n_levels; ++l) {
+    const void* p = feats ? (const void*)feats[l] : (const void*)grads[l];
+    MMT_REQUIRE(p != nullptr && ((uintptr_t)p % 16) == 0, "%s: level %d pointer null or not 16-byte aligned", who, l);
+    MMT_REQUIRE(hs[l] > 0 && ws[l] > 0, "%s: bad level size", who);
+    if (feats) tab.feat[l] = feats[l];
+    if (grads) tab.grad[l] = grads[l];
+    tab.h[l] = hs[l]; tab.w[l] = ws[l]; tab.scale[l] = scales[l];
+  }
+  return MMT_OK;
+}
+
+extern "C" int mmt_roi_align_fpn_forward_f32(const float* const* level_feats_host, const int* level_h_host,
+                                             const int* level_w_host, const float* level_scale_host,
+                                             int n_levels, int batch, int channels, const float* rois,
+                                             int n_rois, int pooled_h, int pooled_w, int sampling_ratio,
+                                             const int* roi_levels, float* output, void* stream_) {
+  MMT_REQUIRE(n_rois >= 0 && channels > 0 && channels % 4 == 0 && pooled_h > 0 && pooled_w > 0 && batch >= 0,
+              "roi_align_fpn_forward: bad sizes (channels must be a multiple of 4)");
+  if (n_rois == 0) return MMT_OK;
+  MMT_REQUIRE(level_feats_host && rois && roi_levels && output, "roi_align_fpn_forward: null pointer");
+  MMT_REQUIRE((uintptr_t)output % 16 == 0, "roi_align_fpn_forward: output must be 16-byte aligned");
+  LevelTab tab;
+  if (int rc = fill_level_tab(tab, level_feats_host, nullptr, level_h_host, level_w_host, level_scale_host,
+                              n_levels, "roi_align_fpn_forward")) return rc;
+  const long long total = (long long)n_rois * pooled_h * pooled_w * (channels / 4);
+  roi_align_fpn_fwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream_>>>(
+      tab, channels, rois, roi_levels, pooled_h, pooled_w, sampling_ratio, output, total);
+  return mmt::check_launch("roi_align_fpn_forward");
+}
+
+extern "C" int mmt_roi_align_fpn_backward_f32(const float* grad_output, const float* rois,
+                                              const int* roi_levels, int n_rois, int pooled_h, int pooled_w,
+                                              int sampling_ratio, float* const* level_grads_host,
+                                              const int* level_h_host, const int* level_w_host,
+                                              const float* level_scale_host, int n_levels, int batch,
+                                              int channels, void* stream_) {
+  MMT_REQUIRE(n_rois >= 0 && channels > 0 && channels % 4 == 0 && pooled_h > 0 && pooled_w > 0 && batch >= 0,
+              "roi_align_fpn_backward: bad sizes (channels must be a multiple of 4)");
+  if (n_rois == 0) return MMT_OK;
+  MMT_REQUIRE(grad_output && rois && roi_levels && level_grads_host, "roi_align_fpn_backward: null pointer");
+  MMT_REQUIRE((uintptr_t)grad_output % 16 == 0, "roi_align_fpn_backward: grad_output must be 16-byte aligned");
+  LevelTab tab;
+  if (int rc = fill_level_tab(tab, nullptr, level_grads_host, level_h_host, level_w_host, level_scale_host,
+                              n_levels, "roi_align_fpn_backward")) return rc;
+  const long long total = (long long)n_rois * pooled_h * pooled_w * (channels / 4);
+  roi_align_fpn_bwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream_>>>(
+      tab, channels, grad_output, rois, roi_levels, pooled_h, pooled_w, sampling_ratio, total);
+  return mmt::check_launch("roi_align_fpn_backward");
 }

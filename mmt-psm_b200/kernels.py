@@ -1,0 +1,445 @@
+"""Tensor-level entry points over the C ABI (raw pointers in, caller-owned outputs).
+
+Every function takes CUDA fp32 tensors, allocates outputs / workspace through torch's caching
+allocator, launches on torch's CURRENT stream and never synchronises unless the reference API it
+mirrors forces it (only `nms`, which must return a tensor whose length is data dependent).
+There is no CPU path: non-CUDA tensors raise.
+"""
+import ctypes
+from ctypes import c_float, c_int, c_void_p
+
+import torch
+
+from . import lib as _l
+from .lib import ConvShape, Strides4, check
+
+CONV_AUTO, CONV_TCGEN05, CONV_SIMT = 0, 1, 2
+EPI_RELU = 1
+
+
+def _need_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("mmtpsm_b200 ops run on CUDA tensors only (no CPU fallback); got %s" % t.device)
+
+
+def _p(t):
+    return c_void_p(t.data_ptr()) if t is not None else c_void_p(0)
+
+
+def _stream():
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _f32c(t):
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _strides(t, order):
+    """Element strides of a 4-D tensor as (n, c, h, w) given which dims those are."""
+    st = t.stride()
+    return Strides4(st[order[0]], st[order[1]], st[order[2]], st[order[3]])
+
+
+# --------------------------------------------------------------------------------------- NMS
+def nms_segmented(boxes, scores, seg_offsets, iou_threshold):
+    """Independent NMS problems laid out back to back, one launch chain, no host sync.
+
+    boxes [T,4] xyxy, scores [T]; seg_offsets: python list of S+1 ints.
+    Returns (keep [T] int64 — per segment the kept indices relative to the segment start, ascending,
+    stored from seg_offsets[s]; counts [S] int32), both on the device.
+    """
+    _need_cuda(boxes, scores)
+    L = _l.lib()
+    boxes = _f32c(boxes)
+    scores = _f32c(scores)
+    S = len(seg_offsets) - 1
+    total = int(seg_offsets[-1])
+    keep = torch.empty(max(total, 1), dtype=torch.int64, device=boxes.device)
+    counts = torch.zeros(max(S, 1), dtype=torch.int32, device=boxes.device)
+    if S == 0 or total == 0:
+        return keep[:total], counts[:S]
+    max_n = max(seg_offsets[i + 1] - seg_offsets[i] for i in range(S))
+    ws_bytes = L.mmt_nms_workspace_bytes(total, S, max_n)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=boxes.device)
+    offs = (c_int * (S + 1))(*[int(o) for o in seg_offsets])
+    check(L.mmt_nms_segmented_f32(_p(boxes), _p(scores), offs, S, float(iou_threshold), _p(keep),
+                                  _p(counts), _p(ws), ws_bytes, _stream()), "nms")
+    return keep[:total], counts[:S]
+
+
+def nms(dets, scores, iou_threshold):
+    """`_C.nms(dets, scores, thr)` (reference csrc/nms.h:10-28): int64 kept indices, ascending.
+    Empty input returns an empty int64 CPU tensor exactly like the reference (nms.h:17-18)."""
+    if dets.numel() == 0:
+        return torch.empty(0, dtype=torch.int64, device="cpu")
+    keep, counts = nms_segmented(dets, scores, [0, dets.shape[0]], iou_threshold)
+    return keep[: int(counts[0].item())]
+
+
+# ---------------------------------------------------------------------------------- ROIAlign
+def roi_align_forward(input, rois, spatial_scale, pooled_h, pooled_w, sampling_ratio):
+    """`_C.roi_align_forward` (reference csrc/ROIAlign.h:11-26): NCHW in -> [K,C,ph,pw] out.
+    A channels_last input is consumed as is (coalesced NHWC path) and yields a channels_last output."""
+    _need_cuda(input, rois)
+    L = _l.lib()
+    if input.dtype != torch.float32:
+        input = input.float()
+    nhwc = input.is_contiguous(memory_format=torch.channels_last) and not input.is_contiguous()
+    if not nhwc:
+        input = input.contiguous()
+    rois = _f32c(rois)
+    B, C, H, W = input.shape
+    K = rois.shape[0]
+    out = torch.empty((K, C, pooled_h, pooled_w), dtype=torch.float32, device=input.device,
+                      memory_format=torch.channels_last if nhwc else torch.contiguous_format)
+    if K == 0:
+        return out
+    check(L.mmt_roi_align_forward_f32(_p(input), _strides(input, (0, 1, 2, 3)), B, C, H, W, _p(rois), K,
+                                      float(spatial_scale), pooled_h, pooled_w, sampling_ratio, _p(out),
+                                      _strides(out, (0, 1, 2, 3)), _stream()), "roi_align_forward")
+    return out
+
+
+def roi_align_backward(grad, rois, spatial_scale, pooled_h, pooled_w, batch, channels, height, width,
+                       sampling_ratio):
+    """`_C.roi_align_backward` (reference csrc/ROIAlign.h:28-45)."""
+    _need_cuda(grad, rois)
+    L = _l.lib()
+    nhwc = grad.is_contiguous(memory_format=torch.channels_last) and not grad.is_contiguous()
+    grad = grad.float() if grad.dtype != torch.float32 else grad
+    if not nhwc:
+        grad = grad.contiguous()
+    rois = _f32c(rois)
+    gin = torch.zeros((batch, channels, height, width), dtype=torch.float32, device=grad.device,
+                      memory_format=torch.channels_last if nhwc else torch.contiguous_format)
+    K = rois.shape[0]
+    if K == 0:
+        return gin
+    check(L.mmt_roi_align_backward_f32(_p(grad), _strides(grad, (0, 1, 2, 3)), _p(rois), K,
+                                       float(spatial_scale), pooled_h, pooled_w, sampling_ratio, _p(gin),
+                                       _strides(gin, (0, 1, 2, 3)), batch, channels, height, width,
+                                       _stream()), "roi_align_backward")
+    return gin
+
+
+def _level_tables(feats, scales):
+    n = len(feats)
+    ptrs = (c_void_p * n)(*[f.data_ptr() for f in feats])
+    hs = (c_int * n)(*[f.shape[1] for f in feats])
+    ws = (c_int * n)(*[f.shape[2] for f in feats])
+    sc = (c_float * n)(*[float(s) for s in scales])
+    return ptrs, hs, ws, sc
+
+
+def roi_align_fpn_forward(feats_nhwc, scales, rois, levels, pooled, sampling_ratio):
+    """Fused FPN pooler: feats_nhwc list of dense [B,h,w,C]; rois [K,5]; levels [K] int32.
+    Returns dense NHWC [K, pooled, pooled, C]."""
+    _need_cuda(rois, levels, *feats_nhwc)
+    L = _l.lib()
+    for f in feats_nhwc:
+        assert f.is_contiguous() and f.dtype == torch.float32
+    rois = _f32c(rois)
+    levels = levels.to(torch.int32).contiguous()
+    B, _, _, C = feats_nhwc[0].shape
+    K = rois.shape[0]
+    out = torch.empty((K, pooled, pooled, C), dtype=torch.float32, device=rois.device)
+    if K == 0:
+        return out
+    ptrs, hs, ws, sc = _level_tables(feats_nhwc, scales)
+    check(L.mmt_roi_align_fpn_forward_f32(ptrs, hs, ws, sc, len(feats_nhwc), B, C, _p(rois), K, pooled,
+                                          pooled, sampling_ratio, _p(levels), _p(out), _stream()),
+          "roi_align_fpn_forward")
+    return out
+
+
+def roi_align_fpn_backward(grad_out, scales, rois, levels, pooled, sampling_ratio, grads_nhwc):
+    """Accumulates into the (caller zero-filled or live) per-level gradient maps `grads_nhwc`."""
+    _need_cuda(grad_out, rois, levels, *grads_nhwc)
+    L = _l.lib()
+    grad_out = _f32c(grad_out)
+    rois = _f32c(rois)
+    levels = levels.to(torch.int32).contiguous()
+    K = rois.shape[0]
+    if K == 0:
+        return
+    B, _, _, C = grads_nhwc[0].shape
+    ptrs, hs, ws, sc = _level_tables(grads_nhwc, scales)
+    check(L.mmt_roi_align_fpn_backward_f32(_p(grad_out), _p(rois), _p(levels), K, pooled, pooled,
+                                           sampling_ratio, ptrs, hs, ws, sc, len(grads_nhwc), B, C,
+                                           _stream()), "roi_align_fpn_backward")
+
+
+def roi_pool_forward(input, rois, spatial_scale, pooled_h, pooled_w):
+    """`_C.roi_pool_forward` (reference csrc/ROIPool.h:10-24): returns (output, argmax int32)."""
+    _need_cuda(input, rois)
+    L = _l.lib()
+    input = _f32c(input)
+    rois = _f32c(rois)
+    B, C, H, W = input.shape
+    K = rois.shape[0]
+    out = torch.empty((K, C, pooled_h, pooled_w), dtype=torch.float32, device=input.device)
+    arg = torch.empty((K, C, pooled_h, pooled_w), dtype=torch.int32, device=input.device)
+    check(L.mmt_roi_pool_forward_f32(_p(input), B, C, H, W, _p(rois), K, float(spatial_scale), pooled_h,
+                                     pooled_w, _p(out), _p(arg), _stream()), "roi_pool_forward")
+    return out, arg
+
+
+def roi_pool_backward(grad, input, rois, argmax, spatial_scale, pooled_h, pooled_w, batch, channels,
+                      height, width):
+    """`_C.roi_pool_backward` (reference csrc/ROIPool.h:26-45)."""
+    _need_cuda(grad, rois, argmax)
+    L = _l.lib()
+    grad = _f32c(grad)
+    rois = _f32c(rois)
+    gin = torch.zeros((batch, channels, height, width), dtype=torch.float32, device=grad.device)
+    check(L.mmt_roi_pool_backward_f32(_p(grad), _p(argmax.contiguous()), _p(rois), rois.shape[0], pooled_h,
+                                      pooled_w, _p(gin), batch, channels, height, width, _stream()),
+          "roi_pool_backward")
+    return gin
+
+
+# ------------------------------------------------------------------------------- focal loss
+def sigmoid_focal_loss_forward(logits, targets, num_classes, gamma, alpha):
+    _need_cuda(logits, targets)
+    L = _l.lib()
+    logits = _f32c(logits)
+    targets = targets.to(torch.int32).contiguous()
+    out = torch.empty_like(logits)
+    check(L.mmt_sigmoid_focal_loss_forward_f32(_p(logits), _p(targets), logits.shape[0], num_classes,
+                                               float(gamma), float(alpha), _p(out), _stream()), "focal_fwd")
+    return out
+
+
+def sigmoid_focal_loss_backward(logits, targets, d_losses, num_classes, gamma, alpha):
+    _need_cuda(logits, targets, d_losses)
+    L = _l.lib()
+    logits = _f32c(logits)
+    d_losses = _f32c(d_losses)
+    targets = targets.to(torch.int32).contiguous()
+    out = torch.empty_like(logits)
+    check(L.mmt_sigmoid_focal_loss_backward_f32(_p(logits), _p(targets), _p(d_losses), logits.shape[0],
+                                                num_classes, float(gamma), float(alpha), _p(out), _stream()),
+          "focal_bwd")
+    return out
+
+
+# ------------------------------------------------------------------------------------- PSM
+def psm_loss(student_logits, teacher_logits, labels, temperature=0.5, sharpen=True, hard_negative=True,
+             neg_weight=1.5, neg_order=None):
+    """student [n,C]; teacher [V,n,C]; labels [n] int64. Returns (loss[1], grad_student[n,C], selected[n] int32)."""
+    _need_cuda(student_logits, teacher_logits, labels)
+    L = _l.lib()
+    s = _f32c(student_logits)
+    t = _f32c(teacher_logits)
+    labels = labels.to(torch.int64).contiguous()
+    V, n, C = t.shape
+    loss = torch.empty(1, dtype=torch.float32, device=s.device)
+    grad = torch.empty_like(s)
+    sel = torch.zeros(max(n, 1), dtype=torch.int32, device=s.device)
+    wsb = L.mmt_psm_workspace_bytes(n)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=s.device)
+    if neg_order is not None:
+        neg_order = neg_order.to(torch.int32).contiguous()
+    check(L.mmt_psm_loss_f32(_p(s), _p(t), V, _p(labels), n, C, float(temperature), int(bool(sharpen)),
+                             int(bool(hard_negative)), float(neg_weight), _p(neg_order), _p(loss), _p(grad),
+                             _p(sel), _p(ws), wsb, _stream()), "psm_loss")
+    return loss, grad, sel[:n]
+
+
+# ------------------------------------------------------------------------------------- MGD
+def mgd_masks(integral_mask, level_sizes):
+    """integral_mask [B,H,W] float; level_sizes list of (h,w). Returns (list of uint8 [B,h,w], sums [n_levels])."""
+    _need_cuda(integral_mask)
+    L = _l.lib()
+    m = _f32c(integral_mask)
+    B, H, W = m.shape
+    n = len(level_sizes)
+    total = sum(B * h * w for h, w in level_sizes)
+    masks = torch.empty(total, dtype=torch.uint8, device=m.device)
+    sums = torch.empty(n, dtype=torch.float32, device=m.device)
+    hs = (c_int * n)(*[h for h, _ in level_sizes])
+    ws = (c_int * n)(*[w for _, w in level_sizes])
+    check(L.mmt_mgd_masks_f32(_p(m), B, H, W, hs, ws, n, _p(masks), _p(sums), _stream()), "mgd_masks")
+    out, off = [], 0
+    for h, w in level_sizes:
+        out.append(masks[off: off + B * h * w].view(B, h, w))
+        off += B * h * w
+    return out, sums
+
+
+def mgd_level(student_nhwc, teacher_views_nhwc, flip_mask, level_mask, level_mask_sum, term_weight, partial,
+              want_grad):
+    """One pyramid level. student / teachers dense NHWC [B,h,w,C]; `partial` [n_views] accumulated."""
+    _need_cuda(student_nhwc, level_mask, level_mask_sum, partial, *teacher_views_nhwc)
+    L = _l.lib()
+    B, H, W, C = student_nhwc.shape
+    V = len(teacher_views_nhwc)
+    for t in teacher_views_nhwc:
+        assert t.is_contiguous() and t.shape == student_nhwc.shape and t.dtype == torch.float32
+    assert student_nhwc.is_contiguous() and student_nhwc.dtype == torch.float32
+    st = Strides4(H * W * C, 1, W * C, C)
+    ptrs = (c_void_p * V)(*[t.data_ptr() for t in teacher_views_nhwc])
+    grad = torch.empty_like(student_nhwc) if want_grad else None
+    check(L.mmt_mgd_level_f32(_p(student_nhwc), st, ptrs, st, V, int(flip_mask), _p(level_mask),
+                              _p(level_mask_sum), B, C, H, W, float(term_weight), _p(partial), _p(grad), st,
+                              _stream()), "mgd_level")
+    return grad
+
+
+def mgd_finalize(partials, mask_sums, n_levels, n_views, channels):
+    _need_cuda(partials, mask_sums)
+    L = _l.lib()
+    loss = torch.empty(1, dtype=torch.float32, device=partials.device)
+    check(L.mmt_mgd_finalize_f32(_p(partials), _p(mask_sums), n_levels, n_views, channels, _p(loss), _stream()),
+          "mgd_finalize")
+    return loss
+
+
+# ------------------------------------------------------------------------------- EMA / SGD
+def ema_(teacher_flat, student_flat, alpha):
+    _need_cuda(teacher_flat, student_flat)
+    L = _l.lib()
+    assert teacher_flat.is_contiguous() and student_flat.is_contiguous()
+    assert teacher_flat.dtype == torch.float32 and student_flat.dtype == torch.float32
+    assert teacher_flat.numel() == student_flat.numel()
+    check(L.mmt_ema_f32(_p(teacher_flat), _p(student_flat), teacher_flat.numel(), float(alpha), _stream()), "ema")
+
+
+def sgd_ema_(student_flat, teacher_flat, grad_flat, momentum_flat, segments_dev, n_segments, momentum, alpha,
+             first_step, grad_scale=1.0):
+    _need_cuda(student_flat, grad_flat, momentum_flat, segments_dev)
+    L = _l.lib()
+    check(L.mmt_sgd_ema_f32(_p(student_flat), _p(teacher_flat), _p(grad_flat), _p(momentum_flat),
+                            student_flat.numel(), _p(segments_dev), n_segments, float(momentum), float(alpha),
+                            int(bool(first_step)), float(grad_scale), _stream()), "sgd_ema")
+
+
+def make_segments(entries, device):
+    """entries: list of (begin, end, lr, weight_decay, trainable). Returns a device uint8 tensor."""
+    arr = (_l.ParamSegment * len(entries))()
+    for i, (b, e, lr, wd, tr) in enumerate(entries):
+        arr[i].begin, arr[i].end, arr[i].lr, arr[i].weight_decay, arr[i].trainable = b, e, lr, wd, int(tr)
+    raw = bytes(arr)
+    t = torch.frombuffer(bytearray(raw), dtype=torch.uint8).clone()
+    return t.to(device)
+
+
+# ------------------------------------------------------------------------------------ convs
+def conv_shape(batch, in_h, in_w, in_c, out_c, k, stride, pad):
+    oh = (in_h + 2 * pad - k) // stride + 1
+    ow = (in_w + 2 * pad - k) // stride + 1
+    return ConvShape(batch, in_h, in_w, in_c, out_c, k, k, stride, pad, oh, ow)
+
+
+def conv_fprop(x, w, shape, scale=None, bias=None, residual=None, relu=False, impl=CONV_AUTO, out=None):
+    """x NHWC [B,H,W,Ci] dense, w OHWI [Co,kh,kw,Ci] dense -> y NHWC [B,OH,OW,Co]."""
+    _need_cuda(x, w, scale, bias, residual)
+    L = _l.lib()
+    assert x.is_contiguous() and w.is_contiguous() and x.dtype == torch.float32 and w.dtype == torch.float32
+    y = out if out is not None else torch.empty((shape.batch, shape.out_h, shape.out_w, shape.out_c),
+                                                dtype=torch.float32, device=x.device)
+    check(L.mmt_conv_fprop_f32(_p(x), _p(w), _p(scale), _p(bias), _p(residual), _p(y), ctypes.byref(shape),
+                               EPI_RELU if relu else 0, impl, _stream()), "conv_fprop")
+    return y
+
+
+def conv_dgrad(dy, w, shape, impl=CONV_AUTO):
+    _need_cuda(dy, w)
+    L = _l.lib()
+    assert dy.is_contiguous() and w.is_contiguous()
+    dx = torch.empty((shape.batch, shape.in_h, shape.in_w, shape.in_c), dtype=torch.float32, device=dy.device)
+    wsb = L.mmt_conv_workspace_bytes(ctypes.byref(shape))
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dy.device)
+    check(L.mmt_conv_dgrad_f32(_p(dy), _p(w), _p(dx), ctypes.byref(shape), impl, _p(ws), wsb, _stream()),
+          "conv_dgrad")
+    return dx
+
+
+def conv_wgrad(x, dy, shape, want_dbias=False, impl=CONV_AUTO):
+    _need_cuda(x, dy)
+    L = _l.lib()
+    assert x.is_contiguous() and dy.is_contiguous()
+    dw = torch.empty((shape.out_c, shape.k_h, shape.k_w, shape.in_c), dtype=torch.float32, device=x.device)
+    db = torch.empty(shape.out_c, dtype=torch.float32, device=x.device) if want_dbias else None
+    wsb = L.mmt_conv_workspace_bytes(ctypes.byref(shape))
+    ws = torch.empty(wsb, dtype=torch.uint8, device=x.device)
+    check(L.mmt_conv_wgrad_f32(_p(x), _p(dy), _p(dw), _p(db), ctypes.byref(shape), impl, _p(ws), wsb, _stream()),
+          "conv_wgrad")
+    return dw, db
+
+
+def bn_relu_backward(grad_y, y, scale, relu):
+    _need_cuda(grad_y, y, scale)
+    L = _l.lib()
+    assert grad_y.is_contiguous()
+    C = grad_y.shape[-1]
+    gz = torch.empty_like(grad_y)
+    check(L.mmt_bn_relu_backward_f32(_p(grad_y), _p(y), _p(scale), _p(gz), grad_y.numel() // C, C,
+                                     int(bool(relu)), _stream()), "bn_relu_backward")
+    return gz
+
+
+def maxpool3x3s2(x):
+    _need_cuda(x)
+    L = _l.lib()
+    B, H, W, C = x.shape
+    y = torch.empty((B, (H - 1) // 2 + 1, (W - 1) // 2 + 1, C), dtype=torch.float32, device=x.device)
+    check(L.mmt_maxpool3x3s2_forward_f32(_p(x), _p(y), B, H, W, C, _stream()), "maxpool")
+    return y
+
+
+def subsample2(x):
+    _need_cuda(x)
+    L = _l.lib()
+    B, H, W, C = x.shape
+    y = torch.empty((B, (H - 1) // 2 + 1, (W - 1) // 2 + 1, C), dtype=torch.float32, device=x.device)
+    check(L.mmt_subsample2_forward_f32(_p(x), _p(y), B, H, W, C, _stream()), "subsample2")
+    return y
+
+
+def subsample2_backward_(grad_y, grad_x):
+    _need_cuda(grad_y, grad_x)
+    L = _l.lib()
+    B, H, W, C = grad_x.shape
+    check(L.mmt_subsample2_backward_f32(_p(grad_y), _p(grad_x), B, H, W, C, _stream()), "subsample2_backward")
+
+
+def upsample2_add(lateral, top):
+    _need_cuda(lateral, top)
+    L = _l.lib()
+    B, H, W, C = lateral.shape
+    out = torch.empty_like(lateral)
+    check(L.mmt_upsample2_add_f32(_p(lateral), _p(top), _p(out), B, H, W, top.shape[1], top.shape[2], C, _stream()),
+          "upsample2_add")
+    return out
+
+
+def upsample2_backward_(grad_out, grad_top):
+    _need_cuda(grad_out, grad_top)
+    L = _l.lib()
+    B, H, W, C = grad_out.shape
+    check(L.mmt_upsample2_backward_f32(_p(grad_out), _p(grad_top), B, H, W, grad_top.shape[1], grad_top.shape[2],
+                                       C, _stream()), "upsample2_backward")
+
+
+def nchw_to_nhwc(x):
+    _need_cuda(x)
+    L = _l.lib()
+    x = _f32c(x)
+    N, C, H, W = x.shape
+    y = torch.empty((N, H, W, C), dtype=torch.float32, device=x.device)
+    check(L.mmt_nchw_to_nhwc_f32(_p(x), _p(y), N, C, H, W, _stream()), "nchw_to_nhwc")
+    return y
+
+
+def nhwc_to_nchw(x):
+    _need_cuda(x)
+    L = _l.lib()
+    x = _f32c(x)
+    N, H, W, C = x.shape
+    y = torch.empty((N, C, H, W), dtype=torch.float32, device=x.device)
+    check(L.mmt_nhwc_to_nchw_f32(_p(x), _p(y), N, C, H, W, _stream()), "nhwc_to_nchw")
+    return y

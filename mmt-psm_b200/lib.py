@@ -1,0 +1,113 @@
+"""ctypes binding of libmmtpsm_b200.so (the C ABI declared in include/mmtpsm_b200.h).
+
+This is the ONLY place the shared library is opened.  There is no CPU or PyTorch fallback: if the
+library is missing, `lib()` raises, and every op in `kernels.py` refuses non-CUDA tensors.
+"""
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int64, c_size_t, c_uint, c_void_p
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "_lib", "libmmtpsm_b200.so")
+
+
+class Strides4(Structure):
+    _fields_ = [("n", c_int64), ("c", c_int64), ("h", c_int64), ("w", c_int64)]
+
+
+class ConvShape(Structure):
+    _fields_ = [("batch", c_int), ("in_h", c_int), ("in_w", c_int), ("in_c", c_int),
+                ("out_c", c_int), ("k_h", c_int), ("k_w", c_int), ("stride", c_int), ("pad", c_int),
+                ("out_h", c_int), ("out_w", c_int)]
+
+
+class ParamSegment(Structure):
+    _fields_ = [("begin", c_int64), ("end", c_int64), ("lr", c_float), ("weight_decay", c_float),
+                ("trainable", c_int), ("reserved", c_int)]
+
+
+P = c_void_p
+_PROTOS = {
+    "mmt_last_error": (c_char_p, []),
+    "mmt_version": (c_char_p, []),
+    "mmt_launch_count": (c_int64, []),
+    "mmt_reset_launch_count": (None, []),
+    "mmt_nms_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "mmt_nms_segmented_f32": (c_int, [P, P, POINTER(c_int), c_int, c_float, P, P, P, c_size_t, P]),
+    "mmt_nms_f32": (c_int, [P, P, c_int, c_float, P, P, P, c_size_t, P]),
+    "mmt_roi_align_forward_f32": (c_int, [P, Strides4, c_int, c_int, c_int, c_int, P, c_int, c_float,
+                                          c_int, c_int, c_int, P, Strides4, P]),
+    "mmt_roi_align_backward_f32": (c_int, [P, Strides4, P, c_int, c_float, c_int, c_int, c_int, P,
+                                           Strides4, c_int, c_int, c_int, c_int, P]),
+    "mmt_roi_align_fpn_forward_f32": (c_int, [POINTER(P), POINTER(c_int), POINTER(c_int),
+                                              POINTER(c_float), c_int, c_int, c_int, P, c_int, c_int,
+                                              c_int, c_int, P, P, P]),
+    "mmt_roi_align_fpn_backward_f32": (c_int, [P, P, P, c_int, c_int, c_int, c_int, POINTER(P),
+                                               POINTER(c_int), POINTER(c_int), POINTER(c_float), c_int,
+                                               c_int, c_int, P]),
+    "mmt_roi_pool_forward_f32": (c_int, [P, c_int, c_int, c_int, c_int, P, c_int, c_float, c_int,
+                                         c_int, P, P, P]),
+    "mmt_roi_pool_backward_f32": (c_int, [P, P, P, c_int, c_int, c_int, P, c_int, c_int, c_int,
+                                          c_int, P]),
+    "mmt_sigmoid_focal_loss_forward_f32": (c_int, [P, P, c_int, c_int, c_float, c_float, P, P]),
+    "mmt_sigmoid_focal_loss_backward_f32": (c_int, [P, P, P, c_int, c_int, c_float, c_float, P, P]),
+    "mmt_psm_workspace_bytes": (c_size_t, [c_int]),
+    "mmt_psm_loss_f32": (c_int, [P, P, c_int, P, c_int, c_int, c_float, c_int, c_int, c_float, P, P,
+                                 P, P, P, c_size_t, P]),
+    "mmt_mgd_masks_f32": (c_int, [P, c_int, c_int, c_int, POINTER(c_int), POINTER(c_int), c_int, P,
+                                  P, P]),
+    "mmt_mgd_level_f32": (c_int, [P, Strides4, POINTER(P), Strides4, c_int, c_uint, P, P, c_int,
+                                  c_int, c_int, c_int, c_float, P, P, Strides4, P]),
+    "mmt_mgd_finalize_f32": (c_int, [P, P, c_int, c_int, c_int, P, P]),
+    "mmt_ema_f32": (c_int, [P, P, c_int64, c_float, P]),
+    "mmt_sgd_ema_f32": (c_int, [P, P, P, P, c_int64, P, c_int, c_float, c_float, c_int, c_float, P]),
+    "mmt_conv_workspace_bytes": (c_size_t, [POINTER(ConvShape)]),
+    "mmt_conv_fprop_f32": (c_int, [P, P, P, P, P, P, POINTER(ConvShape), c_int, c_int, P]),
+    "mmt_conv_dgrad_f32": (c_int, [P, P, P, POINTER(ConvShape), c_int, P, c_size_t, P]),
+    "mmt_conv_wgrad_f32": (c_int, [P, P, P, P, POINTER(ConvShape), c_int, P, c_size_t, P]),
+    "mmt_bn_relu_backward_f32": (c_int, [P, P, P, P, c_int64, c_int, c_int, P]),
+    "mmt_maxpool3x3s2_forward_f32": (c_int, [P, P, c_int, c_int, c_int, c_int, P]),
+    "mmt_subsample2_forward_f32": (c_int, [P, P, c_int, c_int, c_int, c_int, P]),
+    "mmt_subsample2_backward_f32": (c_int, [P, P, c_int, c_int, c_int, c_int, P]),
+    "mmt_upsample2_add_f32": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
+    "mmt_upsample2_backward_f32": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
+    "mmt_nchw_to_nhwc_f32": (c_int, [P, P, c_int, c_int, c_int, c_int, P]),
+    "mmt_nhwc_to_nchw_f32": (c_int, [P, P, c_int, c_int, c_int, c_int, P]),
+}
+
+_lib = None
+
+
+def exported_symbols():
+    """Names the header declares (used by the CPU-side ABI test)."""
+    return sorted(_PROTOS)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "libmmtpsm_b200.so is not built (%s). Run `python mmt-psm_b200/build.py`; "
+                "there is no CPU / PyTorch fallback for the hot path." % LIB_PATH)
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _PROTOS.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = lib().mmt_last_error().decode("utf-8", "replace")
+        raise RuntimeError("mmtpsm_b200 %s failed (status %d): %s" % (what, rc, msg))
+
+
+def launch_count():
+    return int(lib().mmt_launch_count())
+
+
+def reset_launch_count():
+    lib().mmt_reset_launch_count()

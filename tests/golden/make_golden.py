@@ -1,0 +1,224 @@
+"""Generates tests/golden/*.npz by EXECUTING THE (PATCHED) REFERENCE in this container.
+
+    python oracle/build_ref.py            # builds /tmp/mmtpsm_ref (patched copy, see that file)
+    python tests/golden/make_golden.py    # writes the fixtures next to this script
+
+The fixtures are small seeded input/output pairs of the reference's own functions on the hot path;
+they travel to the GPU box (where /root/reference does not exist) and pin both the CPU oracle
+(`oracle/ops_ref.py`, test_oracle_cpu.py) and the CUDA path (`-m gpu` tests).
+"""
+import os
+import sys
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+
+TREE = os.environ.get("MMTPSM_REF_TREE", "/tmp/mmtpsm_ref")
+sys.path.insert(0, TREE)
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+from maskrcnn_benchmark import _C  # noqa: E402  (reference csrc, CPU build)
+from maskrcnn_benchmark.config import cfg  # noqa: E402
+
+MT_OPTS = ["MT.ALPHA", 0.99, "MT.LAMBDA", 5., "MT.RAMPUP_STEP", 250, "MT.RAMPDOWN_STEP", 250, "MT.TEMP", 0.5,
+           "MT.SHARPEN", True, "MT.START_MT", 1000, "MT.AUG_S", 1, "MT.CLS_LOSS_TYPE", "bce", "MT.CLS_LOSS", 0.2,
+           "MT.HARD_NEG", True, "MT.CLS_BALANCE_WEIGHT", 1.5, "MT.RANK_FILTER", 0.2, "MT.FG_HINT", 1.,
+           "MT.T_ADAPT", True, "MODEL.ROI_BOX_HEAD.DO", 0.5, "SOLVER.BASE_LR", 0.005]
+
+
+def save(name, **arrays):
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **{k: np.asarray(v) for k, v in arrays.items()})
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
+def clustered_boxes(g, n, size=800.0):
+    centers = torch.rand(max(n // 6, 1), 2, generator=g) * size
+    idx = torch.randint(0, centers.shape[0], (n,), generator=g)
+    c = centers[idx] + torch.randn(n, 2, generator=g) * 6
+    wh = torch.rand(n, 2, generator=g) * 60 + 8
+    b = torch.cat([c - wh / 2, c + wh / 2], 1).clamp(0, size - 1)
+    return b.float()
+
+
+def gen_nms():
+    g = torch.Generator().manual_seed(11)
+    out = {}
+    for i, (n, thr) in enumerate([(300, 0.7), (257, 0.5), (64, 0.3), (1, 0.5), (900, 0.7)]):
+        b = clustered_boxes(g, n)
+        s = torch.rand(n, generator=g)
+        keep = _C.nms(b, s, thr)  # CPU flavour (>=); inputs have no IoU == thr (checked in the test)
+        out.update({"boxes%d" % i: b.numpy(), "scores%d" % i: s.numpy(), "thr%d" % i: thr, "keep%d" % i: keep.numpy()})
+    # integer-coordinate boxes with many exactly-equal scores (sigmoid saturation case): the reference
+    # CPU sort order for ties is recorded through its result
+    save("nms", n_cases=5, **out)
+
+
+def gen_roi_align():
+    g = torch.Generator().manual_seed(12)
+    out = {}
+    cases = [(2, 8, 40, 50, 30, 0.25, 7, 2), (1, 4, 25, 25, 17, 1 / 16., 14, 2), (2, 12, 13, 13, 9, 1 / 64., 7, 0),
+             (3, 8, 31, 47, 25, 0.125, 7, 3)]
+    for i, (B, C, H, W, K, scale, P, sr) in enumerate(cases):
+        x = torch.randn(B, C, H, W, generator=g)
+        img_w, img_h = W / scale, H / scale
+        ctr = torch.rand(K, 2, generator=g) * torch.tensor([img_w, img_h])
+        wh = torch.rand(K, 2, generator=g) * torch.tensor([img_w, img_h]) * 0.5 + 1
+        boxes = torch.cat([ctr - wh / 2, ctr + wh / 2], 1)
+        boxes[0] = torch.tensor([-20., -30., 10., 12.])           # partly outside
+        boxes[1] = torch.tensor([img_w - 5, img_h - 4, img_w + 40, img_h + 30])
+        boxes[2] = torch.tensor([5., 5., 5.2, 5.1])                # degenerate (< 1 px on the map)
+        ids = torch.randint(0, B, (K, 1), generator=g).float()
+        rois = torch.cat([ids, boxes], 1)
+        y = _C.roi_align_forward(x, rois, scale, P, P, sr)
+        out.update({"x%d" % i: x.numpy(), "rois%d" % i: rois.numpy(), "cfg%d" % i: np.array([scale, P, sr]), "y%d" % i: y.numpy()})
+    save("roi_align", n_cases=len(cases), **out)
+
+
+def gen_psm():
+    from maskrcnn_benchmark.modeling.roi_heads.box_head.loss import make_roi_box_loss_evaluator
+    from maskrcnn_benchmark.structures.bounding_box import BoxList
+    c = cfg.clone()
+    c.merge_from_list(MT_OPTS)
+    ev = make_roi_box_loss_evaluator(c)
+    g = torch.Generator().manual_seed(13)
+    out = {}
+    cases = [(1024, 4, 0.25), (512, 4, 0.05), (64, 2, 0.5), (100, 4, 0.9), (40, 4, 0.0)]
+    for i, (n, views, pos_frac) in enumerate(cases):
+        base = torch.randn(n, 3, generator=g) * 2
+        teacher = [base + torch.randn(n, 3, generator=g) * (0.3 + torch.rand(n, 1, generator=g)) for _ in range(views)]
+        student = (base + torch.randn(n, 3, generator=g)).requires_grad_(True)
+        labels = torch.zeros(n, dtype=torch.int64)
+        npos = int(n * pos_frac)
+        labels[torch.randperm(n, generator=g)[:npos]] = torch.randint(1, 3, (npos,), generator=g)
+        halves = [n // 2, n - n // 2]
+        props, o = [], 0
+        for h in halves:
+            bl = BoxList(torch.zeros(h, 4), (800, 800))
+            bl.add_field("labels", labels[o:o + h])
+            props.append(bl)
+            o += h
+        loss = ev.evaluatePSM([student], teacher, props)
+        if torch.isfinite(loss):
+            loss.backward()
+            grad = student.grad.numpy()
+        else:
+            grad = np.zeros((n, 3), np.float32)
+        out.update({"student%d" % i: student.detach().numpy(), "teacher%d" % i: torch.stack(teacher).numpy(),
+                    "labels%d" % i: labels.numpy(), "loss%d" % i: loss.detach().numpy(), "grad%d" % i: grad})
+    save("psm", n_cases=len(cases), temperature=c.MT.TEMP, neg_weight=c.MT.CLS_BALANCE_WEIGHT, **out)
+
+
+def gen_mgd():
+    from maskrcnn_benchmark.modeling.detector.generalized_rcnn import fg_hint_loss
+    g = torch.Generator().manual_seed(14)
+    out = {}
+    cases = [(2, 16, 64, 4), (1, 128, 96, 4), (2, 8, 64, 2)]
+    for i, (B, C, S, V) in enumerate(cases):
+        sizes = [S // 4, S // 8, S // 16, S // 32, (S // 32 + 1) // 2]
+        student = tuple(torch.randn(B, C, s, s, generator=g).requires_grad_(True) for s in sizes)
+        teachers = [tuple(torch.randn(B, C, s, s, generator=g) for s in sizes) for _ in range(V)]
+        mask = torch.zeros(B, S, S, dtype=torch.uint8)
+        for b in range(B):
+            for _ in range(5):
+                cy, cx = torch.randint(0, S, (2,), generator=g).tolist()
+                r = int(torch.randint(3, S // 4, (1,), generator=g))
+                mask[b, max(cy - r, 0):cy + r, max(cx - r, 0):cx + r] += 1
+        loss = fg_hint_loss(teachers, [student], [m for m in mask])
+        loss.backward()
+        out.update({"mask%d" % i: mask.numpy(), "loss%d" % i: loss.detach().numpy(), "dims%d" % i: np.array([B, C, S, V])})
+        for l, s in enumerate(student):
+            out["student%d_%d" % (i, l)] = s.detach().numpy()
+            out["grad%d_%d" % (i, l)] = s.grad.numpy()
+            for v in range(V):
+                out["teacher%d_%d_%d" % (i, v, l)] = teachers[v][l].numpy()
+    save("mgd", n_cases=len(cases), **out)
+
+
+def gen_ema_and_weights():
+    from maskrcnn_benchmark.engine.MTtrainer import MTtrainer, weight_sum_losses
+    g = torch.Generator().manual_seed(15)
+    student = torch.nn.Linear(37, 53)
+    teacher = torch.nn.Linear(37, 53)
+    with torch.no_grad():
+        for p in list(student.parameters()) + list(teacher.parameters()):
+            p.copy_(torch.randn(p.shape, generator=g))
+    out = {"s_w": student.weight.detach().numpy().copy(), "s_b": student.bias.detach().numpy().copy(),
+           "t_w": teacher.weight.detach().numpy().copy(), "t_b": teacher.bias.detach().numpy().copy()}
+    me = SimpleNamespace(teacher=teacher, student=student, alpha=0.99)
+    steps = [0, 3, 99, 5000]
+    for k in steps:
+        MTtrainer.update_teacher(me, k)
+        out["t_w_after%d" % k] = teacher.weight.detach().numpy().copy()
+        out["t_b_after%d" % k] = teacher.bias.detach().numpy().copy()
+    out["steps"] = np.array(steps)
+    # loss weighting schedule (engine/MTtrainer.py:67-109)
+    balanced = {"mt_classifier": 0.2, "nms_loss": 1.0, "mt_fg_loss": 1.0}
+    ld = {"loss_classifier": 0.7, "loss_box_reg": 0.3, "loss_seg": 0.9, "mt_classifier": 0.11, "mt_fg_loss": 0.05, "nms_loss": 0.4}
+    iters = [900, 1001, 1100, 1249, 1250, 5000, 9800, 9999]
+    table = []
+    for it in iters:
+        w = weight_sum_losses(dict(ld), it, 250, 250, 10000, l=5.0, balanced=balanced, start_mt=1000)
+        table.append([float(w[k]) for k in sorted(ld)])
+    out["ws_iters"] = np.array(iters)
+    out["ws_keys"] = np.array(sorted(ld))
+    out["ws_in"] = np.array([ld[k] for k in sorted(ld)])
+    out["ws_out"] = np.array(table)
+    save("ema_weights", **out)
+
+
+def gen_glue():
+    """Host-side glue the CUDA ops sit between: anchors, box coder, matcher, level mapper, boxlist ops."""
+    from maskrcnn_benchmark.modeling.box_coder import BoxCoder
+    from maskrcnn_benchmark.modeling.matcher import Matcher
+    from maskrcnn_benchmark.modeling.poolers import LevelMapper
+    from maskrcnn_benchmark.modeling.rpn.anchor_generator import make_anchor_generator
+    from maskrcnn_benchmark.structures.bounding_box import BoxList
+    from maskrcnn_benchmark.structures.boxlist_ops import boxlist_iou
+    from maskrcnn_benchmark.structures.image_list import to_image_list
+    g = torch.Generator().manual_seed(16)
+    out = {}
+    c = cfg.clone()
+    ag = make_anchor_generator(c)
+    feats = [torch.zeros(1, 1, s, s) for s in (16, 8, 4, 2, 1)]
+    il = to_image_list(torch.zeros(1, 3, 64, 64))
+    anchors = ag(il, feats)[0]
+    for l, a in enumerate(anchors):
+        out["anchors%d" % l] = a.bbox.numpy()
+        out["anchors_vis%d" % l] = a.get_field("visibility").numpy()
+    ref = clustered_boxes(g, 200)
+    prop = ref + torch.randn(200, 4, generator=g) * 4
+    prop[:, 2:] = torch.max(prop[:, 2:], prop[:, :2] + 1)
+    for name, w in (("rpn", (1., 1., 1., 1.)), ("box", (10., 10., 5., 5.))):
+        bc = BoxCoder(weights=w)
+        enc = bc.encode(ref, prop)
+        dec = bc.decode(enc * 1.3 + 0.01, prop)
+        out["coder_%s_enc" % name] = enc.numpy()
+        out["coder_%s_dec" % name] = dec.numpy()
+    out["coder_ref"] = ref.numpy()
+    out["coder_prop"] = prop.numpy()
+    gt = BoxList(clustered_boxes(g, 12), (800, 800))
+    pr = BoxList(torch.cat([clustered_boxes(g, 300), gt.bbox + 2]), (800, 800))
+    iou = boxlist_iou(gt, pr)
+    out["iou_gt"] = gt.bbox.numpy()
+    out["iou_pr"] = pr.bbox.numpy()
+    out["iou"] = iou.numpy()
+    out["match_rpn"] = Matcher(0.7, 0.3, allow_low_quality_matches=True)(iou).numpy()
+    out["match_box"] = Matcher(0.5, 0.5, allow_low_quality_matches=False)(iou).numpy()
+    lm = LevelMapper(2, 5)
+    bl = BoxList(torch.cat([clustered_boxes(g, 300), torch.tensor([[0, 0, 111, 111.], [0, 0, 223, 223.], [0, 0, 447, 447.], [0, 0, 799, 799.], [3, 3, 4, 4.]])]), (800, 800))
+    out["lvl_boxes"] = bl.bbox.numpy()
+    out["lvl"] = lm([bl]).numpy()
+    save("glue", **out)
+
+
+if __name__ == "__main__":
+    torch.manual_seed(0)
+    which = sys.argv[1:] or ["nms", "roi_align", "psm", "mgd", "ema", "glue"]
+    if "nms" in which: gen_nms()
+    if "roi_align" in which: gen_roi_align()
+    if "psm" in which: gen_psm()
+    if "mgd" in which: gen_mgd()
+    if "ema" in which: gen_ema_and_weights()
+    if "glue" in which: gen_glue()

@@ -1,0 +1,391 @@
+"""GPU parity tests proper: every CUDA op, called through the C ABI (ctypes), against
+(a) fixtures produced by the reference itself (tests/golden) and (b) the CPU oracle on seeded inputs."""
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, golden
+
+sys.path.insert(0, ROOT)
+from oracle import ops_ref as R  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+def K():
+    from mmt_psm_b200 import kernels
+    return kernels
+
+
+# ------------------------------------------------------------------------------------------ NMS
+def test_nms_golden_bit_exact(cuda):
+    g = golden("nms")
+    for i in range(int(g["n_cases"])):
+        b = torch.tensor(g["boxes%d" % i], device=cuda)
+        s = torch.tensor(g["scores%d" % i], device=cuda)
+        keep = K().nms(b, s, float(g["thr%d" % i]))
+        assert keep.dtype == torch.int64 and keep.is_cuda
+        assert np.array_equal(keep.cpu().numpy(), g["keep%d" % i])
+
+
+def test_nms_full_size_ties_and_empty(cuda):
+    gen = torch.Generator().manual_seed(21)
+    # RPN-sized problem (2000 boxes) with saturated, tied scores (sigmoid == 1.0f) — SURVEY "NMS ties"
+    n = 2000
+    c = torch.rand(n, 2, generator=gen) * 780
+    wh = torch.rand(n, 2, generator=gen) * 120 + 4
+    b = torch.cat([c, c + wh], 1)
+    s = torch.sigmoid(torch.randn(n, generator=gen) * 12)
+    assert (s == 1).sum() > 10
+    keep = K().nms(b.to(cuda), s.to(cuda), 0.7).cpu().numpy()
+    assert np.array_equal(keep, R.nms_ref(b.numpy(), s.numpy(), 0.7))
+    assert np.all(np.diff(keep) > 0)
+    # idempotence: NMS of the survivors keeps everything
+    k2 = K().nms(b[keep].to(cuda), s[keep].to(cuda), 0.7).cpu().numpy()
+    assert np.array_equal(k2, np.arange(len(keep)))
+    # exact-threshold case distinguishes the CUDA (>) from the CPU (>=) flavour
+    bb = torch.tensor([[0, 0, 3, 1], [0, 0, 3, 1], [2, 0, 5, 1.]], device=cuda)
+    ss = torch.tensor([0.9, 0.8, 0.7], device=cuda)
+    assert K().nms(bb, ss, 1.0).tolist() == [0, 1, 2]
+    # empty input: empty int64 CPU tensor (reference csrc/nms.h:17-18)
+    e = K().nms(torch.zeros(0, 4, device=cuda), torch.zeros(0, device=cuda), 0.5)
+    assert e.numel() == 0 and e.dtype == torch.int64 and e.device.type == "cpu"
+    # single box
+    assert K().nms(bb[:1], ss[:1], 0.5).tolist() == [0]
+
+
+def test_nms_segmented_matches_per_segment(cuda):
+    gen = torch.Generator().manual_seed(22)
+    sizes = [2000, 0, 1875, 507, 1, 64, 65, 2000, 999, 130]
+    boxes, scores = [], []
+    for n in sizes:
+        c = torch.rand(n, 2, generator=gen) * 700
+        wh = torch.rand(n, 2, generator=gen) * 90 + 2
+        boxes.append(torch.cat([c, c + wh], 1))
+        scores.append(torch.rand(n, generator=gen))
+    offs = np.concatenate([[0], np.cumsum(sizes)]).tolist()
+    keep, counts = K().nms_segmented(torch.cat(boxes).to(cuda), torch.cat(scores).to(cuda), offs, 0.7)
+    keep, counts = keep.cpu().numpy(), counts.cpu().numpy()
+    for i, n in enumerate(sizes):
+        ref = R.nms_ref(boxes[i].numpy(), scores[i].numpy(), 0.7)
+        assert counts[i] == len(ref)
+        assert np.array_equal(keep[offs[i]: offs[i] + counts[i]], ref)
+
+
+# ------------------------------------------------------------------------------------- ROIAlign
+def test_roi_align_forward_golden_bit_exact(cuda):
+    g = golden("roi_align")
+    for i in range(int(g["n_cases"])):
+        scale, P, sr = g["cfg%d" % i]
+        x = torch.tensor(g["x%d" % i], device=cuda)
+        rois = torch.tensor(g["rois%d" % i], device=cuda)
+        y = K().roi_align_forward(x, rois, float(scale), int(P), int(P), int(sr))
+        assert np.array_equal(y.cpu().numpy(), g["y%d" % i]), "NCHW case %d" % i
+        y2 = K().roi_align_forward(x.contiguous(memory_format=torch.channels_last), rois, float(scale), int(P), int(P), int(sr))
+        assert np.array_equal(y2.contiguous().cpu().numpy(), g["y%d" % i]), "NHWC case %d" % i
+
+
+def test_roi_align_backward_vs_oracle(cuda):
+    g = golden("roi_align")
+    for i in (0, 2, 3):
+        scale, P, sr = g["cfg%d" % i]
+        x = g["x%d" % i]
+        rois = g["rois%d" % i]
+        go = torch.randn(rois.shape[0], x.shape[1], int(P), int(P), generator=torch.Generator().manual_seed(i))
+        ref = R.roi_align_backward_ref(go.numpy(), rois, float(scale), int(P), int(P), *x.shape, int(sr))
+        for fmt in (torch.contiguous_format, torch.channels_last):
+            gi = K().roi_align_backward(go.to(cuda).contiguous(memory_format=fmt), torch.tensor(rois, device=cuda),
+                                        float(scale), int(P), int(P), *x.shape, int(sr))
+            np.testing.assert_allclose(gi.contiguous().cpu().numpy(), ref, rtol=1e-5, atol=2e-5)
+
+
+def test_roi_align_fpn_fused_equals_per_level(cuda):
+    gen = torch.Generator().manual_seed(23)
+    B, C = 2, 256
+    sizes = [(200, 200), (100, 100), (50, 50), (25, 25)]
+    scales = [1 / 4., 1 / 8., 1 / 16., 1 / 32.]
+    feats = [torch.randn(B, h, w, C, generator=gen).to(cuda) for h, w in sizes]
+    n = 1024
+    c = torch.rand(n, 2, generator=gen) * 800
+    wh = torch.exp(torch.rand(n, 2, generator=gen) * 5.5 + 1)
+    boxes = torch.cat([c - wh / 2, c + wh / 2], 1).clamp(0, 799)
+    ids = torch.randint(0, B, (n, 1), generator=gen).float()
+    rois = torch.cat([ids, boxes], 1)
+    levels = torch.tensor(R.level_mapper_ref(boxes.numpy()), dtype=torch.int32)
+    assert len(set(levels.tolist())) == 4
+    for P in (7, 14):
+        out = K().roi_align_fpn_forward(feats, scales, rois.to(cuda), levels.to(cuda), P, 2)
+        go = torch.randn(out.shape, generator=gen).to(cuda)
+        grads = [torch.zeros_like(f) for f in feats]
+        K().roi_align_fpn_backward(go, scales, rois.to(cuda), levels.to(cuda), P, 2, grads)
+        for l in range(4):
+            idx = torch.nonzero(levels == l).squeeze(1)
+            x_nchw = feats[l].permute(0, 3, 1, 2)  # channels_last view
+            ref = K().roi_align_forward(x_nchw, rois[idx].to(cuda), scales[l], P, P, 2)
+            assert torch.equal(out[idx.to(cuda)], ref.permute(0, 2, 3, 1))
+            gref = K().roi_align_backward(go[idx.to(cuda)].permute(0, 3, 1, 2), rois[idx].to(cuda), scales[l], P, P, B, C,
+                                          sizes[l][0], sizes[l][1], 2)
+            torch.testing.assert_close(grads[l], gref.permute(0, 2, 3, 1), rtol=1e-4, atol=1e-4)
+    # small level checked against the CPU oracle too
+    l = 3
+    idx = torch.nonzero(levels == l).squeeze(1)[:40]
+    ref = R.roi_align_forward_ref(feats[l].permute(0, 3, 1, 2).cpu().numpy(), rois[idx].numpy(), scales[l], 7, 7, 2)
+    out = K().roi_align_fpn_forward(feats, scales, rois[idx].to(cuda), levels[idx].to(cuda), 7, 2)
+    assert np.array_equal(out.permute(0, 3, 1, 2).cpu().numpy(), ref)
+
+
+def test_roi_pool_vs_torchvision(cuda):
+    import torchvision.ops as tvo
+    gen = torch.Generator().manual_seed(24)
+    x = torch.randn(2, 6, 30, 40, generator=gen)
+    c = torch.rand(20, 2, generator=gen) * torch.tensor([300., 220.])
+    wh = torch.rand(20, 2, generator=gen) * 100 + 4
+    rois = torch.cat([torch.randint(0, 2, (20, 1), generator=gen).float(), c, c + wh], 1)
+    out, arg = K().roi_pool_forward(x.to(cuda), rois.to(cuda), 0.125, 7, 7)
+    ref = tvo.roi_pool(x, rois, 7, 0.125)
+    torch.testing.assert_close(out.cpu(), ref)
+    go = torch.randn(out.shape, generator=gen)
+    xr = x.clone().requires_grad_(True)
+    tvo.roi_pool(xr, rois, 7, 0.125).backward(go)
+    gi = K().roi_pool_backward(go.to(cuda), x.to(cuda), rois.to(cuda), arg, 0.125, 7, 7, 2, 6, 30, 40)
+    torch.testing.assert_close(gi.cpu(), xr.grad, rtol=1e-5, atol=1e-5)
+
+
+# ------------------------------------------------------------------------------------- losses
+def test_sigmoid_focal_loss_vs_oracle(cuda):
+    gen = torch.Generator().manual_seed(25)
+    x = torch.randn(4000, 3, generator=gen) * 4
+    t = torch.randint(-1, 4, (4000,), generator=gen)
+    ref = R.sigmoid_focal_loss_ref(x, t, 2.0, 0.25)
+    out = K().sigmoid_focal_loss_forward(x.to(cuda), t.to(cuda), 3, 2.0, 0.25)
+    np.testing.assert_allclose(out.cpu().numpy(), ref.numpy(), rtol=1e-4, atol=1e-7)  # fp32 vs fp64: 1e-4 rel
+    xd = x.double().requires_grad_(True)
+    w = torch.randn(4000, 3, generator=gen)
+    (R.sigmoid_focal_loss_ref(xd, t, 2.0, 0.25) * w.double()).sum().backward()
+    gx = K().sigmoid_focal_loss_backward(x.to(cuda), t.to(cuda), w.to(cuda), 3, 2.0, 0.25)
+    np.testing.assert_allclose(gx.cpu().numpy(), xd.grad.numpy(), rtol=1e-4, atol=1e-6)
+
+
+def test_psm_golden_and_oracle(cuda):
+    g = golden("psm")
+    for i in range(int(g["n_cases"])):
+        s, t, lab = g["student%d" % i], g["teacher%d" % i], g["labels%d" % i]
+        loss, grad, sel = K().psm_loss(torch.tensor(s, device=cuda), torch.tensor(t, device=cuda),
+                                       torch.tensor(lab, device=cuda), float(g["temperature"]), True, True,
+                                       float(g["neg_weight"]))
+        ref = float(g["loss%d" % i])
+        _, sel_ref = R.psm_loss_ref(s, list(t), lab, float(g["temperature"]), True, True, float(g["neg_weight"]))
+        assert np.array_equal(sel.cpu().numpy(), sel_ref.numpy())  # selection indices exact
+        if np.isnan(ref):
+            assert torch.isnan(loss).all()
+            continue
+        assert abs(float(loss) - ref) <= 1e-4 * abs(ref)  # fp32 losses within 1e-4 rel (north_star)
+        np.testing.assert_allclose(grad.cpu().numpy(), g["grad%d" % i], rtol=1e-4, atol=1e-8)
+
+
+def test_mgd_golden(cuda):
+    g = golden("mgd")
+    for i in range(int(g["n_cases"])):
+        B, C, S, V = [int(v) for v in g["dims%d" % i]]
+        mask = torch.tensor(g["mask%d" % i], device=cuda).float()
+        student = [torch.tensor(g["student%d_%d" % (i, l)], device=cuda).permute(0, 2, 3, 1).contiguous() for l in range(5)]
+        sizes = [(s.shape[1], s.shape[2]) for s in student]
+        masks, sums = K().mgd_masks(mask, sizes)
+        _, ref_masks = R.mgd_loss_ref([[g["teacher%d_%d_%d" % (i, v, l)] for l in range(5)] for v in range(V)],
+                                      [g["student%d_%d" % (i, l)] for l in range(5)], g["mask%d" % i])
+        partials = torch.zeros(5, V, device=cuda)
+        flip = sum(1 << v for v in range(V) if v % 2 == 1)
+        grads = []
+        for l in range(5):
+            assert np.array_equal(masks[l].cpu().numpy(), ref_masks[l][:, 0].numpy().astype(np.uint8))
+            teachers = [torch.tensor(g["teacher%d_%d_%d" % (i, v, l)], device=cuda).permute(0, 2, 3, 1).contiguous() for v in range(V)]
+            grads.append(K().mgd_level(student[l], teachers, flip, masks[l], sums[l:l + 1], 1.0 / (5 * V), partials[l], True))
+        loss = K().mgd_finalize(partials, sums, 5, V, C)
+        ref = float(g["loss%d" % i])
+        assert abs(float(loss) - ref) <= 1e-4 * abs(ref)
+        for l in range(5):
+            np.testing.assert_allclose(grads[l].permute(0, 3, 1, 2).cpu().numpy(), g["grad%d_%d" % (i, l)], rtol=1e-4, atol=1e-8)
+
+
+def test_ema_golden_and_sgd(cuda):
+    g = golden("ema_weights")
+    s = torch.tensor(np.concatenate([g["s_w"].ravel(), g["s_b"].ravel()]), device=cuda)
+    t = torch.tensor(np.concatenate([g["t_w"].ravel(), g["t_b"].ravel()]), device=cuda)
+    for k in g["steps"]:
+        K().ema_(t, s, R.ema_alpha(int(k), 0.99))
+        ref = np.concatenate([g["t_w_after%d" % k].ravel(), g["t_b_after%d" % k].ravel()])
+        got = t.cpu().numpy()
+        ulp = np.abs(got.view(np.int32).astype(np.int64) - ref.view(np.int32).astype(np.int64))
+        assert ulp.max() <= 2, ulp.max()   # reference add_ may or may not be FMA-contracted
+    # fused SGD(+momentum, wd) + EMA over a 3-tensor arena with padding between tensors
+    gen = torch.Generator().manual_seed(26)
+    sizes = [1000, 37, 4096]
+    begins, total = [], 0
+    for n in sizes:
+        begins.append(total)
+        total += (n + 3) // 4 * 4
+    p = torch.randn(total, generator=gen)
+    tt = torch.randn(total, generator=gen)
+    gr = torch.randn(total, generator=gen)
+    buf = torch.randn(total, generator=gen)
+    hyper = [(0.005, 1e-4, 1), (0.01, 0.0, 1), (0.005, 1e-4, 0)]
+    segs = K().make_segments([(b, b + n, lr, wd, tr) for (b, n, (lr, wd, tr)) in zip(begins, sizes, hyper)], cuda)
+    for first in (True, False):
+        pd, td, bd = p.to(cuda), tt.to(cuda), buf.to(cuda)
+        K().sgd_ema_(pd, td, gr.to(cuda), bd, segs, 3, 0.9, 0.99, first, 1.0)
+        for b, n, (lr, wd, tr) in zip(begins, sizes, hyper):
+            sl = slice(b, b + n)
+            if tr:
+                p_ref, b_ref = R.sgd_ref(p[sl], gr[sl], buf[sl], lr, 0.9, wd, first)
+            else:
+                p_ref, b_ref = p[sl], buf[sl]
+            t_ref = R.ema_ref(tt[sl], p_ref, 0.99)
+            torch.testing.assert_close(pd[sl].cpu(), p_ref, rtol=1e-6, atol=1e-7)
+            torch.testing.assert_close(td[sl].cpu(), t_ref, rtol=1e-6, atol=1e-7)
+            if tr:
+                torch.testing.assert_close(bd[sl].cpu(), b_ref, rtol=1e-6, atol=1e-7)
+
+
+# ------------------------------------------------------------------------------ elementwise
+def test_elementwise_vs_torch(cuda):
+    import torch.nn.functional as Fn
+    gen = torch.Generator().manual_seed(27)
+    x = torch.randn(2, 37, 50, 64, generator=gen).to(cuda)  # NHWC
+    xn = x.permute(0, 3, 1, 2)
+    assert torch.equal(K().maxpool3x3s2(x), Fn.max_pool2d(xn, 3, 2, 1).permute(0, 2, 3, 1))
+    assert torch.equal(K().subsample2(x), Fn.max_pool2d(xn, 1, 2, 0).permute(0, 2, 3, 1))
+    top = torch.randn(2, 10, 12, 16, generator=gen).to(cuda)
+    lat = torch.randn(2, 20, 24, 16, generator=gen).to(cuda)
+    ref = lat.permute(0, 3, 1, 2) + Fn.interpolate(top.permute(0, 3, 1, 2), scale_factor=2, mode="nearest")
+    assert torch.equal(K().upsample2_add(lat, top), ref.permute(0, 2, 3, 1))
+    go = torch.randn(2, 20, 24, 16, generator=gen).to(cuda)
+    gt = torch.zeros_like(top)
+    K().upsample2_backward_(go, gt)
+    torch.testing.assert_close(gt, go.view(2, 10, 2, 12, 2, 16).sum((2, 4)))
+    gx = torch.zeros_like(x)
+    gy = torch.randn(2, 19, 25, 64, generator=gen).to(cuda)
+    K().subsample2_backward_(gy, gx)
+    assert torch.equal(gx[:, ::2, ::2], gy) and float(gx.abs().sum()) == float(gy.abs().sum())
+    y = torch.randn(2, 9, 11, 32, generator=gen).to(cuda)
+    gyy = torch.randn(2, 9, 11, 32, generator=gen).to(cuda)
+    sc = torch.rand(32, generator=gen).to(cuda) + 0.5
+    torch.testing.assert_close(K().bn_relu_backward(gyy, y, sc, True), gyy * (y > 0) * sc)
+    a = torch.randn(3, 5, 17, 33, generator=gen).to(cuda)
+    assert torch.equal(K().nchw_to_nhwc(a), a.permute(0, 2, 3, 1).contiguous())
+    assert torch.equal(K().nhwc_to_nchw(K().nchw_to_nhwc(a)), a)
+
+
+# ------------------------------------------------------------------------------------ convs
+CONV_CASES = [
+    # B, H, W, Cin, Cout, k, stride, pad
+    (2, 25, 25, 64, 64, 1, 1, 0),
+    (2, 50, 50, 256, 64, 1, 1, 0),
+    (1, 56, 40, 64, 64, 3, 1, 1),
+    (2, 25, 25, 128, 128, 3, 1, 1),
+    (2, 13, 13, 256, 256, 3, 1, 1),
+    (2, 50, 50, 256, 512, 1, 2, 0),
+    (2, 25, 27, 512, 128, 1, 2, 0),
+    (3, 14, 14, 256, 256, 3, 1, 1),
+    (1, 20, 20, 256, 32, 1, 1, 0),
+    (2, 9, 9, 2048, 256, 1, 1, 0),
+]
+
+
+def _conv_inputs(case, gen, cuda):
+    B, H, W, Ci, Co, k, s, p = case
+    x = torch.randn(B, Ci, H, W, generator=gen)
+    w = torch.randn(Co, Ci, k, k, generator=gen) / (Ci * k * k) ** 0.5
+    return x, w
+
+
+def _rel(a, b):
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-20))
+
+
+@pytest.mark.parametrize("impl", ["simt", "tc"])
+def test_conv_fprop(cuda, impl):
+    import torch.nn.functional as Fn
+    kn = K()
+    gen = torch.Generator().manual_seed(28)
+    for case in CONV_CASES:
+        B, H, W, Ci, Co, k, s, p = case
+        x, w = _conv_inputs(case, gen, cuda)
+        scale = torch.rand(Co, generator=gen) + 0.5
+        bias = torch.randn(Co, generator=gen)
+        shape = kn.conv_shape(B, H, W, Ci, Co, k, s, p)
+        res = torch.randn(B, Co, shape.out_h, shape.out_w, generator=gen)
+        xd = x.permute(0, 2, 3, 1).contiguous().to(cuda)
+        wd = w.permute(0, 2, 3, 1).contiguous().to(cuda)
+        rd = res.permute(0, 2, 3, 1).contiguous().to(cuda)
+        y = kn.conv_fprop(xd, wd, shape, scale.to(cuda), bias.to(cuda), rd, True,
+                          kn.CONV_SIMT if impl == "simt" else kn.CONV_TCGEN05)
+        y = y.permute(0, 3, 1, 2).cpu()
+        exact = R.conv_bn_act_ref(x, w, scale, bias, res, True, s, p, operands="fp32")
+        if impl == "simt":
+            assert _rel(y, exact) < 1e-5, (case, _rel(y, exact))
+        else:
+            trunc = R.conv_bn_act_ref(x, w, scale, bias, res, True, s, p, operands="tf32")
+            e_t, e_x = _rel(y, trunc), _rel(y, exact)
+            print("conv_fprop tc", case, "vs tf32-truncated %.2e  vs fp32 %.2e" % (e_t, e_x))
+            assert e_x < 3e-3, (case, e_x)          # TF32 operands, fp32 accumulate
+            assert e_t < 1e-4 or e_x < 1e-3, (case, e_t, e_x)
+        # no-epilogue variant
+        y2 = kn.conv_fprop(xd, wd, shape, None, None, None, False,
+                           kn.CONV_SIMT if impl == "simt" else kn.CONV_TCGEN05).permute(0, 3, 1, 2).cpu()
+        assert _rel(y2, Fn.conv2d(x, w, None, s, p)) < (1e-5 if impl == "simt" else 3e-3)
+
+
+@pytest.mark.parametrize("impl", ["simt", "tc"])
+def test_conv_dgrad_wgrad(cuda, impl):
+    import torch.nn.functional as Fn
+    kn = K()
+    gen = torch.Generator().manual_seed(29)
+    flag = kn.CONV_SIMT if impl == "simt" else kn.CONV_TCGEN05
+    tol = 1e-5 if impl == "simt" else 3e-3
+    for case in CONV_CASES:
+        B, H, W, Ci, Co, k, s, p = case
+        x, w = _conv_inputs(case, gen, cuda)
+        shape = kn.conv_shape(B, H, W, Ci, Co, k, s, p)
+        dy = torch.randn(B, Co, shape.out_h, shape.out_w, generator=gen)
+        xr = x.double().requires_grad_(True)
+        wr = w.double().requires_grad_(True)
+        Fn.conv2d(xr, wr, None, s, p).backward(dy.double())
+        xd = x.permute(0, 2, 3, 1).contiguous().to(cuda)
+        wd = w.permute(0, 2, 3, 1).contiguous().to(cuda)
+        dyd = dy.permute(0, 2, 3, 1).contiguous().to(cuda)
+        dx = kn.conv_dgrad(dyd, wd, shape, flag).permute(0, 3, 1, 2).cpu()
+        assert _rel(dx, xr.grad.float()) < tol, ("dgrad", case, _rel(dx, xr.grad.float()))
+        dw, db = kn.conv_wgrad(xd, dyd, shape, True, flag)
+        dw = dw.permute(0, 3, 1, 2).cpu()
+        assert _rel(dw, wr.grad.float()) < tol, ("wgrad", case, _rel(dw, wr.grad.float()))
+        assert _rel(db.cpu(), dy.sum((0, 2, 3))) < 1e-5
+
+
+def test_conv_stem_7x7_simt(cuda):
+    import torch.nn.functional as Fn
+    kn = K()
+    gen = torch.Generator().manual_seed(30)
+    x = torch.randn(2, 3, 64, 96, generator=gen)
+    w = torch.randn(64, 3, 7, 7, generator=gen) * 0.1
+    shape = kn.conv_shape(2, 64, 96, 3, 64, 7, 2, 3)
+    y = kn.conv_fprop(x.permute(0, 2, 3, 1).contiguous().to(cuda), w.permute(0, 2, 3, 1).contiguous().to(cuda), shape,
+                      None, None, None, True, kn.CONV_AUTO)
+    assert _rel(y.permute(0, 3, 1, 2).cpu(), torch.relu(Fn.conv2d(x, w, None, 2, 3))) < 1e-5
+
+
+def test_conv_full_size_tc_vs_simt(cuda):
+    """BASELINE-size layer (fpn_layer1: 2x200x200x256 -> 256, 3x3): tensor-core path vs the fp32 SIMT kernel."""
+    kn = K()
+    gen = torch.Generator(device="cuda").manual_seed(31)
+    x = torch.randn(2, 200, 200, 256, generator=gen, device=cuda)
+    w = torch.randn(256, 3, 3, 256, generator=gen, device=cuda) / 48
+    b = torch.randn(256, generator=gen, device=cuda)
+    shape = kn.conv_shape(2, 200, 200, 256, 256, 3, 1, 1)
+    y_tc = kn.conv_fprop(x, w, shape, None, b, None, False, kn.CONV_TCGEN05)
+    y_ref = kn.conv_fprop(x, w, shape, None, b, None, False, kn.CONV_SIMT)
+    assert _rel(y_tc, y_ref) < 3e-3
+    # linearity (size-independent property): conv(2x) - 2 conv(x) == -bias
+    y2 = kn.conv_fprop(2 * x, w, shape, None, b, None, False, kn.CONV_TCGEN05)
+    assert _rel(y2 - 2 * y_tc, (-b).expand_as(y_tc)) < 1e-3

@@ -181,6 +181,22 @@ int mmt_mgd_finalize_f32(const float* partials /*[n_levels][n_views]*/,
                          int channels, float* loss_out, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Mask-target rasterisation — replaces the per-positive-ROI HOST loop `project_masks_on_boxes`
+ * (modeling/roi_heads/mask_head/loss.py:37-75): Polygons.crop / .resize / .convert("mask")
+ * (structures/segmentation_mask.py:94-137) -> pycocotools rleFrPoly + rleMerge + rleDecode
+ * (pycoco/maskApi.c:166-206, :53-75, :47-51).  Bit-exact (integer/double arithmetic restated).
+ *   poly_xy            flat (x,y) fp32 vertices of every polygon of the image, image coordinates
+ *   poly_offsets       [n_polygons+1] int32, vertex offsets into poly_xy/2
+ *   inst_poly_offsets  [n_instances+1] int32, polygon ranges of each ground-truth instance
+ *   roi_boxes [n_rois,4] xyxy fp32 (the positive proposals), roi_instance [n_rois] int32 (matched instance)
+ *   masks_out [n_rois, mask_size, mask_size] fp32 in {0,1}.  All pointers are DEVICE pointers.
+ * ------------------------------------------------------------------------------------------ */
+int mmt_rasterize_polygons_f32(const float* poly_xy, const int* poly_offsets,
+                               const int* inst_poly_offsets, const float* roi_boxes,
+                               const int* roi_instance, int n_rois, int mask_size, float* masks_out,
+                               void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Teacher EMA + student SGD — replaces `MTtrainer.update_teacher`
  * (engine/MTtrainer.py:277-281; 264 launches) and torch.optim.SGD as configured by
  * solver/build.py:5-23 (one param group per tensor; bias lr x2, weight decay 0).

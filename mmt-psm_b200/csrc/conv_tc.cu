@@ -379,8 +379,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
           tc_fence_after();
 #pragma unroll
           for (int k = 0; k < 4; ++k) {  // 4 x 8 pixels
-            const uint64_t da = umma_desc_mnmajor_sw128(L.a[stage] + k * 1024, 4096);
-            const uint64_t db = umma_desc_mnmajor_sw128(L.b[stage] + k * 1024, 4096);
+            const uint64_t da = umma_desc_mnmajor_sw128_32b(L.a[stage] + k * 1024, 4096);
+            const uint64_t db = umma_desc_mnmajor_sw128_32b(L.b[stage] + k * 1024, 4096);
             mma_tf32_ss(d_tmem, da, db, idesc, (pt > pb || k) ? 1u : 0u);
           }
           mma_commit(L.empty[stage]);
@@ -485,7 +485,8 @@ struct View4 {  // channels-innermost view: dims (c, w, h, n), element strides o
   long long sw, sh, sn;
 };
 
-int make_map(CUtensorMap* m, const View4& v, int box_c, int box_w, int box_h, const char* what) {
+int make_map(CUtensorMap* m, const View4& v, int box_c, int box_w, int box_h, const char* what,
+             CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return mmt::fail(MMT_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t dims[4] = {(cuuint64_t)v.c, (cuuint64_t)v.w, (cuuint64_t)v.h, (cuuint64_t)v.n};
@@ -495,7 +496,7 @@ int make_map(CUtensorMap* m, const View4& v, int box_c, int box_w, int box_h, co
   if (((uintptr_t)v.base & 15) || (strides[0] & 15) || (strides[1] & 15) || (strides[2] & 15))
     return mmt::fail(MMT_ERR_INVALID_ARGUMENT, "%s: tensor must be 16-byte aligned with 16-byte strides", what);
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(v.base), dims, strides, box, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return mmt::fail(MMT_ERR_CUDA, "%s: cuTensorMapEncodeTiled failed (%d)", what, (int)r);
   return MMT_OK;
@@ -703,8 +704,9 @@ int conv_wgrad_tc(const float* x, const float* dy, float* dw, float* dbias, cons
   int TW, TH;
   pick_patch(vdy.w, vdy.h, 32, TW, TH);
   CUtensorMap tmDY, tmX, tmDW;
-  if (int rc = make_map(&tmDY, vdy, 32, TW, TH, "wgrad dy")) return rc;
-  if (int rc = make_map(&tmX, vx, 32, TW, TH, "wgrad x")) return rc;
+  // MN-major TF32 operands only exist in the "128B swizzle, 32-byte atom" layout (4-row period)
+  if (int rc = make_map(&tmDY, vdy, 32, TW, TH, "wgrad dy", CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return rc;
+  if (int rc = make_map(&tmX, vx, 32, TW, TH, "wgrad x", CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return rc;
   const long long Ktot = (long long)s.k_h * s.k_w * s.in_c;
   if (int rc = make_map_2d(&tmDW, dw, Ktot, s.out_c, Ktot, 32, 128, "wgrad dw")) return rc;
   MMT_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)s.out_c * Ktot, stream));

@@ -155,16 +155,18 @@ __device__ __forceinline__ uint64_t umma_desc_kmajor_sw128(uint32_t addr) {
   d |= (uint64_t)2 << 61;                         // SWIZZLE_128B
   return d;
 }
-// MN-major operand tile: 128-byte rows hold 32 consecutive M/N elements for ONE k; 8 k-rows form
-// a 1024-byte swizzle atom; atoms along K are contiguous (SBO = 1024); the next group of 32 M/N
-// elements starts `lbo_bytes` further (LBO).
-__device__ __forceinline__ uint64_t umma_desc_mnmajor_sw128(uint32_t addr, uint32_t lbo_bytes) {
+// MN-major TF32 operand tile.  The only legal layout for MN-major 32-bit operands is
+// SWIZZLE_128B_BASE32B (layout type 1; what TMA writes with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B):
+// 128-byte rows hold 32 consecutive M/N elements for ONE k, 32-byte chunks are XOR-swizzled with
+// (row % 4); 4 k-rows form a 512-byte atom, atoms along K are contiguous (SBO = 512), and the next
+// group of 32 M/N elements starts `lbo_bytes` further (LBO).
+__device__ __forceinline__ uint64_t umma_desc_mnmajor_sw128_32b(uint32_t addr, uint32_t lbo_bytes) {
   uint64_t d = 0;
   d |= (uint64_t)((addr & 0x3FFFF) >> 4);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)(512 >> 4) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)1 << 61;
   return d;
 }
 // kind::tf32, fp32 accumulate.  a_mn / b_mn: 1 = MN-major operand, 0 = K-major.

@@ -113,8 +113,8 @@ def roi_align_backward(grad, rois, spatial_scale, pooled_h, pooled_w, batch, cha
     if not nhwc:
         grad = grad.contiguous()
     rois = _f32c(rois)
-    gin = torch.zeros((batch, channels, height, width), dtype=torch.float32, device=grad.device,
-                      memory_format=torch.channels_last if nhwc else torch.contiguous_format)
+    gin = torch.empty((batch, channels, height, width), dtype=torch.float32, device=grad.device,
+                      memory_format=torch.channels_last if nhwc else torch.contiguous_format).zero_()
     K = rois.shape[0]
     if K == 0:
         return gin
@@ -296,6 +296,20 @@ def mgd_finalize(partials, mask_sums, n_levels, n_views, channels):
     check(L.mmt_mgd_finalize_f32(_p(partials), _p(mask_sums), n_levels, n_views, channels, _p(loss), _stream()),
           "mgd_finalize")
     return loss
+
+
+def rasterize_polygons(packed, roi_boxes, roi_instance, mask_size):
+    """packed = SegmentationMask.packed(device); roi_boxes [K,4]; roi_instance [K] -> [K,M,M] fp32 {0,1}."""
+    xy, poly_off, inst_off = packed
+    _need_cuda(xy, poly_off, inst_off, roi_boxes, roi_instance)
+    L = _l.lib()
+    roi_boxes = _f32c(roi_boxes)
+    roi_instance = roi_instance.to(torch.int32).contiguous()
+    K = roi_boxes.shape[0]
+    out = torch.empty((K, mask_size, mask_size), dtype=torch.float32, device=roi_boxes.device)
+    check(L.mmt_rasterize_polygons_f32(_p(xy), _p(poly_off), _p(inst_off), _p(roi_boxes), _p(roi_instance), K,
+                                       mask_size, _p(out), _stream()), "rasterize_polygons")
+    return out
 
 
 # ------------------------------------------------------------------------------- EMA / SGD

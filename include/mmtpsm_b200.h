@@ -197,6 +197,18 @@ int mmt_rasterize_polygons_f32(const float* poly_xy, const int* poly_offsets,
                                void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Teacher mask paste-and-sum — replaces `Masker.forward_single_image` / `paste_mask_in_image`
+ * (modeling/roi_heads/mask_head/inference.py:169-231; one CPU canvas per detection) followed by
+ * `.sum(0)` (modeling/detector/generalized_rcnn.py:129-132): integral_out[b,y,x] = number of
+ * detections of image b whose pasted (padding 1, bilinear, > threshold) mask covers pixel (y,x).
+ *   mask_probs [n_dets, M, M] fp32, boxes [n_dets,4] xyxy, image_index [n_dets] int32 (DEVICE)
+ *   integral_out [n_images, im_h, im_w] fp32 — overwritten.
+ * ------------------------------------------------------------------------------------------ */
+int mmt_paste_masks_sum_f32(const float* mask_probs, const float* boxes, const int* image_index,
+                            int n_dets, int mask_size, int n_images, int im_h, int im_w,
+                            float threshold, float* integral_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Teacher EMA + student SGD — replaces `MTtrainer.update_teacher`
  * (engine/MTtrainer.py:277-281; 264 launches) and torch.optim.SGD as configured by
  * solver/build.py:5-23 (one param group per tensor; bias lr x2, weight decay 0).

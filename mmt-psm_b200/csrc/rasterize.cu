@@ -142,3 +142,71 @@ extern "C" int mmt_rasterize_polygons_f32(const float* poly_xy, const int* poly_
                                                              roi_instance, mask_size, masks_out);
   return mmt::check_launch("rasterize_polygons");
 }
+
+// ------------------------------------------------------------------------------------------------
+// Teacher mask paste-and-sum.
+//
+// Replaces the CPU loop of maskrcnn_benchmark/modeling/roi_heads/mask_head/inference.py:169-231
+// (`Masker.forward_single_image` -> `paste_mask_in_image` per detection: pad the MxM probability map by 1,
+// expand the box by (M+2)/M, truncate to int32, bilinear-resize (align_corners=False) to the box, threshold,
+// paste into an im_h x im_w uint8 canvas) followed by `.sum(0)` over detections
+// (modeling/detector/generalized_rcnn.py:129-132).  One thread per pasted pixel; the only consumer is the
+// integral foreground map, so the canvases are never materialised.
+namespace {
+
+__global__ void __launch_bounds__(256) paste_sum_kernel(const float* __restrict__ probs,
+                                                        const float* __restrict__ boxes,
+                                                        const int* __restrict__ img_idx, int M, int im_h,
+                                                        int im_w, float thresh, float* __restrict__ out) {
+  const int d = blockIdx.y;
+  const float* b = boxes + d * 4;
+  // expand_boxes (inference.py:94-110), fp32 like torch; scale = float(M + 2) / M is a python double
+  const float scale = (float)((double)(M + 2) / (double)M);
+  float w_half = __fmul_rn(__fsub_rn(b[2], b[0]), .5f), h_half = __fmul_rn(__fsub_rn(b[3], b[1]), .5f);
+  const float x_c = __fmul_rn(__fadd_rn(b[2], b[0]), .5f), y_c = __fmul_rn(__fadd_rn(b[3], b[1]), .5f);
+  w_half = __fmul_rn(w_half, scale);
+  h_half = __fmul_rn(h_half, scale);
+  const int bx0 = (int)__fsub_rn(x_c, w_half), bx1 = (int)__fadd_rn(x_c, w_half);
+  const int by0 = (int)__fsub_rn(y_c, h_half), by1 = (int)__fadd_rn(y_c, h_half);
+  const int w = max(bx1 - bx0 + 1, 1), h = max(by1 - by0 + 1, 1);
+  const int x_0 = max(bx0, 0), x_1 = min(bx1 + 1, im_w), y_0 = max(by0, 0), y_1 = min(by1 + 1, im_h);
+  const int rw = x_1 - x_0, rh = y_1 - y_0;
+  if (rw <= 0 || rh <= 0) return;
+  const int P = M + 2;
+  const float sx = (float)P / (float)w, sy = (float)P / (float)h;  // area_pixel_compute_scale
+  const float* src = probs + (long long)d * M * M;
+  float* dst = out + (long long)img_idx[d] * im_h * im_w;
+  auto padded = [&](int yy, int xx) -> float {
+    return (yy >= 1 && yy <= M && xx >= 1 && xx <= M) ? __ldg(src + (yy - 1) * M + (xx - 1)) : 0.f;
+  };
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < rw * rh; i += gridDim.x * blockDim.x) {
+    const int px = x_0 + i % rw, py = y_0 + i / rw;
+    const int ox = px - bx0, oy = py - by0;  // pixel of the resized mask
+    float fx = sx * ((float)ox + .5f) - .5f, fy = sy * ((float)oy + .5f) - .5f;
+    fx = fx < 0.f ? 0.f : fx;
+    fy = fy < 0.f ? 0.f : fy;
+    const int ix0 = (int)fx, iy0 = (int)fy;
+    const int ix1 = ix0 + (ix0 < P - 1 ? 1 : 0), iy1 = iy0 + (iy0 < P - 1 ? 1 : 0);
+    const float lx1 = fx - (float)ix0, ly1 = fy - (float)iy0, lx0 = 1.f - lx1, ly0 = 1.f - ly1;
+    const float v = ly0 * (lx0 * padded(iy0, ix0) + lx1 * padded(iy0, ix1)) +
+                    ly1 * (lx0 * padded(iy1, ix0) + lx1 * padded(iy1, ix1));
+    if (v > thresh) atomicAdd(dst + (long long)py * im_w + px, 1.f);
+  }
+}
+
+}  // namespace
+
+extern "C" int mmt_paste_masks_sum_f32(const float* mask_probs, const float* boxes, const int* image_index,
+                                       int n_dets, int mask_size, int n_images, int im_h, int im_w,
+                                       float threshold, float* integral_out, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  MMT_REQUIRE(n_dets >= 0 && mask_size > 0 && n_images > 0 && im_h > 0 && im_w > 0, "paste_masks: bad sizes");
+  MMT_REQUIRE(integral_out != nullptr, "paste_masks: null output");
+  MMT_CUDA(cudaMemsetAsync(integral_out, 0, sizeof(float) * (size_t)n_images * im_h * im_w, stream));
+  if (n_dets == 0) return MMT_OK;
+  MMT_REQUIRE(mask_probs && boxes && image_index, "paste_masks: null pointer");
+  MMT_REQUIRE(n_dets <= 65535, "paste_masks: too many detections");
+  paste_sum_kernel<<<dim3(16, n_dets), 256, 0, stream>>>(mask_probs, boxes, image_index, mask_size, im_h, im_w,
+                                                        threshold, integral_out);
+  return mmt::check_launch("paste_masks_sum");
+}

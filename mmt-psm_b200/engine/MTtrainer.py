@@ -1,0 +1,176 @@
+"""Mean-teacher training loop — mirrors reference engine/MTtrainer.py:16-284 (`MTtrainer.train`,
+`forward_source`, `forward_unlabel`, `update_teacher`, `weight_sum_losses`, `reduce_loss_dict`).
+
+One iteration = supervised student forward -> (no-grad) teacher forward on K colour views x {orig, flip} ->
+student forward on the unlabeled view (PSM + MGD) -> weighted sum -> backward -> [NCCL all-reduce of the flat
+student gradient arena] -> ONE fused SGD + teacher-EMA launch.  Data parallelism is the north star's addition
+(the reference never wraps the student): every rank holds a student+teacher replica, gradients are
+summed with a single `all_reduce` over the flat fp32 arena and scaled by 1/world inside the optimizer kernel;
+teachers stay bit-identical across ranks without any traffic because EMA is a function of the synced student."""
+import datetime
+import logging
+import time
+
+import torch
+import torch.distributed as dist
+
+from ..utils.comm import get_world_size
+from ..utils.miscellaneous import sigmoid_rampdown, sigmoid_rampup
+
+
+def reduce_loss_dict(loss_dict):
+    """Logging-only reduction to rank 0 (reference MTtrainer.py:16-41)."""
+    world = get_world_size()
+    if world < 2:
+        return loss_dict
+    with torch.no_grad():
+        names = sorted(loss_dict.keys())
+        vals = torch.stack([loss_dict[k].reshape(()) for k in names], dim=0)
+        dist.reduce(vals, dst=0)
+        if dist.get_rank() == 0:
+            vals /= world
+        return {k: v for k, v in zip(names, vals)}
+
+
+def weight_sum_losses(loss_dict, step, rampup_length, rampdown_length, total_length, l=1, balanced=None, start_mt=1000):
+    """Consistency-loss ramp and per-term weights (reference MTtrainer.py:67-109; note the ramp-DOWN also uses
+    `rampup_length` as its length, :92)."""
+    if 0 < (step - start_mt) < rampup_length:
+        weight = l * sigmoid_rampup(step - start_mt, rampup_length)
+    elif (total_length - step) < rampdown_length:
+        weight = l * sigmoid_rampdown(total_length - step, rampup_length)
+    else:
+        weight = l
+    out = {k: (weight * v if "mt" in k else v) for k, v in loss_dict.items()}
+    for k in list(out):
+        if balanced is not None and k in balanced:
+            out[k] = out[k] * balanced[k]
+    return out
+
+
+class MTtrainer(object):
+    def __init__(self, model_s, model_t, data_loader, optimizer, scheduler, ckpt_s, ckpt_t, checkpoint_period, cfg):
+        self.cfg = cfg
+        self.logger = logging.getLogger("maskrcnn_benchmark.trainer")
+        self.scheduler = scheduler
+        self.student, self.teacher = model_s, model_t
+        self.student_bs, self.teacher_bs = cfg.MT.AUG_S, cfg.MT.AUG_K
+        self.device = next(model_s.parameters()).device
+        self.checkpoint_period = checkpoint_period
+        self.ckpt_s, self.ckpt_t = ckpt_s, ckpt_t
+        self.optimizer = optimizer
+        self.lambda_value, self.alpha = cfg.MT.LAMBDA, cfg.MT.ALPHA
+        self.rampup_step, self.rampdown_step, self.start_mt = cfg.MT.RAMPUP_STEP, cfg.MT.RAMPDOWN_STEP, cfg.MT.START_MT
+        self.balanced_weight = {"mt_classifier": cfg.MT.CLS_LOSS, "nms_loss": cfg.MODEL.RELATION_NMS.LOSS,
+                                "mt_fg_loss": cfg.MT.FG_HINT}
+        self.dataloader_s = data_loader["source"] if data_loader else None
+        self.dataloader_u = data_loader.get("no_label") if (data_loader and cfg.DATASETS.NO_LABEL) else None
+        self._iter_u = None
+        self.max_iter = len(self.dataloader_s) if self.dataloader_s is not None else cfg.SOLVER.MAX_ITER
+        self.start_iter = 0
+        self.n_step_unlabel = cfg.MT.N_STEP_UNLABEL
+        self.world = get_world_size()
+        self.last_losses = None
+
+    def weight_sum_loss(self, loss_dict, step):
+        return weight_sum_losses(loss_dict, step, self.rampup_step, self.rampdown_step, self.max_iter,
+                                 l=self.lambda_value, balanced=self.balanced_weight, start_mt=self.start_mt)
+
+    # ---- forward passes -----------------------------------------------------------------------
+    def forward_source(self, image, target):
+        image = image.to(self.device)
+        target = [t.to(self.device) for t in target]
+        return self.student(image, target)
+
+    def _next_unlabeled(self):
+        # the reference builds a NEW loader iterator (worker respawn) every iteration (MTtrainer.py:252);
+        # a persistent iterator yields the same stream of batches without the respawn
+        if self._iter_u is None:
+            self._iter_u = iter(self.dataloader_u)
+        try:
+            return next(self._iter_u)
+        except StopIteration:
+            self._iter_u = iter(self.dataloader_u)
+            return next(self._iter_u)
+
+    def forward_unlabel(self, data_u_list=None):
+        unlabel, loss_dict = [], {}
+        for _ in range(self.n_step_unlabel):
+            if data_u_list is None:
+                data_u_list, _ = self._next_unlabeled()
+            teacher_list = [f.to(self.device) for f in data_u_list[:self.teacher_bs]]
+            student = [s.to(self.device) for s in data_u_list[-self.student_bs:]]
+            with torch.no_grad():
+                try:
+                    teacher_results = self.teacher.forward_teacher(teacher_list)
+                except ValueError as e:  # the reference swallows everything; only "no boxes" is expected
+                    if "boxes available" not in str(e):
+                        raise
+                    self.logger.info("teacher produced no boxes for one image, skip this pair")
+                    data_u_list = None
+                    continue
+            unlabel.append(self.student.forward_student(student, teacher_results))
+            data_u_list = None
+        if not unlabel:
+            return loss_dict
+        keys = unlabel[0].keys()
+        return {k: sum(d[k] for d in unlabel) / len(unlabel) for k in keys}
+
+    def update_teacher(self, step):
+        alpha = min(1 - 1 / (step + 1), self.alpha)
+        self.optimizer.ema_only(alpha)
+
+    # ---- one iteration ------------------------------------------------------------------------
+    def train_step(self, iteration, data_s, target_s, data_u_list=None):
+        loss_dict = self.forward_source(data_s, target_s)
+        if iteration > self.start_mt and self.lambda_value > 0 and self.cfg.DATASETS.NO_LABEL:
+            loss_dict.update(self.forward_unlabel(data_u_list))
+        self.scheduler.step()
+        losses_dict = self.weight_sum_loss(loss_dict, iteration)
+        losses = sum(v for v in losses_dict.values())
+        self.optimizer.zero_grad()
+        losses.backward()
+        if self.world > 1:
+            dist.all_reduce(self.optimizer.flat_g)  # one NCCL all-reduce over the whole student gradient arena
+        ema = None
+        if self.lambda_value > 0 and iteration > (self.start_mt - 10):
+            ema = min(1 - 1 / (iteration - (self.start_mt - 10) + 1), self.alpha)
+        self.optimizer.step(ema_alpha=ema, grad_scale=1.0 / self.world)
+        self.last_losses = losses_dict
+        return losses_dict, losses
+
+    def train(self):
+        from ..utils.metric_logger import MetricLogger
+        meters = MetricLogger(delimiter="  ")
+        self.student.train()
+        self.teacher.eval()
+        t0 = end = time.time()
+        for iteration, (data_s, target_s, _) in enumerate(self.dataloader_s, self.start_iter):
+            losses_dict, losses = self.train_step(iteration, data_s, target_s)
+            if iteration % 20 == 0 or iteration == self.max_iter:  # the only host syncs of the loop
+                red = reduce_loss_dict(losses_dict)
+                meters.update(loss=sum(v for v in red.values()), **red)
+                meters.update(time=(time.time() - end) / (20 if iteration else 1))
+                end = time.time()
+                eta = str(datetime.timedelta(seconds=int(meters.time.global_avg * (self.max_iter - iteration))))
+                self.logger.info("eta: %s  iter: %d  %s  lr: %.6f  max mem: %.0f" % (
+                    eta, iteration, str(meters), self.optimizer.param_groups[0]["lr"],
+                    torch.cuda.max_memory_allocated() / 1024.0 / 1024.0))
+            if iteration % self.checkpoint_period == 0:
+                self.save_model(iteration)
+            if iteration == self.max_iter:
+                self.save_model(final=True)
+        total = time.time() - t0
+        self.logger.info("Total training time: %s (%.4f s / it)" % (datetime.timedelta(seconds=total), total / max(self.max_iter, 1)))
+
+    def save_model(self, iteration=0, final=False):
+        if self.ckpt_s is None:
+            return
+        if iteration > 0 and not final:
+            self.ckpt_s.save("model_{:07d}".format(iteration))
+            if iteration > self.start_mt:
+                self.ckpt_t.save("t_model_{:07d}".format(iteration))
+        if final:
+            self.ckpt_s.save("model_final")
+            if iteration > self.start_mt:
+                self.ckpt_t.save("t_model_final")

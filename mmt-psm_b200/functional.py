@@ -1,0 +1,179 @@
+"""Autograd bindings of the CUDA kernels (NHWC fp32 activations, OHWI filters).
+
+Each `torch.autograd.Function` below is one fused forward launch and, in backward, the matching dgrad /
+wgrad / scatter launches of libmmtpsm_b200 — there is no PyTorch fallback inside any of them.
+Layout conventions:  activations [B,H,W,C] dense; filters [Co,kh,kw,Ci] dense; ROI features [K,P,P,C].
+"""
+import torch
+
+from . import kernels as K
+
+
+class _ConvBnAct(torch.autograd.Function):
+    """y = act(conv(x, w) * scale + bias + residual).
+
+    Replaces Conv2d -> FrozenBatchNorm2d -> (+identity) -> relu_ (reference layers/misc.py:30-43,
+    layers/batch_norm.py:19-24, modeling/backbone/resnet.py:254-275) and Conv2d(+bias)(+relu) of the FPN /
+    RPN / mask heads.  `scale` is a frozen per-channel multiplier (no gradient); `bias` may be a learnable
+    conv bias (gradient = per-channel sum) or a frozen BN shift (requires_grad False)."""
+
+    @staticmethod
+    def forward(ctx, x, w, scale, bias, residual, relu, stride, pad):
+        B, H, W, Ci = x.shape
+        Co, k = w.shape[0], w.shape[1]
+        shape = K.conv_shape(B, H, W, Ci, Co, k, stride, pad)
+        y = K.conv_fprop(x, w, shape, scale, bias, residual, relu)
+        ctx.shape, ctx.relu = shape, relu
+        ctx.has_res = residual is not None
+        ctx.save_for_backward(x, w, scale, y if relu else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w, scale, y = ctx.saved_tensors
+        shape = ctx.shape
+        gy = gy.contiguous()
+        g_res = K.bn_relu_backward(gy, y, None, True) if ctx.relu else gy      # d/d(pre-activation)
+        g_conv = K.bn_relu_backward(g_res, None, scale, False) if scale is not None else g_res
+        need_x, need_w, _, need_b, need_r = ctx.needs_input_grad[:5]
+        dx = K.conv_dgrad(g_conv, w, shape) if need_x else None
+        dw = db = None
+        if need_w or need_b:
+            dw, db = K.conv_wgrad(x, g_conv, shape, want_dbias=need_b)
+        return dx, (dw if need_w else None), None, db, (g_res if (need_r and ctx.has_res) else None), None, None, None
+
+
+def conv_bn_act(x, w, scale=None, bias=None, residual=None, relu=False, stride=1, pad=0):
+    return _ConvBnAct.apply(x, w, scale, bias, residual, relu, stride, pad)
+
+
+def linear(x, w, bias=None, relu=False):
+    """x [N,K] @ w[O,K]^T (+bias)(+relu) on the conv engine: a 1x1 convolution over N 'pixels'.
+    Replaces nn.Linear of the box head (reference roi_box_feature_extractors.py:97-98,119-121;
+    roi_box_predictors.py:39-40)."""
+    N, Kd = x.shape
+    if N == 0:
+        return x.new_zeros((0, w.shape[0]))
+    y = conv_bn_act(x.reshape(1, 1, N, Kd), w.reshape(w.shape[0], 1, 1, Kd), None, bias, None, relu, 1, 0)
+    return y.reshape(N, w.shape[0])
+
+
+class _UpsampleAdd(torch.autograd.Function):
+    """FPN top-down merge: lateral + nearest_x2(top)  (reference modeling/backbone/fpn.py:57-62)."""
+
+    @staticmethod
+    def forward(ctx, lateral, top):
+        ctx.top_shape = top.shape
+        return K.upsample2_add(lateral, top)
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous()
+        g_top = None
+        if ctx.needs_input_grad[1]:
+            g_top = torch.zeros(ctx.top_shape, dtype=g.dtype, device=g.device)
+            K.upsample2_backward_(g, g_top)
+        return (g if ctx.needs_input_grad[0] else None), g_top
+
+
+upsample_add = _UpsampleAdd.apply
+
+
+class _Subsample2(torch.autograd.Function):
+    """P6 = max_pool2d(P5, 1, 2, 0) = every other pixel (reference modeling/backbone/fpn.py:72-74)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        ctx.in_shape = x.shape
+        return K.subsample2(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        gx = torch.zeros(ctx.in_shape, dtype=g.dtype, device=g.device)
+        K.subsample2_backward_(g.contiguous(), gx)
+        return gx
+
+
+subsample2 = _Subsample2.apply
+
+
+class _FpnRoiAlign(torch.autograd.Function):
+    """All FPN levels in one launch (reference modeling/poolers.py:91-121 + layers/roi_align.py:11-44)."""
+
+    @staticmethod
+    def forward(ctx, rois, levels, scales, pooled, sampling_ratio, *feats):
+        ctx.scales, ctx.pooled, ctx.sr = scales, pooled, sampling_ratio
+        ctx.shapes = [f.shape for f in feats]
+        ctx.save_for_backward(rois, levels)
+        return K.roi_align_fpn_forward(list(feats), scales, rois, levels, pooled, sampling_ratio)
+
+    @staticmethod
+    def backward(ctx, g):
+        rois, levels = ctx.saved_tensors
+        grads = [torch.zeros(s, dtype=g.dtype, device=g.device) for s in ctx.shapes]
+        K.roi_align_fpn_backward(g.contiguous(), ctx.scales, rois, levels, ctx.pooled, ctx.sr, grads)
+        return (None, None, None, None, None) + tuple(grads)
+
+
+def fpn_roi_align(feats, scales, rois, levels, pooled, sampling_ratio):
+    return _FpnRoiAlign.apply(rois, levels, tuple(scales), pooled, sampling_ratio, *feats)
+
+
+class _PsmLoss(torch.autograd.Function):
+    """PSM consistency loss (reference box_head/loss.py:164-237,267-287,311-315) — one launch; the analytic
+    gradient w.r.t. the student logits is produced by the same kernel."""
+
+    @staticmethod
+    def forward(ctx, student_logits, teacher_logits, labels, temperature, sharpen, hard_negative, neg_weight):
+        loss, grad, sel = K.psm_loss(student_logits, teacher_logits, labels, temperature, sharpen, hard_negative,
+                                     neg_weight)
+        ctx.save_for_backward(grad)
+        ctx.mark_non_differentiable(sel)
+        return loss.reshape(()), sel
+
+    @staticmethod
+    def backward(ctx, g, _):
+        (grad,) = ctx.saved_tensors
+        return grad * g, None, None, None, None, None, None
+
+
+def psm_loss(student_logits, teacher_logits, labels, temperature, sharpen, hard_negative, neg_weight):
+    return _PsmLoss.apply(student_logits, teacher_logits, labels, temperature, sharpen, hard_negative, neg_weight)
+
+
+class _MgdLoss(torch.autograd.Function):
+    """MGD masked feature-distillation loss (reference generalized_rcnn.py:243-282) for one student view:
+    per level one pass reads the student map once and all teacher views, emitting the partial sums and the
+    student gradient."""
+
+    @staticmethod
+    def forward(ctx, integral_mask, flip_mask, n_views, *tensors):
+        n_levels = len(tensors) // (n_views + 1)
+        students = tensors[:n_levels]
+        teachers = tensors[n_levels:]  # view-major: teachers[v * n_levels + l]
+        sizes = [(s.shape[1], s.shape[2]) for s in students]
+        masks, sums = K.mgd_masks(integral_mask, sizes)
+        C = students[0].shape[3]
+        partials = torch.zeros((n_levels, n_views), dtype=torch.float32, device=students[0].device)
+        want = any(ctx.needs_input_grad[3:3 + n_levels])
+        grads = []
+        w = 1.0 / (n_levels * n_views)
+        for l in range(n_levels):
+            tv = [teachers[v * n_levels + l] for v in range(n_views)]
+            grads.append(K.mgd_level(students[l], tv, flip_mask, masks[l], sums[l:l + 1], w, partials[l], want))
+        loss = K.mgd_finalize(partials, sums, n_levels, n_views, C)
+        if want:
+            ctx.save_for_backward(*grads)
+        ctx.n_levels, ctx.n_rest = n_levels, len(teachers)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        grads = ctx.saved_tensors
+        return (None, None, None) + tuple(gr * g for gr in grads) + (None,) * ctx.n_rest
+
+
+def mgd_loss(integral_mask, student_levels, teacher_views, flip_mask):
+    """student_levels: list of NHWC maps; teacher_views: list (views) of lists (levels) of NHWC maps (no grad)."""
+    flat = [t for view in teacher_views for t in view]
+    return _MgdLoss.apply(integral_mask, flip_mask, len(teacher_views), *student_levels, *flat)

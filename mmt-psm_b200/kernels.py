@@ -312,6 +312,20 @@ def rasterize_polygons(packed, roi_boxes, roi_instance, mask_size):
     return out
 
 
+def paste_masks_sum(mask_probs, boxes, image_index, n_images, im_h, im_w, threshold=0.5):
+    """mask_probs [D,M,M]; boxes [D,4]; image_index [D] int32 -> integral foreground map [n_images, im_h, im_w]."""
+    _need_cuda(mask_probs, boxes, image_index)
+    L = _l.lib()
+    mask_probs = _f32c(mask_probs)
+    boxes = _f32c(boxes)
+    image_index = image_index.to(torch.int32).contiguous()
+    out = torch.empty((n_images, im_h, im_w), dtype=torch.float32, device=boxes.device)
+    check(L.mmt_paste_masks_sum_f32(_p(mask_probs), _p(boxes), _p(image_index), mask_probs.shape[0],
+                                    mask_probs.shape[-1], n_images, im_h, im_w, float(threshold), _p(out), _stream()),
+          "paste_masks_sum")
+    return out
+
+
 # ------------------------------------------------------------------------------- EMA / SGD
 def ema_(teacher_flat, student_flat, alpha):
     _need_cuda(teacher_flat, student_flat)

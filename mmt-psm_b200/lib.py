@@ -60,6 +60,7 @@ _PROTOS = {
                                   c_int, c_int, c_int, c_float, P, P, Strides4, P]),
     "mmt_mgd_finalize_f32": (c_int, [P, P, c_int, c_int, c_int, P, P]),
     "mmt_rasterize_polygons_f32": (c_int, [P, P, P, P, P, c_int, c_int, P, P]),
+    "mmt_paste_masks_sum_f32": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_float, P, P]),
     "mmt_ema_f32": (c_int, [P, P, c_int64, c_float, P]),
     "mmt_sgd_ema_f32": (c_int, [P, P, P, P, c_int64, P, c_int, c_float, c_float, c_int, c_float, P]),
     "mmt_conv_workspace_bytes": (c_size_t, [POINTER(ConvShape)]),

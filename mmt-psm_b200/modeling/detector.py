@@ -1,0 +1,239 @@
+"""GeneralizedRCNN meta-architecture with the mean-teacher entry points.
+
+Mirrors reference modeling/detector/generalized_rcnn.py:17-282 (`forward`, `forward_teacher`,
+`forward_student`, `extract_aug_feat`, `get_emb_feature`, `fg_hint_loss`) and detectors.py:5-7
+(`build_detection_model(cfg, is_teacher, is_student)`): same signatures, same returned dict keys
+(`result_t`, `class_logit_t`, `embedding`, `seg_mask`, `ffi_boxes`), same loss-dict keys.
+Internally every feature map is NHWC.  Two result-preserving restructurings of the teacher pass:
+  * the K colour views x {orig, h-flip} are ONE batched backbone pass ([2K*B,3,H,W]) instead of 2K passes;
+  * the coarse-inference pass re-uses the features of view 0 (the reference runs the backbone on the very
+    same tensor twice: generalized_rcnn.py:127 and :204; frozen BN makes both passes identical).
+"""
+import torch
+from torch import nn
+
+from .. import functional as Fk
+from ..structures.image_list import ImageList, to_image_list
+from .backbone import build_backbone
+from .box_head import MaskRCNNFPNAdaptor, build_roi_box_head
+from .mask_head import build_roi_mask_head
+from .rpn import build_rpn
+
+
+class BoxROIHeads(nn.ModuleDict):
+    def __init__(self, cfg, heads):
+        super().__init__(heads)
+        self.cfg = cfg.clone()
+
+    def forward(self, features, proposals, targets=None):
+        x, detections, loss_box, class_logits, box_regression = self.box(features, proposals, targets)
+        return x, detections, dict(loss_box), class_logits, box_regression
+
+    def forward_student(self, features, proposals, class_logits_t):
+        return self.box.forward_student(features, proposals, class_logits_t)
+
+    def forward_teacher(self, feature_tuple, proposals, teacher_infer):
+        x, detections, loss_box, class_logits, box_regression = self.box.forward_teacher(
+            feature_tuple, proposals, targets=teacher_infer)
+        return x, detections, dict(loss_box), class_logits, box_regression
+
+
+class MaskROIHeads(nn.ModuleDict):
+    def __init__(self, cfg, heads):
+        super().__init__(heads)
+        self.cfg = cfg
+
+    def forward(self, losses, features, detections, targets=None, images=None):
+        _, detections, loss_mask = self.mask(features, detections, targets, images)
+        losses.update(loss_mask)
+        return detections, losses
+
+
+def box_roi_heads(cfg, relation=True):
+    return BoxROIHeads(cfg, [("box", build_roi_box_head(cfg, relation=relation))])
+
+
+def mask_roi_heads(cfg, is_student=False):
+    return MaskROIHeads(cfg, [("mask", build_roi_mask_head(cfg, is_student))])
+
+
+class GeneralizedRCNN(nn.Module):
+    def __init__(self, cfg, is_teacher=False, is_student=False):
+        super().__init__()
+        self.cfg = cfg
+        self.backbone = build_backbone(cfg)
+        self.rpn = build_rpn(cfg, is_teacher)
+        self.box_heads = box_roi_heads(cfg)
+        self.mask_heads = mask_roi_heads(cfg, is_student)
+        if cfg.MODEL.RELATION_NMS.USE_RELATION_NMS:
+            raise NotImplementedError("IR-Net duplicate removal (MODEL.RELATION_NMS.USE_RELATION_NMS) is a 'next' row "
+                                      "(SURVEY §8f-4); run with MODEL.RELATION_NMS.USE_RELATION_NMS False")
+        self.relation_nms = None
+        self.mt_fg_hint = cfg.MT.FG_HINT
+        self.mt_cls = cfg.MT.CLS_LOSS
+        self.hint_adaptor = MaskRCNNFPNAdaptor(cfg)
+
+    def set_module_mode(self, mode):
+        self.rpn.set_teacher_mode(mode)
+        self.box_heads.box.set_teacher_mode(mode)
+        self.mask_heads.mask.set_teacher_mode(mode)
+
+    # ------------------------------------------------------------------------------ supervised
+    def forward(self, images, targets=None, tta=None, _features=None):
+        if self.training and targets is None:
+            raise ValueError("In training mode, targets should be passed")
+        images = to_image_list(images)
+        features = self.backbone(images.tensors) if _features is None else _features
+        proposals, proposal_losses = self.rpn(images, features, targets)
+        x, result, losses, class_logits, box_regression = self.box_heads(features, proposals, targets)
+        result, detector_losses = self.mask_heads(losses, features, result, targets, images)
+        if self.training:
+            out = {}
+            out.update(detector_losses)
+            out.update(proposal_losses)
+            return out
+        return result
+
+    # --------------------------------------------------------------------------------- teacher
+    def extract_aug_feat(self, imglist, teacher=True):
+        """Teacher: every view and its h-flip (the reference flips the ImageList in place and leaves it flipped,
+        generalized_rcnn.py:201-208 — reproduced).  One batched backbone pass, split back per view."""
+        if teacher:
+            tensors = []
+            for img in imglist:
+                tensors.append(img.tensors)
+                img.hflip()
+                tensors.append(img.tensors)
+        else:
+            tensors = []
+            for i, img in enumerate(imglist):
+                if i % 2 == 1:
+                    img.hflip()
+                tensors.append(img.tensors)
+        n = len(tensors)
+        if n == 1:
+            return [self.backbone(tensors[0])]
+        B = tensors[0].shape[0]
+        feats = self.backbone(torch.cat(tensors, 0))
+        return [tuple(f[i * B:(i + 1) * B] for f in feats) for i in range(n)]
+
+    def get_emb_feature(self, feature_list):
+        return [self.hint_adaptor(f) for f in feature_list]
+
+    def forward_teacher(self, images, targets=None):
+        if targets is not None:
+            raise NotImplementedError("forward_teacher with ground-truth targets (PLTRAIN) is out of scope")
+        images = [to_image_list(im) for im in images]
+        view0 = ImageList(images[0].tensors, images[0].image_sizes)  # un-flipped handle on colour view 0
+        aug_features = self.extract_aug_feat(images)
+        # coarse inference on view 0 (eval-mode heads) re-using its backbone features
+        self.set_module_mode("test")
+        teacher_infer = self.forward(view0, _features=aug_features[0])
+        integral = None
+        if self.mt_fg_hint > 0:
+            h, w = view0.tensors.shape[-2:]
+            integral = self.mask_heads.mask.mask_generator.masker.integral_mask(teacher_infer, h, w)
+        self.set_module_mode("train")
+        rpn_feat = aug_features[0]
+        _, _, _, _, proposals, _, ffi_boxes = self.rpn.forward_teacher(view0, rpn_feat, teacher_infer)
+        embeddings = None
+        if self.cfg.MT.FG_HINT or self.cfg.MT.HINT or self.cfg.MT.ODKD:
+            embeddings = self.get_emb_feature(aug_features)
+        result = class_logits = None
+        if self.cfg.MT.CLS_LOSS or self.cfg.MT.ODKD:
+            _, result, _, class_logits, _ = self.box_heads.forward_teacher(aug_features, proposals, teacher_infer)
+        return {"result_t": result, "class_logit_t": class_logits, "embedding": embeddings,
+                "seg_mask": integral, "ffi_boxes": ffi_boxes}
+
+    # --------------------------------------------------------------------------------- student
+    def forward_student(self, images, result_t):
+        loss_dict = {}
+        images = [to_image_list(im) for im in (images if isinstance(images, list) else [images])]
+        feat_list = self.extract_aug_feat(images, teacher=False)
+        if self.cfg.MT.FG_HINT:
+            loss_dict.update(mt_fg_loss=self.get_fg_feature_loss(feat_list, result_t["seg_mask"], result_t["embedding"]))
+        if self.cfg.MT.FFI or self.cfg.MT.ODKD:
+            raise NotImplementedError("MT.FFI / MT.ODKD (comparison methods) are out of scope")
+        if self.cfg.MT.CLS_LOSS:
+            loss_dict.update(self.box_heads.forward_student(feat_list, result_t["result_t"], result_t["class_logit_t"]))
+        return loss_dict
+
+    def get_fg_feature_loss(self, feature_list, seg_mask, teacher_feat):
+        if len(feature_list) != 1:
+            raise NotImplementedError("MGD is built for MT.AUG_S = 1 (one student view), as scripts/train_mt.sh sets")
+        student = self.hint_adaptor(feature_list[0])
+        return fg_hint_loss(teacher_feat, [student], seg_mask)
+
+
+def fg_hint_loss(teachers, students, masks):
+    """MGD (reference generalized_rcnn.py:243-282).  teachers: list (views) of lists (levels) of NHWC maps, odd
+    views are h-flipped views (un-flipped inside the kernel); students: [levels of the single student view];
+    masks: integral foreground map [B,H,W] (tensor, or list of [H,W] tensors like the reference)."""
+    if isinstance(masks, (list, tuple)):
+        masks = torch.stack(list(masks))
+    flip = sum(1 << i for i in range(len(teachers)) if i % 2 == 1)
+    return Fk.mgd_loss(masks.float(), list(students[0]), [list(t) for t in teachers], flip)
+
+
+_META = {"GeneralizedRCNN": GeneralizedRCNN}
+
+
+def build_detection_model(cfg, is_teacher=False, is_student=False):
+    return _META[cfg.MODEL.META_ARCHITECTURE](cfg, is_teacher=is_teacher, is_student=is_student)
+
+
+# ------------------------------------------------------------------------------------------------
+# state-dict boundary: reference layout (OIHW convs, IOHW deconv, fc6 columns in (c,h,w) order)
+def _special(model):
+    from ..layers.conv import Conv2d, ConvTranspose2x2
+    conv, deconv = {}, {}
+    for name, m in model.named_modules():
+        if isinstance(m, Conv2d):
+            conv[name + ".weight"] = m
+        elif isinstance(m, ConvTranspose2x2):
+            deconv[name + ".weight"] = m
+    return conv, deconv
+
+
+def reference_state_dict(model):
+    """state_dict with every tensor in the REFERENCE's layout and key names, loadable by the reference's
+    checkpointer (utils/checkpoint.py) and model_serialization.py suffix matcher."""
+    conv, deconv = _special(model)
+    fe = model.box_heads.box.feature_extractor
+    out = {}
+    for k, v in model.state_dict().items():
+        if k in conv:
+            out[k] = conv[k].reference_weight()
+        elif k in deconv:
+            out[k] = deconv[k].reference_weight()
+        elif k == "box_heads.box.feature_extractor.fc6.weight":
+            out[k] = fe.fc6_reference_weight()
+        else:
+            out[k] = v.detach().clone()
+    return out
+
+
+def load_reference_state_dict(model, sd, strict=False):
+    """Load a reference-layout state dict (e.g. e2e_mask_rcnn_R_50_FPN_1x.pth contents).  Keys the hot path does
+    not build (relation modules) are ignored unless strict."""
+    conv, deconv = _special(model)
+    fe = model.box_heads.box.feature_extractor
+    own = model.state_dict()
+    missing = [k for k in own if k not in sd]
+    unexpected = [k for k in sd if k not in own]
+    if strict and (missing or unexpected):
+        raise KeyError("missing %s unexpected %s" % (missing, unexpected))
+    with torch.no_grad():
+        for k, v in sd.items():
+            if k not in own:
+                continue
+            v = v.to(own[k].device, torch.float32)
+            if k in conv:
+                conv[k].load_reference_weight(v)
+            elif k in deconv:
+                deconv[k].load_reference_weight(v)
+            elif k == "box_heads.box.feature_extractor.fc6.weight":
+                fe.load_fc6_reference_weight(v)
+            else:
+                own[k].copy_(v)
+    return missing, unexpected

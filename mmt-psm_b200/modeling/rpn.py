@@ -1,0 +1,298 @@
+"""RPN: head, proposal selection and loss.
+
+Mirrors reference modeling/rpn/rpn.py:14-221 (RPNHead / RPNModule incl. `forward_teacher`),
+rpn/inference.py:15-272 (RPNPostProcessor) and rpn/loss.py:21-214 (RPNLossComputation) — same cfg keys, same
+selection rules, same loss formulae.  B200 differences:
+  * the head's 3x3 conv (+bias+ReLU) and the fused cls(3)+bbox(12) 1x1 conv are tcgen05 launches on NHWC maps,
+    so the reference's permute(0,2,3,1).reshape flattening is a free view;
+  * the 5 levels x B images NMS problems of one pass (10 `_C.nms` calls with 10 blocking D2H copies in the
+    reference, csrc/cuda/nms.cu:100) are ONE segmented on-device NMS and one 40-byte count read-back.
+"""
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from .. import kernels as K
+from ..layers import Conv2d, smooth_l1_loss
+from ..structures.bounding_box import BoxList
+from ..structures.boxlist_ops import boxlist_iou, cat_boxlist
+from . import registry
+from .anchor_generator import make_anchor_generator
+from .balanced_positive_negative_sampler import BalancedPositiveNegativeSampler
+from .box_coder import BoxCoder
+from .matcher import Matcher
+from .utils import cat
+
+_HEAD_PAD = 32  # fused cls+bbox output channels are padded to one 32-wide MMA tile
+
+
+@registry.RPN_HEADS.register("SingleConvRPNHead")
+class RPNHead(nn.Module):
+    def __init__(self, cfg, in_channels, num_anchors):
+        super().__init__()
+        self.conv = Conv2d(in_channels, in_channels, 3, 1, 1)
+        self.cls_logits = Conv2d(in_channels, num_anchors, 1, 1, 0)
+        self.bbox_pred = Conv2d(in_channels, num_anchors * 4, 1, 1, 0)
+        self.num_anchors = num_anchors
+        for l in (self.conv, self.cls_logits, self.bbox_pred):
+            nn.init.normal_(l.weight, std=0.01)
+            nn.init.constant_(l.bias, 0)
+
+    def forward(self, x):
+        """x: list of NHWC maps.  Returns (objectness [B,h,w,A], bbox_reg [B,h,w,4A]) per level."""
+        A = self.num_anchors
+        pad = _HEAD_PAD - 5 * A
+        w = torch.cat([self.cls_logits.weight, self.bbox_pred.weight,
+                       self.conv.weight.new_zeros((pad, 1, 1, self.conv.in_channels))], 0)
+        b = torch.cat([self.cls_logits.bias, self.bbox_pred.bias, self.conv.bias.new_zeros(pad)], 0)
+        logits, bbox_reg = [], []
+        from .. import functional as Fk
+        for feat in x:
+            t = self.conv(feat, relu=True)
+            o = Fk.conv_bn_act(t, w, None, b, None, False, 1, 0)
+            logits.append(o[..., :A])
+            bbox_reg.append(o[..., A:5 * A])
+        return logits, bbox_reg
+
+
+class RPNPostProcessor(nn.Module):
+    def __init__(self, pre_nms_top_n, post_nms_top_n, nms_thresh, min_size, box_coder=None, fpn_post_nms_top_n=None,
+                 is_teacher=False):
+        super().__init__()
+        self.pre_nms_top_n, self.post_nms_top_n = pre_nms_top_n, post_nms_top_n
+        self.nms_thresh, self.min_size = nms_thresh, min_size
+        self.box_coder = box_coder if box_coder is not None else BoxCoder(weights=(1.0, 1.0, 1.0, 1.0))
+        self.fpn_post_nms_top_n = post_nms_top_n if fpn_post_nms_top_n is None else fpn_post_nms_top_n
+        self.is_teacher = is_teacher
+
+    def add_gt_proposals(self, proposals, targets):
+        device = proposals[0].bbox.device
+        out = []
+        for p, t in zip(proposals, targets):
+            gt = t.copy_with_fields([])
+            gt.add_field("objectness", torch.ones(len(gt), device=device))
+            out.append(cat_boxlist((p, gt)))
+        return out
+
+    def _level_candidates(self, anchors, objectness, box_regression):
+        """Top-k + decode + clip for one level.  objectness [N,h,w,A], box_regression [N,h,w,4A] (NHWC).
+        Returns proposals [N,k,4], scores [N,k] (score-sorted), image sizes."""
+        N = objectness.shape[0]
+        device = objectness.device
+        obj = objectness.reshape(N, -1).sigmoid()
+        reg = box_regression.reshape(N, -1, 4)
+        k = min(self.pre_nms_top_n, obj.shape[1])
+        obj, topk_idx = obj.topk(k, dim=1, sorted=True)
+        batch_idx = torch.arange(N, device=device)[:, None]
+        reg = reg[batch_idx, topk_idx]
+        image_shapes = [a.size for a in anchors]
+        all_anchors = torch.cat([a.bbox for a in anchors], dim=0).reshape(N, -1, 4)[batch_idx, topk_idx]
+        props = self.box_coder.decode(reg.reshape(-1, 4), all_anchors.reshape(-1, 4)).view(N, -1, 4)
+        for j, (w, h) in enumerate(image_shapes):  # BoxList.clip_to_image(remove_empty=False)
+            props[j, :, 0].clamp_(min=0, max=w - 1)
+            props[j, :, 1].clamp_(min=0, max=h - 1)
+            props[j, :, 2].clamp_(min=0, max=w - 1)
+            props[j, :, 3].clamp_(min=0, max=h - 1)
+        return props, obj, image_shapes
+
+    @torch.no_grad()
+    def forward(self, anchors, objectness, box_regression, targets=None):
+        num_levels = len(objectness)
+        N = objectness[0].shape[0]
+        per_level_anchors = list(zip(*anchors))
+        boxes, scores, sizes = [], [], []
+        for a, o, b in zip(per_level_anchors, objectness, box_regression):
+            p, s, image_shapes = self._level_candidates(a, o, b)
+            boxes.append(p)
+            scores.append(s)
+            sizes.append(p.shape[1])
+        # segments in (level, image) order, all NMS problems of this pass in one launch chain
+        flat_boxes = torch.cat([p.reshape(-1, 4) for p in boxes], 0)
+        flat_scores = torch.cat([s.reshape(-1) for s in scores], 0)
+        valid = None
+        if self.min_size > 0:  # remove_small_boxes: filtered boxes are pushed behind every valid one
+            wh = flat_boxes[:, 2:] - flat_boxes[:, :2] + 1
+            valid = (wh[:, 0] >= self.min_size) & (wh[:, 1] >= self.min_size)
+            flat_scores_nms = torch.where(valid, flat_scores, flat_scores.new_full((), -1.0))
+        else:
+            flat_scores_nms = flat_scores
+        offs = [0]
+        for k in sizes:
+            for _ in range(N):
+                offs.append(offs[-1] + k)
+        keep, counts = K.nms_segmented(flat_boxes, flat_scores_nms, offs, self.nms_thresh)
+        counts_host = counts.cpu().tolist()  # the only host read-back of the pass
+        per_image = [[] for _ in range(N)]
+        seg = 0
+        for l in range(num_levels):
+            for j in range(N):
+                n_keep = counts_host[seg]
+                idx = keep[offs[seg]: offs[seg] + n_keep] + offs[seg]
+                if valid is not None:
+                    idx = idx[valid[idx]]
+                if self.post_nms_top_n > 0:
+                    idx = idx[: self.post_nms_top_n]
+                bl = BoxList(flat_boxes[idx], image_shapes[j], mode="xyxy")
+                bl.add_field("objectness", flat_scores[idx])
+                per_image[j].append(bl)
+                seg += 1
+        boxlists = [cat_boxlist(b) for b in per_image]
+        if num_levels > 1:
+            boxlists = self.select_over_all_levels(boxlists)
+        if self.training and targets is not None:
+            boxlists = self.add_gt_proposals(boxlists, targets)
+        return boxlists
+
+    def select_over_all_levels(self, boxlists):
+        n = len(boxlists)
+        if self.training:  # batch-wide top-k (reference rpn/inference.py:222-234)
+            objectness = torch.cat([b.get_field("objectness") for b in boxlists], dim=0)
+            box_sizes = [len(b) for b in boxlists]
+            k = min(self.fpn_post_nms_top_n, len(objectness))
+            _, inds = torch.topk(objectness, k, dim=0, sorted=True)
+            mask = torch.zeros_like(objectness, dtype=torch.bool)
+            mask[inds] = True
+            mask = mask.split(box_sizes)
+            for i in range(n):
+                boxlists[i] = boxlists[i][mask[i]]
+        else:
+            for i in range(n):
+                objectness = boxlists[i].get_field("objectness")
+                k = min(self.fpn_post_nms_top_n, len(objectness))
+                _, inds = torch.topk(objectness, k, dim=0, sorted=True)
+                boxlists[i] = boxlists[i][inds]
+        return boxlists
+
+
+def make_rpn_postprocessor(config, rpn_box_coder, is_train, is_teacher=False):
+    r = config.MODEL.RPN
+    if is_train:
+        pre, post, fpn_post = r.PRE_NMS_TOP_N_TRAIN, r.POST_NMS_TOP_N_TRAIN, r.FPN_POST_NMS_TOP_N_TRAIN
+    else:
+        pre, post, fpn_post = r.PRE_NMS_TOP_N_TEST, r.POST_NMS_TOP_N_TEST, r.FPN_POST_NMS_TOP_N_TEST
+    return RPNPostProcessor(pre, post, r.NMS_THRESH, r.MIN_SIZE, rpn_box_coder, fpn_post, is_teacher)
+
+
+class RPNLossComputation(object):
+    def __init__(self, proposal_matcher, fg_bg_sampler, box_coder, cfg=None):
+        self.proposal_matcher = proposal_matcher
+        self.fg_bg_sampler = fg_bg_sampler
+        self.box_coder = box_coder
+
+    def match_targets_to_anchors(self, anchor, target):
+        matched_idxs = self.proposal_matcher(boxlist_iou(target, anchor))
+        target = target.copy_with_fields([])
+        matched = target[matched_idxs.clamp(min=0)]
+        matched.add_field("matched_idxs", matched_idxs)
+        return matched
+
+    def prepare_targets(self, anchors, targets):
+        labels, regression_targets = [], []
+        for a, t in zip(anchors, targets):
+            matched = self.match_targets_to_anchors(a, t)
+            midx = matched.get_field("matched_idxs")
+            lab = (midx >= 0).to(dtype=torch.float32)
+            lab[~a.get_field("visibility").bool()] = -1
+            lab[midx == Matcher.BETWEEN_THRESHOLDS] = -1
+            labels.append(lab)
+            regression_targets.append(self.box_coder.encode(matched.bbox, a.bbox))
+        return labels, regression_targets
+
+    def _sample(self, anchors, targets):
+        anchors = [cat_boxlist(a) for a in anchors]
+        labels, regression_targets = self.prepare_targets(anchors, targets)
+        pos, neg = self.fg_bg_sampler(labels)
+        pos = torch.nonzero(torch.cat(pos, dim=0)).squeeze(1)
+        neg = torch.nonzero(torch.cat(neg, dim=0)).squeeze(1)
+        return labels, regression_targets, pos, neg
+
+    def teacher_sample_selection(self, anchors, objectness, box_regression, targets):
+        """Reference rpn/loss.py:85-136.  Its outputs are unused downstream but it draws from the
+        sampler's random stream, so it is kept to leave the RNG sequence of an iteration unchanged."""
+        labels, _, pos, neg = self._sample(anchors, targets)
+        sampled = torch.cat([pos, neg], dim=0)
+        obj = cat([o.reshape(o.shape[0], -1) for o in objectness], dim=1).reshape(-1)
+        reg = cat([b.reshape(b.shape[0], -1, 4) for b in box_regression], dim=1).reshape(-1, 4)
+        labels = torch.cat(labels, dim=0)
+        return obj[sampled], reg[pos], (sampled, pos.shape), labels[sampled]
+
+    def __call__(self, anchors, objectness, box_regression, targets):
+        labels, regression_targets, pos, neg = self._sample(anchors, targets)
+        sampled = torch.cat([pos, neg], dim=0)
+        # NHWC maps flatten directly to the (h, w, anchor) order of the labels
+        obj = cat([o.reshape(o.shape[0], -1) for o in objectness], dim=1).reshape(-1)
+        reg = cat([b.reshape(b.shape[0], -1, 4) for b in box_regression], dim=1).reshape(-1, 4)
+        labels = torch.cat(labels, dim=0)
+        regression_targets = torch.cat(regression_targets, dim=0)
+        box_loss = smooth_l1_loss(reg[pos], regression_targets[pos], beta=1.0 / 9, size_average=False) / sampled.numel()
+        objectness_loss = F.binary_cross_entropy_with_logits(obj[sampled], labels[sampled])
+        return objectness_loss, box_loss
+
+
+def make_rpn_loss_evaluator(cfg, box_coder):
+    r = cfg.MODEL.RPN
+    matcher = Matcher(r.FG_IOU_THRESHOLD, r.BG_IOU_THRESHOLD, allow_low_quality_matches=True)
+    sampler = BalancedPositiveNegativeSampler(r.BATCH_SIZE_PER_IMAGE, r.POSITIVE_FRACTION)
+    return RPNLossComputation(matcher, sampler, box_coder, cfg)
+
+
+class RPNModule(nn.Module):
+    def __init__(self, cfg, is_teacher=False):
+        super().__init__()
+        self.mode = None
+        self.cfg = cfg.clone()
+        self.anchor_generator = make_anchor_generator(cfg)
+        in_channels = cfg.MODEL.BACKBONE.OUT_CHANNELS
+        self.head = registry.RPN_HEADS[cfg.MODEL.RPN.RPN_HEAD](
+            cfg, in_channels, self.anchor_generator.num_anchors_per_location()[0])
+        coder = BoxCoder(weights=(1.0, 1.0, 1.0, 1.0))
+        self.box_selector_train = make_rpn_postprocessor(cfg, coder, is_train=True, is_teacher=is_teacher)
+        self.box_selector_test = make_rpn_postprocessor(cfg, coder, is_train=False, is_teacher=is_teacher)
+        self.loss_evaluator = make_rpn_loss_evaluator(cfg, coder)
+
+    def set_teacher_mode(self, mode):
+        self.mode = mode
+
+    def _head_and_anchors(self, images, features):
+        if isinstance(features, list):
+            raise NotImplementedError("multi-view RPN averaging is dead code on this path (SURVEY §2.3): the RPN is "
+                                      "always handed ONE feature tuple")
+        objectness, reg = self.head(features)
+        anchors = self.anchor_generator(images, [f.shape[1:3] for f in features])
+        return objectness, reg, anchors
+
+    def forward(self, images, features, targets=None):
+        objectness, reg, anchors = self._head_and_anchors(images, features)
+        if self.training or self.mode == "train":
+            return self._forward_train(anchors, objectness, reg, targets)
+        return self._forward_test(anchors, objectness, reg)
+
+    def forward_teacher(self, images, features, targets=None):
+        objectness, reg, anchors = self._head_and_anchors(images, features)
+        with torch.no_grad():
+            if self.cfg.MT.FFI:
+                raise NotImplementedError("MT.FFI (comparison method) is out of scope")
+            boxes = self.box_selector_train(anchors, objectness, reg, targets)
+            obj, box_reg, sample_idx, label = self.loss_evaluator.teacher_sample_selection(
+                anchors, objectness, reg, targets)
+        return obj, box_reg, sample_idx, label, boxes, {}, None
+
+    def _forward_train(self, anchors, objectness, reg, targets):
+        if self.cfg.MODEL.RPN_ONLY:
+            boxes = anchors
+        else:
+            with torch.no_grad():
+                boxes = self.box_selector_train(anchors, objectness, reg, targets)
+        loss_objectness, loss_rpn_box_reg = self.loss_evaluator(anchors, objectness, reg, targets)
+        return boxes, {"loss_objectness": loss_objectness, "loss_rpn_box_reg": loss_rpn_box_reg}
+
+    def _forward_test(self, anchors, objectness, reg):
+        boxes = self.box_selector_test(anchors, objectness, reg)
+        if self.cfg.MODEL.RPN_ONLY:
+            inds = [b.get_field("objectness").sort(descending=True)[1] for b in boxes]
+            boxes = [b[i] for b, i in zip(boxes, inds)]
+        return boxes, {}
+
+
+def build_rpn(cfg, is_teacher=False):
+    return RPNModule(cfg, is_teacher=is_teacher)

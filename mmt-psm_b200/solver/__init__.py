@@ -1,0 +1,142 @@
+"""Optimizer + LR schedule — mirrors `maskrcnn_benchmark.solver` (reference solver/build.py:5-33,
+lr_scheduler.py:10-53).  `make_optimizer` returns a FusedSGDEMA: the student's parameters, gradients and momentum
+(and the EMA teacher's parameters) live in flat fp32 arenas, and ONE kernel launch per iteration performs
+SGD(momentum, per-tensor lr / weight decay) followed by the teacher EMA — instead of torch.optim.SGD over 130 param
+groups plus 264 mul_/add_ launches (engine/MTtrainer.py:277-281)."""
+from bisect import bisect_right
+
+import torch
+
+from .. import kernels as K
+
+
+class FusedSGDEMA(object):
+    def __init__(self, cfg, student, teacher=None):
+        s = cfg.SOLVER
+        self.momentum = s.MOMENTUM
+        self.student, self.teacher = student, teacher
+        params = list(student.named_parameters())
+        device = params[0][1].device
+        self.entries, total = [], 0
+        for name, p in params:
+            n = p.numel()
+            lr_mult, wd = (s.BIAS_LR_FACTOR, s.WEIGHT_DECAY_BIAS) if "bias" in name else (1.0, s.WEIGHT_DECAY)
+            self.entries.append(dict(name=name, begin=total, end=total + n, lr_mult=lr_mult, wd=wd,
+                                     trainable=p.requires_grad))
+            total += (n + 3) // 4 * 4
+        self.total = total
+        self.flat_p = torch.zeros(total, dtype=torch.float32, device=device)
+        self.flat_g = torch.zeros(total, dtype=torch.float32, device=device)
+        self.flat_m = torch.zeros(total, dtype=torch.float32, device=device)
+        self.touched = [False] * len(params)
+        for i, ((name, p), e) in enumerate(zip(params, self.entries)):
+            view = self.flat_p[e["begin"]:e["end"]].view_as(p)
+            view.copy_(p.data)
+            p.data = view
+            if p.requires_grad:
+                p.grad = self.flat_g[e["begin"]:e["end"]].view_as(p)
+                p.register_post_accumulate_grad_hook(self._mark(i))
+        self.flat_t = None
+        if teacher is not None:
+            tparams = list(teacher.named_parameters())
+            assert [n for n, _ in tparams] == [n for n, _ in params], "teacher/student parameter lists differ"
+            self.flat_t = torch.zeros(total, dtype=torch.float32, device=device)
+            for (name, p), e in zip(tparams, self.entries):
+                view = self.flat_t[e["begin"]:e["end"]].view_as(p)
+                view.copy_(p.data)
+                p.data = view
+        self.base_lr = s.BASE_LR
+        self.lr = s.BASE_LR
+        self.param_groups = [{"lr": self.lr}]  # for the reference's log line (MTtrainer.py:218)
+        self.first_step = True
+        self._seg_cache = {}
+
+    def _mark(self, i):
+        def hook(_):
+            self.touched[i] = True
+        return hook
+
+    def set_lr(self, lr):
+        self.lr = lr
+        self.param_groups[0]["lr"] = lr
+
+    def zero_grad(self):
+        self.flat_g.zero_()
+        self.touched = [False] * len(self.entries)
+
+    def _segments(self, touched):
+        key = (self.lr, tuple(touched))
+        if key not in self._seg_cache:
+            if len(self._seg_cache) > 64:
+                self._seg_cache.clear()
+            ent = [(e["begin"], e["end"], self.lr * e["lr_mult"], e["wd"], e["trainable"] and t)
+                   for e, t in zip(self.entries, touched)]
+            self._seg_cache[key] = K.make_segments(ent, self.flat_p.device)
+        return self._seg_cache[key]
+
+    def step(self, ema_alpha=None, grad_scale=1.0):
+        """SGD on every tensor that received a gradient this iteration (torch.optim.SGD skips grad-less params),
+        then, if `ema_alpha` is given, teacher <- alpha * teacher + (1 - alpha) * student over ALL parameters."""
+        segs = self._segments(self.touched)
+        teacher = self.flat_t if ema_alpha is not None else None
+        K.sgd_ema_(self.flat_p, teacher, self.flat_g, self.flat_m, segs, len(self.entries), self.momentum,
+                   0.0 if ema_alpha is None else ema_alpha, self.first_step, grad_scale)
+        self.first_step = False
+
+    def ema_only(self, alpha):
+        K.ema_(self.flat_t, self.flat_p, alpha)
+
+    def state_dict(self):
+        return {"momentum": self.flat_m.clone(), "first_step": self.first_step, "lr": self.lr}
+
+    def load_state_dict(self, sd):
+        self.flat_m.copy_(sd["momentum"])
+        self.first_step = sd["first_step"]
+        self.set_lr(sd["lr"])
+
+
+def make_optimizer(cfg, model, teacher=None):
+    return FusedSGDEMA(cfg, model, teacher)
+
+
+class WarmupMultiStepLR(object):
+    """Same schedule as reference solver/lr_scheduler.py:10-53 (linear / constant warm-up x multi-step decay)."""
+
+    def __init__(self, optimizer, milestones, gamma=0.1, warmup_factor=1.0 / 3, warmup_iters=500,
+                 warmup_method="linear", last_epoch=-1):
+        if list(milestones) != sorted(milestones):
+            raise ValueError("Milestones should be a list of increasing integers. Got %s" % (milestones,))
+        if warmup_method not in ("constant", "linear"):
+            raise ValueError("Only 'constant' or 'linear' warmup_method accepted, got %s" % warmup_method)
+        self.optimizer, self.milestones, self.gamma = optimizer, list(milestones), gamma
+        self.warmup_factor, self.warmup_iters, self.warmup_method = warmup_factor, warmup_iters, warmup_method
+        self.base_lr = optimizer.base_lr
+        self.last_epoch = last_epoch
+        self.step()
+
+    def get_lr(self):
+        f = 1
+        if self.last_epoch < self.warmup_iters:
+            if self.warmup_method == "constant":
+                f = self.warmup_factor
+            else:
+                a = self.last_epoch / self.warmup_iters
+                f = self.warmup_factor * (1 - a) + a
+        return self.base_lr * f * self.gamma ** bisect_right(self.milestones, self.last_epoch)
+
+    def step(self):
+        self.last_epoch += 1
+        self.optimizer.set_lr(self.get_lr())
+
+    def state_dict(self):
+        return {"last_epoch": self.last_epoch}
+
+    def load_state_dict(self, sd):
+        self.last_epoch = sd["last_epoch"]
+        self.optimizer.set_lr(self.get_lr())
+
+
+def make_lr_scheduler(cfg, optimizer):
+    s = cfg.SOLVER
+    return WarmupMultiStepLR(optimizer, s.STEPS, s.GAMMA, warmup_factor=s.WARMUP_FACTOR, warmup_iters=s.WARMUP_ITERS,
+                             warmup_method=s.WARMUP_METHOD)

@@ -213,12 +213,55 @@ def gen_glue():
     save("glue", **out)
 
 
+def synthetic_instances(g, n_obj, size=800.0):
+    """n_obj instances: 16-gons (sometimes two polygons per instance), like the bench's synthetic targets."""
+    inst = []
+    for i in range(n_obj):
+        polys = []
+        for _ in range(2 if i % 5 == 4 else 1):
+            c = torch.rand(2, generator=g) * size
+            r = float(torch.rand(1, generator=g)) * 60 + 8
+            ang = torch.arange(16, dtype=torch.float32) / 16 * 6.2831853 + float(torch.rand(1, generator=g))
+            rad = r * (0.7 + 0.6 * torch.rand(16, generator=g))
+            pts = torch.stack([c[0] + rad * torch.cos(ang), c[1] + rad * torch.sin(ang)], 1).clamp(0, size - 1)
+            polys.append(pts.reshape(-1).tolist())
+        inst.append(polys)
+    return inst
+
+
+def gen_mask_targets():
+    from maskrcnn_benchmark.modeling.roi_heads.mask_head.loss import project_masks_on_boxes
+    from maskrcnn_benchmark.structures.bounding_box import BoxList
+    from maskrcnn_benchmark.structures.segmentation_mask import SegmentationMask
+    g = torch.Generator().manual_seed(17)
+    inst = synthetic_instances(g, 24)
+    sm = SegmentationMask(inst, (800, 800))
+    K = 96
+    which = torch.randint(0, len(inst), (K,), generator=g)
+    boxes = []
+    for i in which.tolist():
+        pts = torch.tensor([v for p in inst[i] for v in p]).view(-1, 2)
+        lo, hi = pts.min(0)[0], pts.max(0)[0]
+        jit = (torch.rand(4, generator=g) - 0.5) * 0.4 * torch.cat([hi - lo, hi - lo])
+        boxes.append(torch.cat([lo, hi]) + jit)
+    boxes = torch.stack(boxes)
+    boxes[3] = torch.tensor([100.2, 100.7, 100.9, 101.1])  # sub-pixel box (w,h < 1 -> clamped to 1)
+    boxes[5] = boxes[5].round()                              # integer box with w == h possible
+    boxes[5, 3] = boxes[5, 1] + (boxes[5, 2] - boxes[5, 0])
+    masks = project_masks_on_boxes(sm[which], BoxList(boxes, (800, 800)), 28)
+    flat = [np.asarray(p, np.float32) for polys in inst for p in polys]
+    save("mask_targets", xy=np.concatenate(flat), poly_len=np.array([len(p) // 2 for p in flat]),
+         inst_npoly=np.array([len(polys) for polys in inst]), boxes=boxes.numpy(), which=which.numpy(),
+         masks=masks.numpy().astype(np.uint8))
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
-    which = sys.argv[1:] or ["nms", "roi_align", "psm", "mgd", "ema", "glue"]
+    which = sys.argv[1:] or ["nms", "roi_align", "psm", "mgd", "ema", "glue", "mask_targets"]
     if "nms" in which: gen_nms()
     if "roi_align" in which: gen_roi_align()
     if "psm" in which: gen_psm()
     if "mgd" in which: gen_mgd()
     if "ema" in which: gen_ema_and_weights()
     if "glue" in which: gen_glue()
+    if "mask_targets" in which: gen_mask_targets()

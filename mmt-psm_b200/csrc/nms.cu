@@ -48,11 +48,15 @@ __global__ void __launch_bounds__(256) rank_sort_kernel(const float* __restrict_
   if ((int)(blockIdx.x * blockDim.x) >= n) return;
   __shared__ float tile[256];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const float si = (i < n) ? scores[base + i] : 0.f;
+  // NaN scores (a diverged network) are ranked last instead of corrupting the permutation
+  float si = (i < n) ? scores[base + i] : 0.f;
+  if (si != si) si = -INFINITY;
   int rank = 0;
   for (int j0 = 0; j0 < n; j0 += 256) {
     const int j = j0 + threadIdx.x;
-    tile[threadIdx.x] = (j < n) ? scores[base + j] : 0.f;
+    float sj_in = (j < n) ? scores[base + j] : 0.f;
+    if (sj_in != sj_in) sj_in = -INFINITY;
+    tile[threadIdx.x] = sj_in;
     __syncthreads();
     const int lim = min(256, n - j0);
     if (i < n) {

@@ -106,7 +106,7 @@ class MTtrainer(object):
                 except ValueError as e:  # the reference swallows everything; only "no boxes" is expected
                     if "boxes available" not in str(e):
                         raise
-                    self.logger.info("teacher produced no boxes for one image, skip this pair")
+                    self.logger.warning("teacher produced no boxes for one image, skip this pair (%s)", e)
                     data_u_list = None
                     continue
             unlabel.append(self.student.forward_student(student, teacher_results))

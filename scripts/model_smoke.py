@@ -3,7 +3,9 @@ import os
 import sys
 import time
 
+import logging
 import torch
+logging.basicConfig(level=logging.INFO)
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import mmt_psm_b200  # noqa
@@ -34,6 +36,8 @@ dev = torch.device("cuda:0")
 torch.manual_seed(0)
 student = build_detection_model(c, is_student=True).to(dev)
 teacher = build_detection_model(c, is_teacher=True).to(dev)
+from mmt_psm_b200.utils.synthetic_init import init_model
+init_model(student, 0)
 teacher.load_state_dict(student.state_dict())
 opt = make_optimizer(c, student, teacher)
 sched = make_lr_scheduler(c, opt)
@@ -42,7 +46,7 @@ student.train()
 teacher.eval()
 images, targets, views = make_batch(1234, 2, size, 3, n_cyto=6 if size < 600 else 20, n_nuc=6 if size < 600 else 20)
 lib.reset_launch_count()
-for it in (0, 1, 2, 3):
+for it in range(int(sys.argv[2]) if len(sys.argv) > 2 else 4):
     torch.cuda.synchronize()
     t0 = time.time()
     ld, total = trainer.train_step(it, images, targets, views if it > 0 else None)

@@ -189,10 +189,11 @@ def patch_python_blocks(mb):
     # 10  device shuffling in the feature extractors: make the `!= 0` test never fire on CPU tensors
     for f in ("modeling/roi_heads/box_head/roi_box_feature_extractors.py",
               "modeling/roi_heads/mask_head/roi_mask_feature_extractors.py"):
-        _sub(p(f), r"\.device\.index\s*!=\s*0", ".device.index not in (None, 0)", must=False)
+        _sub(p(f), r"device\s*=\s*x\[0\]\.device\.index", "device = x[0].device.index or 0")
     # 11  eval-mode mask head hands a list to the post-processor (F7)
     _sub(p("modeling/roi_heads/mask_head/mask_head.py"),
-         r"result = self\.post_processor\(mask_logits,", "result = self.post_processor(torch.cat(list(mask_logits)) if isinstance(mask_logits, (list, tuple)) else mask_logits,", must=False)
+         r"result = self\.(post_processor|mask_generator)\(mask_logits,",
+         r"result = self.\1(torch.cat(list(mask_logits)) if isinstance(mask_logits, (list, tuple)) else mask_logits,")
     # 13  CPU ROIAlign has no backward in the reference: route CPU tensors through the bit-identical
     #     torchvision op (aligned=False) so autograd works
     with open(p("layers/roi_align.py"), "a") as f:

@@ -255,9 +255,57 @@ def gen_mask_targets():
          masks=masks.numpy().astype(np.uint8))
 
 
+def gen_step():
+    """One supervised step + one mean-teacher forward (teacher -> student-unlabeled) of the REFERENCE model on CPU,
+    from the deterministic synthetic weights / inputs of mmt_psm_b200 (DO = 0 so no dropout stream is involved)."""
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    import mmt_psm_b200  # noqa: F401
+    from mmt_psm_b200.data.synthetic import make_batch
+    from mmt_psm_b200.utils.synthetic_init import synthetic_state_dict
+    from maskrcnn_benchmark.modeling.detector import build_detection_model
+    from maskrcnn_benchmark.structures.bounding_box import BoxList
+    from maskrcnn_benchmark.structures.segmentation_mask import SegmentationMask
+    c = cfg.clone()
+    c.merge_from_file(os.path.join(TREE, "configs/pap/e2e_mask_rcnn_R_50_FPN_1x.yaml"))
+    c.merge_from_list(MT_OPTS + ["MODEL.RELATION_NMS.USE_RELATION_NMS", False, "MODEL.RELATION_MASK.USE_RELATION", False,
+                                 "MODEL.ROI_BOX_HEAD.DO", 0.0])
+    student = build_detection_model(c, is_student=True)
+    teacher = build_detection_model(c, is_teacher=True)
+    shapes = {k: tuple(v.shape) for k, v in student.state_dict().items() if "mask_relation_module" not in k}
+    sd = synthetic_state_dict(shapes, 0)
+    for m in (student, teacher):
+        missing, unexpected = m.load_state_dict(sd, strict=False)
+        assert not unexpected and all("mask_relation_module" in k or "cell_anchors" in k for k in missing), missing
+    size = 256
+    images, targets, views = make_batch(1234, 2, size, 3, 6, 6)
+    rt = []
+    for t in targets:
+        b = BoxList(t.bbox, t.size, "xyxy")
+        b.add_field("labels", t.get_field("labels"))
+        b.add_field("masks", SegmentationMask([[p.tolist() for p in inst.polygons] for inst in t.get_field("masks").polygons], t.size))
+        rt.append(b)
+    student.train()
+    teacher.eval()
+    torch.manual_seed(7)
+    sup = student(images, rt)
+    out = {"sup_" + k: v.detach().numpy() for k, v in sup.items()}
+    with torch.no_grad():
+        tr = teacher.forward_teacher([views[0].clone(), views[1].clone()])
+    mt = student.forward_student([views[2].clone()], tr)
+    out.update({"mt_" + k: v.detach().numpy() for k, v in mt.items()})
+    out["t_n_rois"] = np.array([len(b) for b in tr["result_t"]])
+    out["t_labels"] = torch.cat([b.get_field("labels") for b in tr["result_t"]]).numpy()
+    out["t_boxes"] = torch.cat([b.bbox for b in tr["result_t"]]).numpy()
+    out["t_logits"] = torch.stack(tr["class_logit_t"]).numpy()
+    out["t_seg_mask_sum"] = np.array([float(m.sum()) for m in tr["seg_mask"]])
+    out["t_seg_mask"] = np.packbits(torch.stack(tr["seg_mask"]).numpy() > 0)
+    save("step_small", size=size, **out)
+    print({k: float(v) for k, v in out.items() if v.ndim == 0})
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
-    which = sys.argv[1:] or ["nms", "roi_align", "psm", "mgd", "ema", "glue", "mask_targets"]
+    which = sys.argv[1:] or ["nms", "roi_align", "psm", "mgd", "ema", "glue", "mask_targets", "step"]
     if "nms" in which: gen_nms()
     if "roi_align" in which: gen_roi_align()
     if "psm" in which: gen_psm()
@@ -265,3 +313,4 @@ if __name__ == "__main__":
     if "ema" in which: gen_ema_and_weights()
     if "glue" in which: gen_glue()
     if "mask_targets" in which: gen_mask_targets()
+    if "step" in which: gen_step()

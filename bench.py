@@ -1,0 +1,367 @@
+#!/usr/bin/env python
+"""Headline benchmark: labeled images/sec through one full MMT-PSM mean-teacher training iteration
+(student supervised fwd+bwd, EMA-teacher forward on AUG_K=2 colour views x {orig, h-flip}, student
+unlabeled fwd+bwd with PSM + MGD, [NCCL all-reduce of the student gradient arena], fused SGD + teacher EMA)
+on synthetic 1000x1000 two-class crops (-> 800x800 after the reference's Resize), per-GPU batch 2 labeled + 2 unlabeled.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload mt|sup]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+Prints ONE JSON line on rank 0.  `value` = device-timed throughput with inputs resident in HBM; `e2e` = the same
+iteration driven from pinned HOST buffers (H2D of the images / views / targets and D2H of the loss inside the timed
+region); `roofline` = the tcgen05 implicit-GEMM conv kernel family timed live with CUDA events (the library's
+own event bracketing, mmt_prof_*), against MEASURED_PEAKS.json; `cpu_baseline` = the oracle's CPU restatement of
+the reference step (oracle/model_cpu.py, torch CPU + the reference's own compiled CPU `_C` where loadable) on the
+host cores, one iteration.  `--impl reference` times only that CPU arm.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "labeled images/sec, MMT-PSM mean-teacher training iteration (R50-FPN, 1000x1000 crops -> 800x800, MT.AUG_K=2)"
+SIZE, CROP, BATCH = 800, 1000, 2
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="mt", choices=["mt", "sup"])
+    ap.add_argument("--size", type=int, default=SIZE, help="network input size (800 = reference Resize of a 1000 crop)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tensor_burst=d["bf16_tflops"], tensor=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tensor_burst=1590.0, tensor=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+def workload_name(args):
+    if args.workload == "mt":
+        return ("MMT-PSM mean-teacher (MT.AUG_K=2, AUG_S=1, LAMBDA=5, CLS_LOSS=0.2, FG_HINT=1, relation off), R50-FPN, "
+                "per-GPU 2 labeled + 2 unlabeled crops x 3 views, %dx%d" % (args.size, args.size))
+    return "Mask R-CNN R50-FPN supervised-only (MT.LAMBDA=0, relation off), per-GPU bs=2, %dx%d" % (args.size, args.size)
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) < 7:
+                continue
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1])); power.append(float(r[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------- CPU reference
+def build_oracle_trainer(size):
+    """The oracle's restatement of the reference trainer (TEST INFRASTRUCTURE; the CPU arm only)."""
+    import torch
+    import mmt_psm_b200  # noqa: F401
+    from mmt_psm_b200.config.presets import mt_psm_cfg
+    from mmt_psm_b200.data.synthetic import make_batch
+    from mmt_psm_b200.modeling.detector import build_detection_model, reference_state_dict
+    from mmt_psm_b200.utils.synthetic_init import synthetic_state_dict
+    from oracle import model_cpu
+    c = mt_psm_cfg(start_mt=0)
+    m = build_detection_model(c, is_student=True)
+    shapes = {k: tuple(v.shape) for k, v in reference_state_dict(m).items()}
+    del m
+    sd = synthetic_state_dict(shapes, 0)
+    oc = model_cpu.Cfg()
+    oc.start_mt = 0
+    trainer = model_cpu.Trainer(sd, oc)
+    trainer.last_epoch = 2000
+    images, targets, views = make_batch(1234, BATCH, size, 3, 20, 20)
+    tg = [dict(bbox=t.bbox, labels=t.get_field("labels"),
+               polygons=[[p.numpy() for p in inst.polygons] for inst in t.get_field("masks").polygons]) for t in targets]
+    torch.manual_seed(7)
+    return trainer, images, tg, views
+
+
+def time_cpu_reference(args, steps, warmup):
+    """images/sec of the reference's CPU path (oracle port) on this box's host cores; each step = one full iteration."""
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    trainer, images, tg, views = build_oracle_trainer(args.size)
+    use_views = views if args.workload == "mt" else None
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        trainer.step(2000 + i, images, tg, use_views)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    per_step = sum(times) / len(times)
+    return BATCH / per_step, per_step, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warmup = max(1, min(args.steps, 3)), max(0, min(args.warmup, 1))  # bounded: ~10-30 s of CPU work per step
+    value, per_step, cores = time_cpu_reference(args, steps, warmup)
+    sample = "%d full iteration(s) after %d warm-up (each 2 labeled + 2 unlabeled crops x 3 views, %dx%d)" % (steps, warmup, args.size, args.size)
+    out = {"impl": "reference", "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": args.gpus,
+           "steps": steps, "warmup": warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": workload_name(args), "arm": "reference CPU path: oracle/model_cpu.py (torch CPU restatement of "
+                      "the patched reference step, pinned by tests/golden/step_small.npz) on the host cores"},
+           "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
+           "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+
+
+# --------------------------------------------------------------------------------------------- ours
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py (impl=ours) needs a CUDA device: the product has no CPU path")
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if world != args.gpus and rank == 0:
+        print("warning: --gpus %d but WORLD_SIZE %d; reporting n_gpus = WORLD_SIZE" % (args.gpus, world), file=sys.stderr)
+
+    import mmt_psm_b200  # noqa: F401
+    from mmt_psm_b200 import lib
+    from mmt_psm_b200.config.presets import mt_psm_cfg, supervised_cfg
+    from mmt_psm_b200.data.synthetic import make_batch
+    from mmt_psm_b200.engine import MTtrainer
+    from mmt_psm_b200.modeling.detector import build_detection_model
+    from mmt_psm_b200.solver import make_lr_scheduler, make_optimizer
+    from mmt_psm_b200.structures.bounding_box import BoxList
+    from mmt_psm_b200.structures.segmentation_mask import SegmentationMask
+    from mmt_psm_b200.utils.synthetic_init import init_model
+    lib.lib()
+
+    mt = args.workload == "mt"
+    cfg = mt_psm_cfg(start_mt=0) if mt else supervised_cfg()
+    torch.manual_seed(0)
+    student = build_detection_model(cfg, is_student=True).to(dev)
+    teacher = build_detection_model(cfg, is_teacher=True).to(dev)
+    init_model(student, 0)                       # identical weights on every rank (seeded by name)
+    teacher.load_state_dict(student.state_dict())
+    opt = make_optimizer(cfg, student, teacher)
+    sched = make_lr_scheduler(cfg, opt)
+    sched.last_epoch = 2000                      # past warm-up: the steady-state part of the schedule
+    trainer = MTtrainer(student, teacher, None, opt, sched, None, None, 10 ** 9, cfg)
+    student.train()
+    teacher.eval()
+    torch.manual_seed(100 + rank)                # per-rank sampling / dropout streams
+
+    # per-rank shard of the synthetic stream: a small pool of distinct batches in pinned host memory
+    pool = [make_batch(1234 + 17 * rank + 1000 * j, BATCH, args.size, 3, 20, 20, pin=True) for j in range(2)]
+    resident = []
+    for images, targets, views in pool:
+        resident.append((images.to(dev), [t.to(dev) for t in targets], [v.to(dev) for v in views]))
+
+    def fresh_targets(targets):
+        """Targets as a data loader would hand them over: host BoxLists whose polygons have not been packed / uploaded."""
+        out = []
+        for t in targets:
+            n = BoxList(t.bbox.clone(), t.size, t.mode)
+            n.add_field("labels", t.get_field("labels").clone())
+            n.add_field("masks", SegmentationMask([inst.polygons for inst in t.get_field("masks").polygons], t.size))
+            out.append(n)
+        return out
+
+    h2d = 0
+    images, targets, views = pool[0]
+    h2d += images.numel() * 4 + (sum(v.numel() for v in views) * 4 if mt else 0)
+    for t in targets:
+        h2d += t.bbox.numel() * 4 + t.get_field("labels").numel() * 8
+        h2d += sum(p.numel() * 4 for inst in t.get_field("masks").polygons for p in inst.polygons)
+
+    it_counter = [2000]
+
+    def step(j, e2e):
+        it = it_counter[0]
+        it_counter[0] += 1
+        if e2e:
+            images, targets, views = pool[j % len(pool)]
+            ld, total = trainer.train_step(it, images, fresh_targets(targets), views if mt else None)
+            return float(total)              # D2H of the step's loss (one fp32 scalar) = host sync
+        images, targets, views = resident[j % len(resident)]
+        ld, total = trainer.train_step(it, images, targets, views if mt else None)
+        return total
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(k, e2e):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        last = None
+        for j in range(k):
+            last = step(j, e2e)
+        e1.record()
+        barrier()
+        wall = time.perf_counter() - t0
+        ms = e0.elapsed_time(e1)
+        if e2e:
+            ms = max(ms, wall * 1e3)         # the host is part of the e2e path
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), last
+
+    for j in range(args.warmup):
+        step(j, False)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    lib.reset_launch_count()
+    ms_dev, last = timed(args.steps, False)
+    launches = lib.launch_count()
+    final_loss = float(last)
+    ms_e2e, last_e2e = timed(args.steps, True)
+    clocks = sampler.stop() if sampler else None
+    if not (final_loss == final_loss and abs(final_loss) < 1e6):
+        raise RuntimeError("non-finite / diverged loss in the timed region: %r" % final_loss)
+
+    # roofline leg: the tcgen05 conv kernels bracketed by CUDA events on the launching stream, two more iterations
+    roof, families = None, None
+    pk = peaks()
+    if rank == 0 and not args.no_roofline:
+        lib.prof_enable(True)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        nprof = 2
+        for j in range(nprof):
+            step(j, False)
+        e1.record()
+        torch.cuda.synchronize()
+        prof = lib.prof_collect()
+        lib.prof_enable(False)
+        step_ms_prof = e0.elapsed_time(e1) / nprof
+        tc = [prof[k] for k in ("conv_fprop_tc", "conv_dgrad_tc", "conv_wgrad_tc")]
+        ms_tc = sum(f["ms"] for f in tc)
+        fl_tc = sum(f["flops"] for f in tc)
+        n_tc = sum(f["launches"] for f in tc)
+        achieved = fl_tc / (ms_tc * 1e-3) / 1e12 if ms_tc > 0 else 0.0
+        roof = {"bound": "tensor", "kernel": "conv_tc_kernel<BN> + wgrad_tc_kernel<BN> (TMA + tcgen05 kind::tf32 implicit GEMM)",
+                "achieved": achieved, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": achieved / pk["tensor"],
+                "peak_source": pk["source"] + ": bf16 cuBLAS sustained; the kernel feeds TF32 operands (fp32 storage), whose "
+                "hardware rate is half the bf16 rate, so frac <= 0.5 by construction",
+                "frac_of_tf32_rate": achieved / (pk["tensor"] / 2), "traffic": None,
+                "launches_per_step": n_tc / nprof, "avg_launch_us": ms_tc / max(n_tc, 1) * 1e3,
+                "gflop_per_launch": fl_tc / max(n_tc, 1) / 1e9,
+                "share_of_step": ms_tc / nprof / step_ms_prof}
+        families = {k: {"ms_per_step": v["ms"] / nprof, "launches_per_step": v["launches"] / nprof,
+                        "tflops": (v["flops"] / (v["ms"] * 1e-3) / 1e12) if v["ms"] > 0 and v["flops"] > 0 else None,
+                        "gbs": (v["bytes"] / (v["ms"] * 1e-3) / 1e9) if v["ms"] > 0 else None}
+                    for k, v in prof.items() if v["launches"]}
+        families["step_ms_with_events"] = step_ms_prof
+        conv_flops_step = sum(prof[k]["flops"] for k in ("conv_fprop_tc", "conv_dgrad_tc", "conv_wgrad_tc", "conv_simt")) / nprof
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        del resident
+        torch.cuda.empty_cache()
+        v, per_step, cores = time_cpu_reference(args, 1, 0)
+        cpu = {"value": v, "unit": "images/s", "cores": cores, "kind": "port",
+               "sample": "1 full iteration, no warm-up (2 labeled + 2 unlabeled crops x 3 views, %dx%d): %.1f s" % (args.size, args.size, per_step)}
+
+    if rank == 0:
+        imgs = BATCH * world * args.steps
+        value = imgs / (ms_dev * 1e-3)
+        out = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+               "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
+               "vs_baseline": None, "dtype": "tf32 (fp32 storage and accumulate, TF32 tensor-core operands; losses / NMS / ROIAlign fp32)",
+               "data": "synthetic",
+               "config": {"workload": workload_name(args), "global_batch_labeled": BATCH * world,
+                          "global_batch_unlabeled": BATCH * world if mt else 0, "parallelism": "dp%d" % world,
+                          "l2": "no explicit flush: one iteration streams >10 GB of activations through the 126 MB L2",
+                          "final_loss": final_loss},
+               "e2e": {"value": imgs / (ms_e2e * 1e-3), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                       "ms_per_step": ms_e2e / args.steps},
+               "gpu_launches": launches, "clocks": clocks}
+        if roof:
+            out["roofline"] = roof
+            out["kernel_families"] = families
+            out["conv_roofline_frac_step"] = conv_flops_step / (ms_dev / args.steps * 1e-3) / 1e12 / pk["tensor"]
+            out["conv_tflop_per_step"] = conv_flops_step / 1e12
+        if cpu:
+            out["cpu_baseline"] = cpu
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

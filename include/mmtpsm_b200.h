@@ -34,6 +34,22 @@ const char* mmt_version(void);
 int64_t mmt_launch_count(void);
 void mmt_reset_launch_count(void);
 
+/* Per-kernel-family device timing (off by default; used by bench.py's roofline leg only).
+ * While enabled, every launch of a profiled family is bracketed by two cudaEvents recorded on the
+ * launching stream; `mmt_prof_collect` synchronises those events and returns, per family,
+ * the summed device time [ms], the ALGORITHMIC flops and bytes and the launch count.
+ * Families: */
+#define MMT_PROF_CONV_FPROP 0   /* conv_tc_kernel, forward (tcgen05 implicit GEMM)          */
+#define MMT_PROF_CONV_DGRAD 1   /* conv_tc_kernel, data gradient                            */
+#define MMT_PROF_CONV_WGRAD 2   /* wgrad_tc_kernel, weight gradient                         */
+#define MMT_PROF_CONV_SIMT 3    /* fp32 FFMA convs (stem 7x7, odd channel counts)           */
+#define MMT_PROF_ROI_ALIGN 4    /* ROIAlign forward + backward                              */
+#define MMT_PROF_OPTIM 5        /* fused SGD + EMA                                          */
+#define MMT_PROF_OTHER 6        /* every other kernel of this library                       */
+#define MMT_PROF_FAMILIES 7
+void mmt_prof_enable(int on);
+int mmt_prof_collect(double* ms, double* flops, double* bytes, int64_t* launches, int n_families);
+
 /* ------------------------------------------------------------------------------------------
  * NMS — replaces maskrcnn_benchmark/csrc/nms.h:10-28 (`_C.nms`) and csrc/cuda/nms.cu:23-131.
  * Semantics are those of the CUDA flavour (the one the reference's live path always takes,

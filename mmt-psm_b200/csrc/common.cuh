@@ -13,6 +13,24 @@ namespace mmt {
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
 
+// Optional event bracketing of a kernel family (status.cu); a no-op unless mmt_prof_enable(1).
+bool prof_enabled();
+void prof_begin(cudaStream_t stream);
+void prof_end(int family, double flops, double bytes, cudaStream_t stream);
+struct ProfScope {
+  int family;
+  double flops, bytes;
+  cudaStream_t stream;
+  bool on;
+  ProfScope(int family_, double flops_, double bytes_, cudaStream_t s)
+      : family(family_), flops(flops_), bytes(bytes_), stream(s), on(prof_enabled()) {
+    if (on) prof_begin(stream);
+  }
+  ~ProfScope() {
+    if (on) prof_end(family, flops, bytes, stream);
+  }
+};
+
 inline int fail(int code, const char* fmt, ...) {
   char buf[512];
   va_list ap;

@@ -200,6 +200,7 @@ int conv_fprop_simt(const float* x, const float* w, const float* scale, const fl
   FpropB lb{w, K};
   Epilogue ep{scale, bias, residual, (flags & MMT_EPI_RELU) ? 1 : 0};
   dim3 grid((unsigned)ceil_div<long long>(M, BM), (unsigned)ceil_div(s.out_c, BN), 1);
+  ProfScope prof(MMT_PROF_CONV_SIMT, 2.0 * M * s.out_c * K, 4.0 * (M * (double)s.out_c + (double)s.batch * s.in_h * s.in_w * s.in_c), stream);
   tile_gemm_kernel<FpropA, FpropB, false><<<grid, 256, 0, stream>>>(la, lb, M, s.out_c, K, K, y, ep);
   return check_launch("conv_fprop_simt");
 }
@@ -213,6 +214,7 @@ int conv_dgrad_simt(const float* dy, const float* w, float* dx, const mmt_conv_s
   DgradB lb{w, s};
   Epilogue ep{nullptr, nullptr, nullptr, 0};
   dim3 grid((unsigned)ceil_div<long long>(M, BM), (unsigned)ceil_div(s.in_c, BN), 1);
+  ProfScope prof(MMT_PROF_CONV_SIMT, 2.0 * M * s.in_c * K, 4.0 * (M * (double)s.in_c + (double)s.batch * s.out_h * s.out_w * s.out_c), stream);
   tile_gemm_kernel<DgradA, DgradB, false><<<grid, 256, 0, stream>>>(la, lb, M, s.in_c, K, K, dx, ep);
   return check_launch("conv_dgrad_simt");
 }
@@ -236,6 +238,7 @@ int conv_wgrad_simt(const float* x, const float* dy, float* dw, float* dbias, co
   long long k_chunk = ceil_div<long long>(ceil_div<long long>(P, split), BK) * BK;
   split = (int)ceil_div<long long>(P, k_chunk);
   dim3 grid((unsigned)ceil_div(s.out_c, BM), (unsigned)ceil_div(N, BN), (unsigned)split);
+  ProfScope prof(MMT_PROF_CONV_SIMT, 2.0 * P * s.out_c * N, 4.0 * (P * (double)s.out_c + (double)s.batch * s.in_h * s.in_w * s.in_c), stream);
   tile_gemm_kernel<WgradA, WgradB, true><<<grid, 256, 0, stream>>>(la, lb, s.out_c, N, P, k_chunk, dw, ep);
   if (int rc = check_launch("conv_wgrad_simt")) return rc;
   if (dbias) return conv_bias_grad(dy, P, s.out_c, dbias, stream);

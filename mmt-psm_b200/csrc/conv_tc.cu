@@ -540,7 +540,17 @@ struct GemmProblem {
   const float* residual;  // addressed like y with strides r_*
   long long r_sw, r_sh, r_sn;
   int relu;
+  int prof_family;  // MMT_PROF_CONV_FPROP / MMT_PROF_CONV_DGRAD
 };
+
+// algorithmic cost of one implicit GEMM: 2*M*N*K flops; bytes = A read once + filter + output (+ residual)
+inline double gemm_flops(const GemmProblem& g) {
+  return 2.0 * (double)g.y.n * g.y.h * g.y.w * g.n_out * g.kh * g.kw * g.a.c;
+}
+inline double gemm_bytes(const GemmProblem& g) {
+  const double pix = (double)g.y.n * g.y.h * g.y.w;
+  return 4.0 * (pix * g.a.c + (double)g.n_out * g.kh * g.kw * g.a.c + pix * g.n_out * (g.residual ? 2.0 : 1.0));
+}
 
 template <int BN>
 int launch_gemm(const GemmProblem& g, cudaStream_t stream) {
@@ -573,6 +583,7 @@ int launch_gemm(const GemmProblem& g, cudaStream_t stream) {
     attr_set = true;
   }
   const int grid = (int)std::min<long long>(total, mmt::kNumSMs);
+  mmt::ProfScope prof(g.prof_family, gemm_flops(g), gemm_bytes(g), stream);
   conv_tc_kernel<BN><<<grid, kThreads, C::kSmemBytes, stream>>>(tmA, tmB, tmY, p);
   return mmt::check_launch("conv_tc_kernel");
 }
@@ -649,6 +660,7 @@ int conv_fprop_tc(const float* x, const float* w, const float* scale, const floa
   g.kh = s.k_h; g.kw = s.k_w; g.pad_h = s.pad; g.pad_w = s.pad;
   g.scale = scale; g.bias = bias; g.residual = residual;
   g.relu = (flags & MMT_EPI_RELU) ? 1 : 0;
+  g.prof_family = MMT_PROF_CONV_FPROP;
   return dispatch_gemm(g, stream);
 }
 
@@ -673,6 +685,7 @@ int conv_dgrad_tc(const float* dy, const float* w_t, float* dx, const mmt_conv_s
   g.b = w_t; g.n_out = s.in_c;
   g.kh = s.k_h; g.kw = s.k_w; g.pad_h = s.k_h - 1 - s.pad; g.pad_w = s.k_w - 1 - s.pad;
   g.scale = nullptr; g.bias = nullptr; g.residual = nullptr; g.relu = 0;
+  g.prof_family = MMT_PROF_CONV_DGRAD;
   return dispatch_gemm(g, stream);
 }
 
@@ -728,6 +741,9 @@ int conv_wgrad_tc(const float* x, const float* dy, float* dw, float* dbias, cons
   p.tiles_per_split = (int)ceil_div<long long>(ptiles, splits);
   p.splits = (int)ceil_div<long long>(ptiles, p.tiles_per_split);
   p.total_items = base_items * p.splits;
+  const double pix = (double)vdy.n * vdy.h * vdy.w;
+  mmt::ProfScope prof(MMT_PROF_CONV_WGRAD, 2.0 * pix * s.out_c * (double)Ktot,
+                      4.0 * (pix * (s.out_c + s.in_c) + (double)s.out_c * Ktot), stream);
   if (BN == 256) return launch_wgrad<256>(tmDY, tmX, tmDW, p, stream);
   if (BN == 128) return launch_wgrad<128>(tmDY, tmX, tmDW, p, stream);
   return launch_wgrad<64>(tmDY, tmX, tmDW, p, stream);

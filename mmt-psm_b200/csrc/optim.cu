@@ -130,6 +130,8 @@ extern "C" int mmt_sgd_ema_f32(float* student, float* teacher, const float* grad
   MMT_REQUIRE(((uintptr_t)student % 16 == 0) && ((uintptr_t)grad % 16 == 0) &&
                   ((uintptr_t)momentum_buf % 16 == 0) && (!teacher || (uintptr_t)teacher % 16 == 0),
               "sgd_ema: arenas must be 16-byte aligned");
+  // student / momentum read+write, grad read, teacher read+write
+  mmt::ProfScope prof(MMT_PROF_OPTIM, 0.0, 4.0 * n * (teacher ? 7.0 : 5.0), (cudaStream_t)stream_);
   sgd_ema_kernel<<<stream_grid((n + 3) / 4), 256, 0, (cudaStream_t)stream_>>>(
       student, teacher, grad, momentum_buf, n, segments_dev, n_segments, momentum, alpha,
       1.f - alpha, first_step, grad_scale);

@@ -499,6 +499,8 @@ extern "C" int mmt_roi_align_fpn_forward_f32(const float* const* level_feats_hos
   if (int rc = fill_level_tab(tab, level_feats_host, nullptr, level_h_host, level_w_host, level_scale_host,
                               n_levels, "roi_align_fpn_forward")) return rc;
   const long long total = (long long)n_rois * pooled_h * pooled_w * (channels / 4);
+  // algorithmic bytes: the pooled output written once (the taps are gathers from L2-resident maps)
+  mmt::ProfScope prof(MMT_PROF_ROI_ALIGN, 0.0, 16.0 * total, (cudaStream_t)stream_);
   roi_align_fpn_fwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream_>>>(
       tab, channels, rois, roi_levels, pooled_h, pooled_w, sampling_ratio, output, total);
   return mmt::check_launch("roi_align_fpn_forward");
@@ -519,6 +521,7 @@ extern "C" int mmt_roi_align_fpn_backward_f32(const float* grad_output, const fl
   if (int rc = fill_level_tab(tab, nullptr, level_grads_host, level_h_host, level_w_host, level_scale_host,
                               n_levels, "roi_align_fpn_backward")) return rc;
   const long long total = (long long)n_rois * pooled_h * pooled_w * (channels / 4);
+  mmt::ProfScope prof(MMT_PROF_ROI_ALIGN, 0.0, 16.0 * total, (cudaStream_t)stream_);
   roi_align_fpn_bwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream_>>>(
       tab, channels, grad_output, rois, roi_levels, pooled_h, pooled_w, sampling_ratio, total);
   return mmt::check_launch("roi_align_fpn_backward");

@@ -32,6 +32,9 @@ _PROTOS = {
     "mmt_version": (c_char_p, []),
     "mmt_launch_count": (c_int64, []),
     "mmt_reset_launch_count": (None, []),
+    "mmt_prof_enable": (None, [c_int]),
+    "mmt_prof_collect": (c_int, [POINTER(ctypes.c_double), POINTER(ctypes.c_double), POINTER(ctypes.c_double),
+                                 POINTER(c_int64), c_int]),
     "mmt_nms_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "mmt_nms_segmented_f32": (c_int, [P, P, POINTER(c_int), c_int, c_float, P, P, P, c_size_t, P]),
     "mmt_nms_f32": (c_int, [P, P, c_int, c_float, P, P, P, c_size_t, P]),
@@ -113,3 +116,19 @@ def launch_count():
 
 def reset_launch_count():
     lib().mmt_reset_launch_count()
+
+
+PROF_FAMILIES = ("conv_fprop_tc", "conv_dgrad_tc", "conv_wgrad_tc", "conv_simt", "roi_align", "sgd_ema", "other")
+
+
+def prof_enable(on=True):
+    lib().mmt_prof_enable(1 if on else 0)
+
+
+def prof_collect():
+    """{family: dict(ms, flops, bytes, launches)} for everything recorded since prof_enable(True)."""
+    n = len(PROF_FAMILIES)
+    ms, fl, by = (ctypes.c_double * n)(), (ctypes.c_double * n)(), (ctypes.c_double * n)()
+    cnt = (c_int64 * n)()
+    check(lib().mmt_prof_collect(ms, fl, by, cnt, n), "prof_collect")
+    return {k: dict(ms=ms[i], flops=fl[i], bytes=by[i], launches=int(cnt[i])) for i, k in enumerate(PROF_FAMILIES)}

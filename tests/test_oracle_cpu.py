@@ -32,7 +32,7 @@ def test_nms_threshold_flavours_differ_at_exact_iou():
 
 
 def test_nms_oracle_vs_compiled_reference():
-    ref = pytest.importorskip("oracle_ref_C", reason="oracle/_ref/_C not built")
+    ref = pytest.importorskip("oracle_ref_C", reason="oracle/_ref/_C not built", exc_type=ImportError)
     g = torch.Generator().manual_seed(5)
     for n in (0, 1, 50, 400):
         b = torch.rand(n, 4, generator=g) * 100

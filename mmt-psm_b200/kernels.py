@@ -16,6 +16,22 @@ from .lib import ConvShape, Strides4, check
 CONV_AUTO, CONV_TCGEN05, CONV_SIMT = 0, 1, 2
 EPI_RELU = 1
 
+# Process-wide conv math mode, the analogue of `torch.backends.cudnn.allow_tf32` (which the reference leaves at its
+# default, True): "tf32" = tcgen05 kind::tf32 implicit GEMM wherever the shape allows (default), "fp32" = the fp32
+# FFMA kernels everywhere (bit-for-bit fp32 multiply-adds; used by the step-level parity tests).
+_conv_impl = CONV_AUTO
+
+
+def set_conv_math(mode):
+    global _conv_impl
+    if mode not in ("tf32", "fp32"):
+        raise ValueError("conv math mode must be 'tf32' or 'fp32'")
+    _conv_impl = CONV_AUTO if mode == "tf32" else CONV_SIMT
+
+
+def get_conv_math():
+    return "tf32" if _conv_impl == CONV_AUTO else "fp32"
+
 
 def _need_cuda(*tensors):
     for t in tensors:
@@ -362,10 +378,11 @@ def conv_shape(batch, in_h, in_w, in_c, out_c, k, stride, pad):
     return ConvShape(batch, in_h, in_w, in_c, out_c, k, k, stride, pad, oh, ow)
 
 
-def conv_fprop(x, w, shape, scale=None, bias=None, residual=None, relu=False, impl=CONV_AUTO, out=None):
+def conv_fprop(x, w, shape, scale=None, bias=None, residual=None, relu=False, impl=None, out=None):
     """x NHWC [B,H,W,Ci] dense, w OHWI [Co,kh,kw,Ci] dense -> y NHWC [B,OH,OW,Co]."""
     _need_cuda(x, w, scale, bias, residual)
     L = _l.lib()
+    impl = _conv_impl if impl is None else impl
     assert x.is_contiguous() and w.is_contiguous() and x.dtype == torch.float32 and w.dtype == torch.float32
     y = out if out is not None else torch.empty((shape.batch, shape.out_h, shape.out_w, shape.out_c),
                                                 dtype=torch.float32, device=x.device)
@@ -374,9 +391,10 @@ def conv_fprop(x, w, shape, scale=None, bias=None, residual=None, relu=False, im
     return y
 
 
-def conv_dgrad(dy, w, shape, impl=CONV_AUTO):
+def conv_dgrad(dy, w, shape, impl=None):
     _need_cuda(dy, w)
     L = _l.lib()
+    impl = _conv_impl if impl is None else impl
     assert dy.is_contiguous() and w.is_contiguous()
     dx = torch.empty((shape.batch, shape.in_h, shape.in_w, shape.in_c), dtype=torch.float32, device=dy.device)
     wsb = L.mmt_conv_workspace_bytes(ctypes.byref(shape))
@@ -386,9 +404,10 @@ def conv_dgrad(dy, w, shape, impl=CONV_AUTO):
     return dx
 
 
-def conv_wgrad(x, dy, shape, want_dbias=False, impl=CONV_AUTO):
+def conv_wgrad(x, dy, shape, want_dbias=False, impl=None):
     _need_cuda(x, dy)
     L = _l.lib()
+    impl = _conv_impl if impl is None else impl
     assert x.is_contiguous() and dy.is_contiguous()
     dw = torch.empty((shape.out_c, shape.k_h, shape.k_w, shape.in_c), dtype=torch.float32, device=x.device)
     db = torch.empty(shape.out_c, dtype=torch.float32, device=x.device) if want_dbias else None

@@ -5,9 +5,12 @@ There is no network access for the ImageNet / COCO checkpoint the reference star
 default random conv weights explodes numerically.  `synthetic_state_dict` produces, for any {name: shape} table in
 the REFERENCE's layout, the same tensors on every machine (torch CPU generator seeded per name), scaled so
 activations stay O(1): He-normal convs, frozen-BN scale 1 on the bottleneck's inner convs and the downsample (skip) branch, 0.25 on the
-residual-closing conv3, 1/64 on the stem (pixel range -> O(1)).  Used by bench.py, smoke() and the step-level parity fixtures (the
+residual-closing conv3, 1/64 on the stem (pixel range -> O(1)), and MGD adaptors at 0.1 x He (a trained student / teacher
+pair maps the views to nearby embeddings; with unit-scale random adaptors the un-normalised L2 hint loss starts at O(1) and
+SGD at the cfg learning rate diverges within 5 iterations — measured, profiles/r01_loss_trace_*.log).  Used by bench.py, smoke() and the step-level parity fixtures (the
 reference model is loaded with exactly the same dict)."""
 import math
+import os
 import zlib
 
 import torch
@@ -17,7 +20,9 @@ def _gen(name, seed):
     return torch.Generator().manual_seed((zlib.crc32(name.encode()) + 1000003 * seed) % (2 ** 31))
 
 
-def synthetic_state_dict(shapes, seed=0):
+def synthetic_state_dict(shapes, seed=0, adaptor_scale=None):
+    if adaptor_scale is None:
+        adaptor_scale = float(os.environ.get("MMT_SYNTH_ADAPTOR_SCALE", "0.1"))
     out = {}
     for name, shape in shapes.items():
         g = _gen(name, seed)
@@ -44,6 +49,8 @@ def synthetic_state_dict(shapes, seed=0):
             std = math.sqrt(2.0 / fan_in)
             if any(k in name for k in ("cls_logits", "bbox_pred", "mask_fcn_logits")):
                 std = 0.01
+            if "hint_adaptor" in name:
+                std *= adaptor_scale                     # trained adaptors map both networks to nearby embeddings
             if "fpn_layer" in name:
                 std *= 0.25                              # pyramid outputs O(1): what the heads of a trained net see
             t = torch.randn(shape, generator=g) * std

@@ -44,10 +44,13 @@ template <int BN>
 struct Cfg {
   static constexpr int kBBytes = BN * 128;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStagesRaw = (kSmemLimit - 2 * kStagingBytes - 2048) / kStageBytes;
+  static constexpr int kAffineBytes = 2 * BN * 4;  // per-tile copy of the epilogue scale / shift vectors
+  static constexpr int kFixedBytes = 2 * kStagingBytes + kAffineBytes + 256 /*barriers*/;
+  static constexpr int kStagesRaw = (kSmemLimit - kFixedBytes) / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr int kTmemCols = 2 * BN;  // 128 / 256 / 512: powers of two >= 32
-  static constexpr int kSmemBytes = kStages * kStageBytes + 2 * kStagingBytes + 1024 /*align*/ + 256 /*barriers*/;
+  // the dynamic shared window is declared __align__(1024) (SWIZZLE_128B atoms); the kernels trap if it is not
+  static constexpr int kSmemBytes = kStages * kStageBytes + kFixedBytes;
 };
 
 struct FpropParams {
@@ -64,6 +67,7 @@ struct FpropParams {
   const float* residual;
   int relu;
   int total_tiles;
+  int sub_w;  // per-warp store box: 32 pixels = sub_w x (32 / sub_w) of the TW x TH patch
 };
 
 __device__ __forceinline__ void named_bar_sync(int id, int threads) {
@@ -72,25 +76,27 @@ __device__ __forceinline__ void named_bar_sync(int id, int threads) {
 
 struct SmemLayout {
   uint32_t a[8], b[8];
-  uint32_t staging[2];
+  uint32_t staging;  // 4 epilogue warps x 2 buffers x 4 KB (32 rows x 128 B, SWIZZLE_128B)
+  uint32_t affine;   // scale[BN] then shift[BN]
   uint32_t full[8], empty[8], tfull[2], tempty[2];
   uint32_t tmem_slot;
 };
 
-template <int STAGES, int A_BYTES, int B_BYTES>
+template <int STAGES, int A_BYTES, int B_BYTES, int AFFINE_BYTES>
 __device__ __forceinline__ SmemLayout carve(uint8_t* raw) {
   SmemLayout L;
-  uint32_t base = smem_u32(raw);
-  base = (base + 1023u) & ~1023u;
+  const uint32_t base = smem_u32(raw);
+  if (base & 1023u) __trap();  // extern __shared__ __align__(1024) was not honoured
 #pragma unroll
   for (int s = 0; s < 8; ++s) {
     L.a[s] = base + (s < STAGES ? s : 0) * (A_BYTES + B_BYTES);
     L.b[s] = L.a[s] + A_BYTES;
   }
   uint32_t p = base + STAGES * (A_BYTES + B_BYTES);
-  L.staging[0] = p;
-  L.staging[1] = p + kStagingBytes;
+  L.staging = p;
   p += 2 * kStagingBytes;
+  L.affine = p;
+  p += AFFINE_BYTES;
 #pragma unroll
   for (int s = 0; s < 8; ++s) {
     L.full[s] = p + 8 * s;
@@ -112,6 +118,14 @@ __device__ __forceinline__ uint32_t ld_shared_u32(uint32_t addr) {
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, float x, float y, float z, float w) {
   asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
 }
+__device__ __forceinline__ float4 ld_shared_v4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_shared_f32(uint32_t addr, float x) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(x) : "memory");
+}
 
 template <int BN>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -119,8 +133,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                const __grid_constant__ CUtensorMap tmY, const FpropParams p) {
   using C = Cfg<BN>;
   constexpr int STAGES = C::kStages;
-  extern __shared__ uint8_t smem_raw[];
-  const SmemLayout L = carve<STAGES, kABytes, C::kBBytes>(smem_raw);
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const SmemLayout L = carve<STAGES, kABytes, C::kBBytes, C::kAffineBytes>(smem_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
@@ -136,8 +150,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       mbar_init(L.tfull[0], 1);
       mbar_init(L.tfull[1], 1);
-      mbar_init(L.tempty[0], 1);
-      mbar_init(L.tempty[1], 1);
+      mbar_init(L.tempty[0], 4);  // one arrival per epilogue warp
+      mbar_init(L.tempty[1], 4);
       fence_barrier_init();
     }
     __syncwarp();
@@ -203,11 +217,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncwarp();
   } else {
     // ------------------------------------------------------------------ epilogue (warps 2..5)
-    const int q = warp & 3;            // TMEM lane quadrant this warp may access
-    const int row = q * 32 + lane;     // pixel index inside the tile
+    // Each warp owns one TMEM lane quadrant = 32 pixels of the tile and runs on its own: private staging
+    // buffers, private TMA stores (bulk groups are per thread: lane 0), no CTA-wide barrier per chunk.
+    const int q = warp & 3;         // TMEM lane quadrant this warp may access
+    const int row = q * 32 + lane;  // pixel index inside the tile (this thread's accumulator row)
     const int epi_tid = threadIdx.x - 64;
+    const uint32_t stage0 = L.staging + (uint32_t)q * 8192u;
     const int tw = row % p.TW, th = row / p.TW;
+    const int sub_tw0 = (q * 32) % p.TW, sub_th0 = (q * 32) / p.TW;  // origin of this warp's 32-pixel store box
+    const bool affine = (p.scale != nullptr) || (p.bias != nullptr);
+    const bool has_res = p.residual != nullptr;
+    // coalesced residual fetch: instruction i reads rows 4i + lane/8 (four whole 128-byte lines per warp instruction)
+    const int col4 = lane & 7;
+    int rtw[8], rth[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = q * 32 + 4 * i + (lane >> 3);
+      rtw[i] = r % p.TW;
+      rth[i] = r / p.TW;
+    }
     int it = 0;
+    int affine_nt = -1;
     uint32_t chunk_counter = 0;
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
       const int nt = t % p.n_tiles, mt = t / p.n_tiles;
@@ -215,56 +245,97 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int h0 = (rem / p.tiles_w) * p.TH, w0 = (rem % p.tiles_w) * p.TW;
       const int acc = it & 1;
       const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+      const int n0 = nt * BN;
+      const int chunks = min(BN / 32, (p.n_out - n0 + 31) / 32);
+
+      if (affine && nt != affine_nt) {  // (re)load this column block's scale / shift: uniform over the 4 warps
+        named_bar_sync(1, 128);         // every warp is done reading the previous block's values
+        for (int c = epi_tid; c < BN; c += 128) {
+          const int col = n0 + c;
+          const bool ok = col < p.n_out;
+          st_shared_f32(L.affine + 4 * c, (ok && p.scale) ? __ldg(p.scale + col) : 1.f);
+          st_shared_f32(L.affine + 4 * (BN + c), (ok && p.bias) ? __ldg(p.bias + col) : 0.f);
+        }
+        named_bar_sync(1, 128);
+        affine_nt = nt;
+      }
+
+      // residual rows of this tile (element offsets) and the first chunk's prefetch, before waiting on the MMAs
+      long long roff[8];
+      bool rok[8];
+      float4 rr[8];
+      if (has_res) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          rok[i] = (w0 + rtw[i] < p.y_w) && (h0 + rth[i] < p.y_h);
+          roff[i] = b * p.r_sb + (long long)(h0 + rth[i]) * p.r_sh + (long long)(w0 + rtw[i]) * p.r_sw + col4 * 4;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          rr[i] = (rok[i] && n0 + col4 * 4 < p.n_out) ? __ldg(reinterpret_cast<const float4*>(p.residual + roff[i] + n0))
+                                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+
       mbar_wait(L.tfull[acc], acc_phase);
       tc_fence_after();
-      const bool pix_ok = (w0 + tw < p.y_w) && (h0 + th < p.y_h);
-      const float* res_row = p.residual
-                                 ? p.residual + b * p.r_sb + (long long)(h0 + th) * p.r_sh + (long long)(w0 + tw) * p.r_sw
-                                 : nullptr;
 #pragma unroll 1
-      for (int j = 0; j < BN / 32; ++j, ++chunk_counter) {
-        const uint32_t buf = L.staging[chunk_counter & 1u];
-        if (epi_tid == 0) tma_wait_group_read<1>();  // the buffer used two chunks ago has been read
-        named_bar_sync(1, 128);
+      for (int j = 0; j < chunks; ++j, ++chunk_counter) {
+        const uint32_t buf = stage0 + (chunk_counter & 1u) * 4096u;
+        const int c0 = n0 + j * 32;
+        if (lane == 0) tma_wait_group_read<1>();  // the store that used this buffer two chunks ago has read it
+        __syncwarp();
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + j * 32), v);
+        if (has_res) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = 4 * i + (lane >> 3);
+            st_shared_v4(buf + r * 128 + ((col4 ^ (r & 7)) << 4), rr[i].x, rr[i].y, rr[i].z, rr[i].w);
+          }
+          if (j + 1 < chunks) {  // prefetch the next chunk's residual while this one is processed
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              rr[i] = (rok[i] && c0 + 32 + col4 * 4 < p.n_out)
+                          ? __ldg(reinterpret_cast<const float4*>(p.residual + roff[i] + c0 + 32))
+                          : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          __syncwarp();
+        }
         tmem_ld_wait();
-        tc_fence_before();
-        const int c0 = nt * BN + j * 32;
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
-          float o[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            float x = __uint_as_float(v[g * 4 + e]);
-            const int c = c0 + g * 4 + e;
-            if (c < p.n_out) {
-              if (p.scale) x *= __ldg(p.scale + c);
-              if (p.bias) x += __ldg(p.bias + c);
-            }
-            o[e] = x;
+          float o0 = __uint_as_float(v[g * 4 + 0]), o1 = __uint_as_float(v[g * 4 + 1]);
+          float o2 = __uint_as_float(v[g * 4 + 2]), o3 = __uint_as_float(v[g * 4 + 3]);
+          if (affine) {
+            const float4 sc = ld_shared_v4(L.affine + 4 * (j * 32 + g * 4));
+            const float4 sh = ld_shared_v4(L.affine + 4 * (BN + j * 32 + g * 4));
+            o0 = fmaf(o0, sc.x, sh.x); o1 = fmaf(o1, sc.y, sh.y);
+            o2 = fmaf(o2, sc.z, sh.z); o3 = fmaf(o3, sc.w, sh.w);
           }
-          if (res_row != nullptr && pix_ok && c0 + g * 4 < p.n_out) {
-            const float4 rr = __ldg(reinterpret_cast<const float4*>(res_row + c0 + g * 4));
-            o[0] += rr.x; o[1] += rr.y; o[2] += rr.z; o[3] += rr.w;
+          const uint32_t addr = buf + lane * 128 + ((g ^ (lane & 7)) << 4);
+          if (has_res) {
+            const float4 r4 = ld_shared_v4(addr);
+            o0 += r4.x; o1 += r4.y; o2 += r4.z; o3 += r4.w;
           }
           if (p.relu) {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) o[e] = fmaxf(o[e], 0.f);
+            o0 = fmaxf(o0, 0.f); o1 = fmaxf(o1, 0.f); o2 = fmaxf(o2, 0.f); o3 = fmaxf(o3, 0.f);
           }
-          st_shared_v4(buf + row * 128 + ((g ^ (row & 7)) << 4), o[0], o[1], o[2], o[3]);
+          st_shared_v4(addr, o0, o1, o2, o3);
         }
         fence_proxy_async_smem();
-        named_bar_sync(1, 128);
-        if (epi_tid == 0) {
-          tma_store_4d(&tmY, buf, c0, w0, h0, b);
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_4d(&tmY, buf, c0, w0 + sub_tw0, h0 + sub_th0, b);
           tma_commit_group();
         }
       }
-      // every epilogue thread has finished its tcgen05.ld of this accumulator (barrier above)
-      if (epi_tid == 0) mbar_arrive(L.tempty[acc]);
+      // this warp has finished its tcgen05.ld of the accumulator
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(L.tempty[acc]);
     }
-    if (epi_tid == 0) tma_wait_group<0>();
+    if (lane == 0) tma_wait_group<0>();
+    (void)tw; (void)th;
   }
 
   tc_fence_before();
@@ -292,8 +363,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
                 const __grid_constant__ CUtensorMap tmDW, const WgradParams p) {
   using C = Cfg<BN>;
   constexpr int STAGES = C::kStages;
-  extern __shared__ uint8_t smem_raw[];
-  const SmemLayout L = carve<STAGES, kABytes, C::kBBytes>(smem_raw);
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const SmemLayout L = carve<STAGES, kABytes, C::kBBytes, C::kAffineBytes>(smem_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
@@ -406,7 +477,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
       tc_fence_after();
 #pragma unroll 1
       for (int j = 0; j < BN / 32; ++j, ++chunk_counter) {
-        const uint32_t buf = L.staging[chunk_counter & 1u];
+        const uint32_t buf = L.staging + (chunk_counter & 1u) * (uint32_t)kStagingBytes;
         if (epi_tid == 0) tma_wait_group_read<1>();
         named_bar_sync(1, 128);
         uint32_t v[32];
@@ -561,7 +632,8 @@ int launch_gemm(const GemmProblem& g, cudaStream_t stream) {
   if (int rc = make_map(&tmA, g.a, 32, TW, TH, "conv A operand")) return rc;
   const long long Ktot = (long long)g.kh * g.kw * g.a.c;
   if (int rc = make_map_2d(&tmB, g.b, Ktot, g.n_out, Ktot, 32, BN, "conv filter")) return rc;
-  if (int rc = make_map(&tmY, g.y, 32, TW, TH, "conv output")) return rc;
+  const int sub_w = TW < 32 ? TW : 32;  // each epilogue warp stores its own 32-pixel box
+  if (int rc = make_map(&tmY, g.y, 32, sub_w, 32 / sub_w, "conv output")) return rc;
   FpropParams p;
   p.tiles_w = (int)mmt::ceil_div<long long>(g.y.w, TW);
   p.tiles_h = (int)mmt::ceil_div<long long>(g.y.h, TH);
@@ -577,6 +649,7 @@ int launch_gemm(const GemmProblem& g, cudaStream_t stream) {
   const long long total = (long long)p.tiles_w * p.tiles_h * p.tiles_b * p.n_tiles;
   if (total > 0x7fffffffll) return mmt::fail(MMT_ERR_UNSUPPORTED, "conv: too many tiles");
   p.total_tiles = (int)total;
+  p.sub_w = sub_w;
   static bool attr_set = false;
   if (!attr_set) {
     MMT_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));

@@ -33,6 +33,9 @@ const char* mmt_version(void);
  * (used by bench.py for the "gpu_launches" claim). */
 int64_t mmt_launch_count(void);
 void mmt_reset_launch_count(void);
+/* Kernels of this library replayed from a CUDA graph are launched by the driver, not through the entry points that
+ * count; the host wrapper that replays a captured graph adds the number it recorded at capture time. */
+void mmt_add_launch_count(int64_t n);
 
 /* Per-kernel-family device timing (off by default; used by bench.py's roofline leg only).
  * While enabled, every launch of a profiled family is bracketed by two cudaEvents recorded on the
@@ -68,6 +71,20 @@ size_t mmt_nms_workspace_bytes(int total_boxes, int n_segments, int max_segment_
 int mmt_nms_segmented_f32(const float* boxes_xyxy, const float* scores, const int* seg_offsets_host,
                           int n_segments, float iou_threshold, int64_t* keep_out, int* n_keep_out,
                           void* workspace, size_t workspace_bytes, void* stream);
+/* ------------------------------------------------------------------------------------------
+ * Proposal decoding: BoxCoder.decode + BoxList.clip_to_image(remove_empty=False) + remove_small_boxes in one pass
+ * (reference modeling/box_coder.py:56-95, structures/bounding_box.py:211-221, structures/boxlist_ops.py:37-54,
+ * called per level and image from modeling/rpn/inference.py:107-124).  Candidates are laid out image-major:
+ * `per_image` consecutive rows belong to image i = row / per_image.
+ * deltas, anchors [n_images*per_image, 4] fp32 (16-byte aligned); scores [rows] or NULL;
+ * image_wh [n_images, 2] fp32 (width, height) on the device, or NULL for no clipping;
+ * weights (wx, wy, ww, wh), xform_clip = log(1000/16), min_size <= 0 disables the size filter.
+ * boxes [rows,4]; scores_nms [rows] (= score if the box passes the size filter else -1) or NULL;
+ * valid [rows] uint8 or NULL. */
+int mmt_decode_clip_boxes_f32(const float* deltas, const float* anchors, const float* scores,
+                              const float* image_wh, int n_images, int per_image, float wx, float wy,
+                              float ww, float wh, float xform_clip, float min_size, float* boxes,
+                              float* scores_nms, unsigned char* valid, void* stream);
 /* Single problem convenience form (exactly `_C.nms(dets, scores, thr)` minus the tensor plumbing). */
 int mmt_nms_f32(const float* boxes_xyxy, const float* scores, int n, float iou_threshold,
                 int64_t* keep_out, int* n_keep_out, void* workspace, size_t workspace_bytes,

@@ -53,6 +53,7 @@ const char* mmt_last_error(void) { return mmt::g_err; }
 const char* mmt_version(void) { return "mmtpsm_b200 0.1 (sm_100a)"; }
 int64_t mmt_launch_count(void) { return mmt::g_launches.load(); }
 void mmt_reset_launch_count(void) { mmt::g_launches.store(0); }
+void mmt_add_launch_count(int64_t n) { mmt::g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 void mmt_prof_enable(int on) {
   std::lock_guard<std::mutex> lk(mmt::g_prof_mu);

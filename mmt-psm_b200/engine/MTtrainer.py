@@ -49,7 +49,8 @@ def weight_sum_losses(loss_dict, step, rampup_length, rampdown_length, total_len
 
 
 class MTtrainer(object):
-    def __init__(self, model_s, model_t, data_loader, optimizer, scheduler, ckpt_s, ckpt_t, checkpoint_period, cfg):
+    def __init__(self, model_s, model_t, data_loader, optimizer, scheduler, ckpt_s, ckpt_t, checkpoint_period, cfg,
+                 cuda_graphs=False):
         self.cfg = cfg
         self.logger = logging.getLogger("maskrcnn_benchmark.trainer")
         self.scheduler = scheduler
@@ -71,6 +72,13 @@ class MTtrainer(object):
         self.n_step_unlabel = cfg.MT.N_STEP_UNLABEL
         self.world = get_world_size()
         self.last_losses = None
+        self.set_cuda_graphs(cuda_graphs)
+
+    def set_cuda_graphs(self, on):
+        """Replay the fixed-shape conv trunks of both networks from CUDA graphs (fixed-size crops only)."""
+        self.cuda_graphs = bool(on)
+        self.student.enable_cuda_graphs(on, getattr(self.optimizer, "mark_touched", None))
+        self.teacher.enable_cuda_graphs(on)
 
     def weight_sum_loss(self, loss_dict, step):
         return weight_sum_losses(loss_dict, step, self.rampup_step, self.rampdown_step, self.max_iter,

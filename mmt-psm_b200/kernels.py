@@ -95,6 +95,34 @@ def nms(dets, scores, iou_threshold):
     return keep[: int(counts[0].item())]
 
 
+def decode_clip_boxes(deltas, anchors, weights, xform_clip, image_wh=None, per_image=None, scores=None, min_size=0.0):
+    """Fused BoxCoder.decode + clip_to_image + remove_small_boxes over image-major candidate rows.
+    deltas / anchors [T,4]; image_wh device tensor [N,2] (w,h) or None; returns (boxes [T,4], scores_nms [T] or None,
+    valid [T] bool or None)."""
+    _need_cuda(deltas, anchors, scores, image_wh)
+    L = _l.lib()
+    deltas, anchors = _f32c(deltas), _f32c(anchors)
+    T = deltas.shape[0]
+    assert anchors.shape == deltas.shape == (T, 4)
+    boxes = torch.empty_like(deltas)
+    want_valid = min_size > 0
+    s_nms = torch.empty(T, dtype=torch.float32, device=deltas.device) if scores is not None else None
+    valid = torch.empty(T, dtype=torch.bool, device=deltas.device) if want_valid else None
+    if image_wh is not None:
+        n_images = image_wh.shape[0]
+        per_image = T // max(n_images, 1) if per_image is None else per_image
+        assert n_images * per_image == T
+    else:
+        n_images, per_image = 1, T
+    if scores is not None:
+        scores = _f32c(scores)
+    wx, wy, ww, wh = weights
+    check(L.mmt_decode_clip_boxes_f32(_p(deltas), _p(anchors), _p(scores), _p(image_wh), n_images, per_image, float(wx),
+                                      float(wy), float(ww), float(wh), float(xform_clip), float(min_size), _p(boxes),
+                                      _p(s_nms), _p(valid), _stream()), "decode_clip_boxes")
+    return boxes, s_nms, valid
+
+
 # ---------------------------------------------------------------------------------- ROIAlign
 def roi_align_forward(input, rois, spatial_scale, pooled_h, pooled_w, sampling_ratio):
     """`_C.roi_align_forward` (reference csrc/ROIAlign.h:11-26): NCHW in -> [K,C,ph,pw] out.

@@ -32,12 +32,15 @@ _PROTOS = {
     "mmt_version": (c_char_p, []),
     "mmt_launch_count": (c_int64, []),
     "mmt_reset_launch_count": (None, []),
+    "mmt_add_launch_count": (None, [c_int64]),
     "mmt_prof_enable": (None, [c_int]),
     "mmt_prof_collect": (c_int, [POINTER(ctypes.c_double), POINTER(ctypes.c_double), POINTER(ctypes.c_double),
                                  POINTER(c_int64), c_int]),
     "mmt_nms_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "mmt_nms_segmented_f32": (c_int, [P, P, POINTER(c_int), c_int, c_float, P, P, P, c_size_t, P]),
     "mmt_nms_f32": (c_int, [P, P, c_int, c_float, P, P, P, c_size_t, P]),
+    "mmt_decode_clip_boxes_f32": (c_int, [P, P, P, P, c_int, c_int, c_float, c_float, c_float, c_float, c_float,
+                                          c_float, P, P, P, P]),
     "mmt_roi_align_forward_f32": (c_int, [P, Strides4, c_int, c_int, c_int, c_int, P, c_int, c_float,
                                           c_int, c_int, c_int, P, Strides4, P]),
     "mmt_roi_align_backward_f32": (c_int, [P, Strides4, P, c_int, c_float, c_int, c_int, c_int, P,
@@ -116,6 +119,10 @@ def launch_count():
 
 def reset_launch_count():
     lib().mmt_reset_launch_count()
+
+
+def add_launch_count(n):
+    lib().mmt_add_launch_count(int(n))
 
 
 PROF_FAMILIES = ("conv_fprop_tc", "conv_dgrad_tc", "conv_wgrad_tc", "conv_simt", "roi_align", "sgd_ema", "other")

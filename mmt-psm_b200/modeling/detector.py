@@ -72,6 +72,59 @@ class GeneralizedRCNN(nn.Module):
         self.mt_fg_hint = cfg.MT.FG_HINT
         self.mt_cls = cfg.MT.CLS_LOSS
         self.hint_adaptor = MaskRCNNFPNAdaptor(cfg)
+        self._graphs, self._graphs_on, self._graph_on_backward = {}, False, None
+
+    # ------------------------------------------------------------------------------ CUDA graphs
+    def enable_cuda_graphs(self, on=True, on_backward=None):
+        """Replay the static-shape conv trunk (backbone + FPN) from CUDA graphs, one captured instance per call site
+        and input shape (utils/cuda_graphs.py).  `on_backward(params)` tells the optimizer which parameters the
+        replayed backward accumulated into (their post-accumulate hooks only fire at capture time)."""
+        self._graphs_on, self._graph_on_backward = bool(on), on_backward
+        if not on:
+            self._graphs = {}
+
+    def _trunk_fn(self, site, n_views=1):
+        """The fixed-shape part of a pass as one function of the image batch: backbone + FPN, then
+        'sup': the RPN head;  'aug' (teacher, n_views stacked views): MGD adaptors on every view and the RPN head on
+        view 0;  'unl' (student, unlabeled view): MGD adaptors.  Returns a flat tuple (5 features [+5 emb] [+5 rpn])."""
+        want_emb = site != "sup" and bool(self.cfg.MT.FG_HINT or self.cfg.MT.HINT or self.cfg.MT.ODKD)
+
+        def fn(x):
+            feats = tuple(self.backbone(x))
+            out = feats
+            if want_emb:
+                out = out + tuple(self.hint_adaptor(feats))
+            if site != "unl":
+                B = x.shape[0] // n_views
+                out = out + tuple(self.rpn.head.forward_fused([f[:B] for f in feats] if n_views > 1 else list(feats)))
+            return out
+        return fn, want_emb
+
+    def _trunk(self, site, x, n_views=1):
+        """Runs (or replays from a CUDA graph) the trunk of call site `site`; returns dict(features, emb, rpn)."""
+        fn, want_emb = self._trunk_fn(site, n_views)
+        if not (self._graphs_on and x.is_cuda):
+            flat = fn(x)
+        else:
+            from ..utils.cuda_graphs import GraphedCallable
+            need_grad = torch.is_grad_enabled() and self.training
+            key = (site, tuple(x.shape), n_views, need_grad)
+            g = self._graphs.get(key)
+            if g is None:
+                if len(self._graphs) >= 8:
+                    raise RuntimeError("more than 8 distinct (call site, input shape) trunks captured; CUDA graphs are meant "
+                                       "for fixed-size crops — call enable_cuda_graphs(False) for variable-size input")
+                g = GraphedCallable(fn, [x], backward=need_grad, on_backward=self._graph_on_backward)
+                self._graphs[key] = g
+            flat = tuple(g(x))
+        n = len(flat) // (1 + int(want_emb) + int(site != "unl"))
+        out = {"features": flat[:n], "emb": None, "rpn": None}
+        rest = flat[n:]
+        if want_emb:
+            out["emb"], rest = rest[:n], rest[n:]
+        if site != "unl":
+            out["rpn"] = rest[:n]
+        return out
 
     def set_module_mode(self, mode):
         self.rpn.set_teacher_mode(mode)
@@ -79,12 +132,15 @@ class GeneralizedRCNN(nn.Module):
         self.mask_heads.mask.set_teacher_mode(mode)
 
     # ------------------------------------------------------------------------------ supervised
-    def forward(self, images, targets=None, tta=None, _features=None):
+    def forward(self, images, targets=None, tta=None, _features=None, _rpn_head=None):
         if self.training and targets is None:
             raise ValueError("In training mode, targets should be passed")
         images = to_image_list(images)
-        features = self.backbone(images.tensors) if _features is None else _features
-        proposals, proposal_losses = self.rpn(images, features, targets)
+        if _features is None:
+            t = self._trunk("sup", images.tensors)
+            _features, _rpn_head = t["features"], t["rpn"]
+        features = _features
+        proposals, proposal_losses = self.rpn(images, features, targets, head_out=_rpn_head)
         x, result, losses, class_logits, box_regression = self.box_heads(features, proposals, targets)
         result, detector_losses = self.mask_heads(losses, features, result, targets, images)
         if self.training:
@@ -111,11 +167,13 @@ class GeneralizedRCNN(nn.Module):
                     img.hflip()
                 tensors.append(img.tensors)
         n = len(tensors)
-        if n == 1:
-            return [self.backbone(tensors[0])]
+        site = "aug" if teacher else "unl"
         B = tensors[0].shape[0]
-        feats = self.backbone(torch.cat(tensors, 0))
-        return [tuple(f[i * B:(i + 1) * B] for f in feats) for i in range(n)]
+        t = self._trunk(site, tensors[0] if n == 1 else torch.cat(tensors, 0), n_views=n)
+        split = lambda maps: [tuple(f[i * B:(i + 1) * B] for f in maps) for i in range(n)]
+        self._last_emb = split(t["emb"]) if t["emb"] is not None else None   # adaptor outputs computed with the trunk
+        self._last_rpn = t["rpn"]
+        return split(t["features"])
 
     def get_emb_feature(self, feature_list):
         return [self.hint_adaptor(f) for f in feature_list]
@@ -128,17 +186,18 @@ class GeneralizedRCNN(nn.Module):
         aug_features = self.extract_aug_feat(images)
         # coarse inference on view 0 (eval-mode heads) re-using its backbone features
         self.set_module_mode("test")
-        teacher_infer = self.forward(view0, _features=aug_features[0])
+        rpn_head = self._last_rpn   # RPN head maps of view 0: used by the coarse inference AND the proposal pass below
+        teacher_infer = self.forward(view0, _features=aug_features[0], _rpn_head=rpn_head)
         integral = None
         if self.mt_fg_hint > 0:
             h, w = view0.tensors.shape[-2:]
             integral = self.mask_heads.mask.mask_generator.masker.integral_mask(teacher_infer, h, w)
         self.set_module_mode("train")
         rpn_feat = aug_features[0]
-        _, _, _, _, proposals, _, ffi_boxes = self.rpn.forward_teacher(view0, rpn_feat, teacher_infer)
+        _, _, _, _, proposals, _, ffi_boxes = self.rpn.forward_teacher(view0, rpn_feat, teacher_infer, head_out=rpn_head)
         embeddings = None
         if self.cfg.MT.FG_HINT or self.cfg.MT.HINT or self.cfg.MT.ODKD:
-            embeddings = self.get_emb_feature(aug_features)
+            embeddings = [list(e) for e in self._last_emb]
         result = class_logits = None
         if self.cfg.MT.CLS_LOSS or self.cfg.MT.ODKD:
             _, result, _, class_logits, _ = self.box_heads.forward_teacher(aug_features, proposals, teacher_infer)
@@ -161,7 +220,7 @@ class GeneralizedRCNN(nn.Module):
     def get_fg_feature_loss(self, feature_list, seg_mask, teacher_feat):
         if len(feature_list) != 1:
             raise NotImplementedError("MGD is built for MT.AUG_S = 1 (one student view), as scripts/train_mt.sh sets")
-        student = self.hint_adaptor(feature_list[0])
+        student = list(self._last_emb[0]) if self._last_emb is not None else self.hint_adaptor(feature_list[0])
         return fg_hint_loss(teacher_feat, [student], seg_mask)
 
 

@@ -38,21 +38,23 @@ class RPNHead(nn.Module):
             nn.init.normal_(l.weight, std=0.01)
             nn.init.constant_(l.bias, 0)
 
-    def forward(self, x):
-        """x: list of NHWC maps.  Returns (objectness [B,h,w,A], bbox_reg [B,h,w,4A]) per level."""
+    def forward_fused(self, x):
+        """x: list of NHWC maps -> per level ONE tensor [B,h,w,32]: channels [0,A) objectness, [A,5A) box deltas."""
         A = self.num_anchors
         pad = _HEAD_PAD - 5 * A
         w = torch.cat([self.cls_logits.weight, self.bbox_pred.weight,
                        self.conv.weight.new_zeros((pad, 1, 1, self.conv.in_channels))], 0)
         b = torch.cat([self.cls_logits.bias, self.bbox_pred.bias, self.conv.bias.new_zeros(pad)], 0)
-        logits, bbox_reg = [], []
         from .. import functional as Fk
-        for feat in x:
-            t = self.conv(feat, relu=True)
-            o = Fk.conv_bn_act(t, w, None, b, None, False, 1, 0)
-            logits.append(o[..., :A])
-            bbox_reg.append(o[..., A:5 * A])
-        return logits, bbox_reg
+        return [Fk.conv_bn_act(self.conv(feat, relu=True), w, None, b, None, False, 1, 0) for feat in x]
+
+    def split(self, fused):
+        A = self.num_anchors
+        return [o[..., :A] for o in fused], [o[..., A:5 * A] for o in fused]
+
+    def forward(self, x):
+        """x: list of NHWC maps.  Returns (objectness [B,h,w,A], bbox_reg [B,h,w,4A]) per level."""
+        return self.split(self.forward_fused(x))
 
 
 class RPNPostProcessor(nn.Module):
@@ -74,71 +76,88 @@ class RPNPostProcessor(nn.Module):
             out.append(cat_boxlist((p, gt)))
         return out
 
-    def _level_candidates(self, anchors, objectness, box_regression):
-        """Top-k + decode + clip for one level.  objectness [N,h,w,A], box_regression [N,h,w,4A] (NHWC).
-        Returns proposals [N,k,4], scores [N,k] (score-sorted), image sizes."""
-        N = objectness.shape[0]
-        device = objectness.device
-        obj = objectness.reshape(N, -1).sigmoid()
-        reg = box_regression.reshape(N, -1, 4)
-        k = min(self.pre_nms_top_n, obj.shape[1])
-        obj, topk_idx = obj.topk(k, dim=1, sorted=True)
-        batch_idx = torch.arange(N, device=device)[:, None]
-        reg = reg[batch_idx, topk_idx]
-        image_shapes = [a.size for a in anchors]
-        all_anchors = torch.cat([a.bbox for a in anchors], dim=0).reshape(N, -1, 4)[batch_idx, topk_idx]
-        props = self.box_coder.decode(reg.reshape(-1, 4), all_anchors.reshape(-1, 4)).view(N, -1, 4)
-        for j, (w, h) in enumerate(image_shapes):  # BoxList.clip_to_image(remove_empty=False)
-            props[j, :, 0].clamp_(min=0, max=w - 1)
-            props[j, :, 1].clamp_(min=0, max=h - 1)
-            props[j, :, 2].clamp_(min=0, max=w - 1)
-            props[j, :, 3].clamp_(min=0, max=h - 1)
-        return props, obj, image_shapes
+    def _segments(self, N, sizes, image_shapes, device):
+        """Static description of the (image, level) NMS problems of a pass, cached per shape: host offsets plus, per
+        candidate row, its segment id / segment start / position inside the segment (device int64)."""
+        key = (N, sizes, image_shapes, str(device))
+        cache = self.__dict__.setdefault("_seg_cache", {})
+        if key not in cache:
+            if len(cache) > 16:
+                cache.clear()
+            offs, seg_id, seg_start = [0], [], []
+            for j in range(N):
+                for k in sizes:
+                    seg_id += [len(offs) - 1] * k
+                    seg_start += [offs[-1]] * k
+                    offs.append(offs[-1] + k)
+            seg_id = torch.tensor(seg_id, dtype=torch.int64, device=device)
+            seg_start = torch.tensor(seg_start, dtype=torch.int64, device=device)
+            pos = torch.arange(offs[-1], dtype=torch.int64, device=device) - seg_start
+            wh = torch.tensor([[float(w), float(h)] for (w, h) in image_shapes], dtype=torch.float32, device=device)
+            cache[key] = (offs, seg_id, seg_start, pos, wh)
+        return cache[key]
 
     @torch.no_grad()
     def forward(self, anchors, objectness, box_regression, targets=None):
+        """Reference rpn/inference.py:78-137 (per level and image: sigmoid, top-k, decode, clip, small-box filter, NMS,
+        keep post_nms_top_n) + :216-244 (selection over levels), restructured so that every (image, level) problem of
+        the pass goes through the SAME few launches: per-level top-k, one fused decode/clip/filter kernel, one segmented
+        NMS, one compaction.  Two host read-backs per pass (sizes of the kept set), none per level or image."""
         num_levels = len(objectness)
         N = objectness[0].shape[0]
-        per_level_anchors = list(zip(*anchors))
-        boxes, scores, sizes = [], [], []
-        for a, o, b in zip(per_level_anchors, objectness, box_regression):
-            p, s, image_shapes = self._level_candidates(a, o, b)
-            boxes.append(p)
-            scores.append(s)
-            sizes.append(p.shape[1])
-        # segments in (level, image) order, all NMS problems of this pass in one launch chain
-        flat_boxes = torch.cat([p.reshape(-1, 4) for p in boxes], 0)
-        flat_scores = torch.cat([s.reshape(-1) for s in scores], 0)
-        valid = None
-        if self.min_size > 0:  # remove_small_boxes: filtered boxes are pushed behind every valid one
-            wh = flat_boxes[:, 2:] - flat_boxes[:, :2] + 1
-            valid = (wh[:, 0] >= self.min_size) & (wh[:, 1] >= self.min_size)
-            flat_scores_nms = torch.where(valid, flat_scores, flat_scores.new_full((), -1.0))
-        else:
-            flat_scores_nms = flat_scores
-        offs = [0]
-        for k in sizes:
-            for _ in range(N):
-                offs.append(offs[-1] + k)
-        keep, counts = K.nms_segmented(flat_boxes, flat_scores_nms, offs, self.nms_thresh)
-        counts_host = counts.cpu().tolist()  # the only host read-back of the pass
-        per_image = [[] for _ in range(N)]
-        seg = 0
-        for l in range(num_levels):
-            for j in range(N):
-                n_keep = counts_host[seg]
-                idx = keep[offs[seg]: offs[seg] + n_keep] + offs[seg]
-                if valid is not None:
-                    idx = idx[valid[idx]]
-                if self.post_nms_top_n > 0:
-                    idx = idx[: self.post_nms_top_n]
-                bl = BoxList(flat_boxes[idx], image_shapes[j], mode="xyxy")
-                bl.add_field("objectness", flat_scores[idx])
-                per_image[j].append(bl)
-                seg += 1
-        boxlists = [cat_boxlist(b) for b in per_image]
-        if num_levels > 1:
-            boxlists = self.select_over_all_levels(boxlists)
+        device = objectness[0].device
+        image_shapes = tuple(tuple(a[0].size) for a in anchors)
+        sc, dl, an, sizes = [], [], [], []
+        for l, (o, b) in enumerate(zip(objectness, box_regression)):
+            obj = o.reshape(N, -1).sigmoid()
+            k = min(self.pre_nms_top_n, obj.shape[1])
+            s, idx = obj.topk(k, dim=1, sorted=True)
+            sc.append(s)
+            dl.append(b.reshape(N, -1, 4).gather(1, idx[..., None].expand(-1, -1, 4)))
+            an.append(anchors[0][l].bbox[idx])  # one anchor grid for the whole (padded) batch
+            sizes.append(k)
+        K_ = sum(sizes)
+        T = N * K_
+        offs, seg_id, seg_start, pos, image_wh = self._segments(N, tuple(sizes), image_shapes, device)
+        flat_scores = torch.cat(sc, 1).reshape(-1)            # image-major: row = j * K_ + (level offset + rank)
+        boxes, scores_nms, valid = K.decode_clip_boxes(
+            torch.cat(dl, 1).reshape(-1, 4), torch.cat(an, 1).reshape(-1, 4), self.box_coder.weights,
+            self.box_coder.bbox_xform_clip, image_wh, K_, flat_scores, self.min_size)
+        # filtered (too small) boxes carry score -1: they sort behind, and so can never suppress, a valid box
+        keep, counts = K.nms_segmented(boxes, scores_nms, offs, self.nms_thresh)
+        # kept flags per candidate row, on the device: entry p of segment s is live iff p < counts[s]
+        live = pos < counts.to(torch.int64)[seg_id]
+        flags = torch.zeros(T + 1, dtype=torch.bool, device=device)
+        flags.index_fill_(0, torch.where(live, keep + seg_start, torch.full_like(keep, T)), True)
+        flags = flags[:T]
+        if valid is not None:
+            flags &= valid
+        if self.post_nms_top_n > 0 and max(sizes) > self.post_nms_top_n:   # keep[:post_nms_top_n] per (image, level)
+            f2, a = flags.view(N, K_), 0
+            for k in sizes:
+                if k > self.post_nms_top_n:
+                    f2[:, a:a + k] &= f2[:, a:a + k].cumsum(1) <= self.post_nms_top_n
+                a += k
+        # ascending row index = image-major, level-major, descending score inside a level: the reference's cat order
+        kept = flags.nonzero().squeeze(1)
+        if num_levels > 1 and self.training:
+            # batch-wide top-k over the concatenated kept boxes (reference :222-234), original order preserved
+            k = min(self.fpn_post_nms_top_n, kept.numel())
+            _, inds = torch.topk(flat_scores[kept], k, dim=0, sorted=True)
+            kept = kept[inds.sort()[0]]
+        per_image = torch.bincount(torch.div(kept, K_, rounding_mode="floor"), minlength=N).tolist()
+        boxlists, a = [], 0
+        for j in range(N):
+            idx = kept[a:a + per_image[j]]
+            a += per_image[j]
+            if num_levels > 1 and not self.training:   # per-image top-k, score order (reference :236-243)
+                obj = flat_scores[idx]
+                k = min(self.fpn_post_nms_top_n, per_image[j])
+                _, inds = torch.topk(obj, k, dim=0, sorted=True)
+                idx = idx[inds]
+            bl = BoxList(boxes[idx], image_shapes[j], mode="xyxy")
+            bl.add_field("objectness", flat_scores[idx])
+            boxlists.append(bl)
         if self.training and targets is not None:
             boxlists = self.add_gt_proposals(boxlists, targets)
         return boxlists
@@ -253,22 +272,23 @@ class RPNModule(nn.Module):
     def set_teacher_mode(self, mode):
         self.mode = mode
 
-    def _head_and_anchors(self, images, features):
+    def _head_and_anchors(self, images, features, head_out=None):
         if isinstance(features, list):
             raise NotImplementedError("multi-view RPN averaging is dead code on this path (SURVEY §2.3): the RPN is "
                                       "always handed ONE feature tuple")
-        objectness, reg = self.head(features)
+        # `head_out`: the fused head maps already computed with the trunk (same launches, inside its CUDA graph)
+        objectness, reg = self.head(features) if head_out is None else self.head.split(head_out)
         anchors = self.anchor_generator(images, [f.shape[1:3] for f in features])
         return objectness, reg, anchors
 
-    def forward(self, images, features, targets=None):
-        objectness, reg, anchors = self._head_and_anchors(images, features)
+    def forward(self, images, features, targets=None, head_out=None):
+        objectness, reg, anchors = self._head_and_anchors(images, features, head_out)
         if self.training or self.mode == "train":
             return self._forward_train(anchors, objectness, reg, targets)
         return self._forward_test(anchors, objectness, reg)
 
-    def forward_teacher(self, images, features, targets=None):
-        objectness, reg, anchors = self._head_and_anchors(images, features)
+    def forward_teacher(self, images, features, targets=None, head_out=None):
+        objectness, reg, anchors = self._head_and_anchors(images, features, head_out)
         with torch.no_grad():
             if self.cfg.MT.FFI:
                 raise NotImplementedError("MT.FFI (comparison method) is out of scope")

@@ -29,6 +29,7 @@ class FusedSGDEMA(object):
         self.flat_g = torch.zeros(total, dtype=torch.float32, device=device)
         self.flat_m = torch.zeros(total, dtype=torch.float32, device=device)
         self.touched = [False] * len(params)
+        self._index = {id(p): i for i, (_, p) in enumerate(params)}
         for i, ((name, p), e) in enumerate(zip(params, self.entries)):
             view = self.flat_p[e["begin"]:e["end"]].view_as(p)
             view.copy_(p.data)
@@ -55,6 +56,13 @@ class FusedSGDEMA(object):
         def hook(_):
             self.touched[i] = True
         return hook
+
+    def mark_touched(self, params):
+        """Parameters whose gradient was accumulated by a replayed CUDA graph (no autograd hook fires on replay)."""
+        for p in params:
+            i = self._index.get(id(p))
+            if i is not None:
+                self.touched[i] = True
 
     def set_lr(self, lr):
         self.lr = lr

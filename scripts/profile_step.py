@@ -30,7 +30,7 @@ teacher.load_state_dict(student.state_dict())
 opt = make_optimizer(cfg, student, teacher)
 sched = make_lr_scheduler(cfg, opt)
 sched.last_epoch = 2000
-tr = MTtrainer(student, teacher, None, opt, sched, None, None, 10 ** 9, cfg)
+tr = MTtrainer(student, teacher, None, opt, sched, None, None, 10 ** 9, cfg, cuda_graphs=os.environ.get("MMT_GRAPHS", "1") == "1")
 student.train(); teacher.eval()
 pool = []
 for j in range(2):

@@ -277,6 +277,36 @@ def test_elementwise_vs_torch(cuda):
     assert torch.equal(K().nhwc_to_nchw(K().nchw_to_nhwc(a)), a)
 
 
+# ------------------------------------------------------------------------- proposal decoding
+def test_decode_clip_boxes_golden_and_oracle(cuda):
+    kn = K()
+    g = golden("glue")
+    for name, w in (("rpn", (1., 1., 1., 1.)), ("box", (10., 10., 5., 5.))):
+        codes = torch.from_numpy(g["coder_%s_enc" % name]) * 1.3 + 0.01
+        boxes, s_nms, valid = kn.decode_clip_boxes(codes.to(cuda), torch.from_numpy(g["coder_prop"]).to(cuda), w,
+                                                   R.math.log(1000. / 16))
+        # expf on the device vs the reference's CPU exp: last-ulp differences only
+        np.testing.assert_allclose(boxes.cpu().numpy(), g["coder_%s_dec" % name], rtol=2e-6, atol=2e-5)
+        assert s_nms is None and valid is None
+    gen = torch.Generator().manual_seed(41)
+    N, per = 3, 700
+    anchors = torch.rand(N * per, 4, generator=gen) * 300
+    anchors[:, 2:] = anchors[:, :2] + torch.rand(N * per, 2, generator=gen) * 120
+    deltas = torch.randn(N * per, 4, generator=gen) * torch.tensor([0.5, 0.5, 1.5, 1.5])
+    deltas[::50, 2:] = 9.0                                     # exercises the dw / dh clamp
+    scores = torch.rand(N * per, generator=gen)
+    wh = torch.tensor([[320., 256.], [300., 300.], [200., 333.]])
+    ref, ref_valid = R.decode_clip_ref(deltas, anchors, (1., 1., 1., 1.), wh, per, min_size=6.0)
+    boxes, s_nms, valid = kn.decode_clip_boxes(deltas.to(cuda), anchors.to(cuda), (1., 1., 1., 1.), R.math.log(1000. / 16),
+                                               wh.to(cuda), per, scores.to(cuda), 6.0)
+    np.testing.assert_allclose(boxes.cpu().numpy(), ref, rtol=2e-6, atol=1e-3)
+    v = valid.cpu().numpy()
+    near = np.abs((ref[:, 2:] - ref[:, :2] + 1) - 6.0).min(1) < 1e-2      # predicate may flip only at the threshold
+    assert np.array_equal(v[~near], ref_valid[~near])
+    assert np.array_equal(s_nms.cpu().numpy(), np.where(v, scores.numpy(), np.float32(-1)))
+    assert 0 < ref_valid.sum() < ref_valid.size
+
+
 # ------------------------------------------------------------------------------------ convs
 CONV_CASES = [
     # B, H, W, Cin, Cout, k, stride, pad

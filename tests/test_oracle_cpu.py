@@ -106,6 +106,19 @@ def test_level_mapper_oracle():
     assert np.array_equal(R.level_mapper_ref(g["lvl_boxes"]), g["lvl"])
 
 
+def test_decode_oracle_matches_reference_box_coder():
+    """oracle decode == the reference's BoxCoder.decode on the golden pairs (both weight sets), bit for bit."""
+    g = golden("glue")
+    for name, w in (("rpn", (1., 1., 1., 1.)), ("box", (10., 10., 5., 5.))):
+        codes = torch.from_numpy(g["coder_%s_enc" % name]) * 1.3 + 0.01
+        out, valid = R.decode_clip_ref(codes, g["coder_prop"], w)
+        assert np.array_equal(out, g["coder_%s_dec" % name]) and valid.all()
+    # clip + size predicate: a box pushed outside a 100 x 80 image collapses onto the border and is filtered
+    out, valid = R.decode_clip_ref(np.zeros((2, 4), np.float32), np.array([[10, 10, 49, 29], [150, 90, 190, 130]], np.float32),
+                                   (1., 1., 1., 1.), image_wh=[[100, 80]], min_size=2)
+    assert np.array_equal(out, np.array([[10, 10, 49, 29], [99, 79, 99, 79]], np.float32)) and valid.tolist() == [True, False]
+
+
 def test_focal_oracle_vs_torchvision():
     import torchvision.ops as tvo
     gen = torch.Generator().manual_seed(3)

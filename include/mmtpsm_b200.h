@@ -288,6 +288,9 @@ typedef struct {
 
 #define MMT_EPI_RELU 1
 
+/* Persistent-grid size of the tcgen05 conv kernels launched (or captured into a CUDA graph) from now on: n CTAs,
+ * one per SM, leaving 148 - n SMs free for kernels of other streams.  Default 148. */
+int mmt_conv_set_max_ctas(int n);
 size_t mmt_conv_workspace_bytes(const mmt_conv_shape* shape);
 int mmt_conv_fprop_f32(const float* x_nhwc, const float* w_ohwi, const float* scale /*nullable*/,
                        const float* bias /*nullable*/, const float* residual_nhwc /*nullable*/,

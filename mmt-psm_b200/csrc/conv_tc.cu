@@ -24,6 +24,7 @@
 //   MN-major (pixels are the GEMM K axis), split-K over pixel ranges, partial tiles are summed
 //   into dw by TMA reduce-add (cp.reduce.async.bulk.tensor ... .add) — no atomics in SM code.
 #include <cuda.h>
+#include <atomic>
 #include <mutex>
 
 #include "common.cuh"
@@ -532,6 +533,14 @@ __global__ void __launch_bounds__(256) filter_dgrad_kernel(const float* __restri
 }
 
 // ------------------------------------------------------------------------------- host side
+// Persistent-grid size.  One CTA per SM by default; mmt_conv_set_max_ctas(n) leaves 148 - n SMs to whatever runs on
+// other streams (the trainer replays the conv trunks on a side stream while the latency-bound proposal / sampling
+// glue runs on the main one: without free SMs every tiny glue kernel waits for a whole persistent conv to drain).
+std::atomic<int> g_max_ctas{mmt::kNumSMs};
+inline int persistent_grid(long long work_items) {
+  return (int)std::min<long long>(work_items, g_max_ctas.load(std::memory_order_relaxed));
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
@@ -655,7 +664,7 @@ int launch_gemm(const GemmProblem& g, cudaStream_t stream) {
     MMT_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
     attr_set = true;
   }
-  const int grid = (int)std::min<long long>(total, mmt::kNumSMs);
+  const int grid = persistent_grid(total);
   mmt::ProfScope prof(g.prof_family, gemm_flops(g), gemm_bytes(g), stream);
   conv_tc_kernel<BN><<<grid, kThreads, C::kSmemBytes, stream>>>(tmA, tmB, tmY, p);
   return mmt::check_launch("conv_tc_kernel");
@@ -685,12 +694,18 @@ int launch_wgrad(const CUtensorMap& tmDY, const CUtensorMap& tmX, const CUtensor
     MMT_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
     attr_set = true;
   }
-  const int grid = std::min(p.total_items, mmt::kNumSMs);
+  const int grid = persistent_grid(p.total_items);
   wgrad_tc_kernel<BN><<<grid, kThreads, C::kSmemBytes, stream>>>(tmDY, tmX, tmDW, p);
   return mmt::check_launch("wgrad_tc_kernel");
 }
 
 }  // namespace
+
+extern "C" int mmt_conv_set_max_ctas(int n) {
+  if (n < 1 || n > mmt::kNumSMs) return mmt::fail(MMT_ERR_INVALID_ARGUMENT, "conv_set_max_ctas: %d not in [1, %d]", n, mmt::kNumSMs);
+  g_max_ctas.store(n);
+  return MMT_OK;
+}
 
 namespace mmt {
 

@@ -130,8 +130,20 @@ class MTtrainer(object):
 
     # ---- one iteration ------------------------------------------------------------------------
     def train_step(self, iteration, data_s, target_s, data_u_list=None):
+        mt_on = iteration > self.start_mt and self.lambda_value > 0 and bool(self.cfg.DATASETS.NO_LABEL)
+        if self.cuda_graphs:
+            # the three conv trunks of the iteration are independent: enqueue them all on the side stream first, so the
+            # host-side glue of each pass overlaps the conv work of the next (detector.prefetch_trunk)
+            data_s = data_s.to(self.device)
+            self.student.prefetch_trunk("sup", data_s.tensors if hasattr(data_s, "tensors") else data_s)
+            if mt_on and data_u_list is not None and self.n_step_unlabel == 1:
+                data_u_list = [d.to(self.device) for d in data_u_list]
+                if all(isinstance(d, torch.Tensor) for d in data_u_list):
+                    with torch.no_grad():
+                        self.teacher.prefetch_trunk("aug", data_u_list[:self.teacher_bs])
+                    self.student.prefetch_trunk("unl", data_u_list[-self.student_bs:])
         loss_dict = self.forward_source(data_s, target_s)
-        if iteration > self.start_mt and self.lambda_value > 0 and self.cfg.DATASETS.NO_LABEL:
+        if mt_on:
             loss_dict.update(self.forward_unlabel(data_u_list))
         self.scheduler.step()
         losses_dict = self.weight_sum_loss(loss_dict, iteration)

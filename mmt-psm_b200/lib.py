@@ -69,6 +69,7 @@ _PROTOS = {
     "mmt_paste_masks_sum_f32": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_float, P, P]),
     "mmt_ema_f32": (c_int, [P, P, c_int64, c_float, P]),
     "mmt_sgd_ema_f32": (c_int, [P, P, P, P, c_int64, P, c_int, c_float, c_float, c_int, c_float, P]),
+    "mmt_conv_set_max_ctas": (c_int, [c_int]),
     "mmt_conv_workspace_bytes": (c_size_t, [POINTER(ConvShape)]),
     "mmt_conv_fprop_f32": (c_int, [P, P, P, P, P, P, POINTER(ConvShape), c_int, c_int, P]),
     "mmt_conv_dgrad_f32": (c_int, [P, P, P, POINTER(ConvShape), c_int, P, c_size_t, P]),

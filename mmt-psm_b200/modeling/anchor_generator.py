@@ -91,7 +91,12 @@ class AnchorGenerator(nn.Module):
         boxlist.add_field("visibility", inside)
 
     def forward(self, image_list, grid_sizes):
-        """grid_sizes: list of (h, w) of the feature maps (layout independent)."""
+        """grid_sizes: list of (h, w) of the feature maps (layout independent).  The BoxLists (with their `visibility`
+        field) only depend on the grid and image sizes: cached, fixed-size crops re-use them every iteration."""
+        key = (tuple(tuple(g) for g in grid_sizes), tuple(tuple(s) for s in image_list.image_sizes),
+               str(next(iter(self.cell_anchors)).device))
+        if getattr(self, "_fwd_cache", None) is not None and self._fwd_cache[0] == key:
+            return [list(per_image) for per_image in self._fwd_cache[1]]
         per_level = self.grid_anchors(grid_sizes)
         anchors = []
         for (ih, iw) in image_list.image_sizes:
@@ -101,7 +106,8 @@ class AnchorGenerator(nn.Module):
                 self.add_visibility_to(bl)
                 in_image.append(bl)
             anchors.append(in_image)
-        return anchors
+        self._fwd_cache = (key, anchors)
+        return [list(per_image) for per_image in anchors]
 
 
 def make_anchor_generator(config):

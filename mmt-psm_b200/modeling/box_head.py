@@ -225,9 +225,13 @@ class FastRCNNLossComputation(object):
         labels = cat([p.get_field("labels") for p in proposals], dim=0)
         regression_targets = cat([p.get_field("regression_targets") for p in proposals], dim=0)
         classification_loss = F.cross_entropy(class_logits, labels)
-        pos = torch.nonzero(labels > 0).squeeze(1)
-        map_inds = 4 * labels[pos][:, None] + torch.tensor([0, 1, 2, 3], device=class_logits.device)
-        box_loss = smooth_l1_loss(box_regression[pos[:, None], map_inds], regression_targets[pos], size_average=False, beta=1)
+        # class-specific deltas of every ROI, reduced under the foreground mask (reference box_head/loss.py:146-160
+        # gathers the foreground rows with nonzero(): same terms, no host sync)
+        fg = labels > 0
+        map_inds = 4 * labels.clamp(min=0)[:, None] + torch.arange(4, device=class_logits.device)
+        n = torch.abs(box_regression.gather(1, map_inds) - regression_targets)
+        l1 = torch.where(n < 1, 0.5 * n ** 2, n - 0.5)
+        box_loss = torch.where(fg[:, None], l1, l1.new_zeros(())).sum()
         return classification_loss, box_loss / labels.numel()
 
     def evaluatePSM(self, class_logits, class_logits_t, proposals):

@@ -73,6 +73,7 @@ class GeneralizedRCNN(nn.Module):
         self.mt_cls = cfg.MT.CLS_LOSS
         self.hint_adaptor = MaskRCNNFPNAdaptor(cfg)
         self._graphs, self._graphs_on, self._graph_on_backward = {}, False, None
+        self._pending, self._side = {}, None
 
     # ------------------------------------------------------------------------------ CUDA graphs
     def enable_cuda_graphs(self, on=True, on_backward=None):
@@ -80,6 +81,7 @@ class GeneralizedRCNN(nn.Module):
         and input shape (utils/cuda_graphs.py).  `on_backward(params)` tells the optimizer which parameters the
         replayed backward accumulated into (their post-accumulate hooks only fire at capture time)."""
         self._graphs_on, self._graph_on_backward = bool(on), on_backward
+        self._pending = {}
         if not on:
             self._graphs = {}
 
@@ -100,23 +102,73 @@ class GeneralizedRCNN(nn.Module):
             return out
         return fn, want_emb
 
-    def _trunk(self, site, x, n_views=1):
-        """Runs (or replays from a CUDA graph) the trunk of call site `site`; returns dict(features, emb, rpn)."""
-        fn, want_emb = self._trunk_fn(site, n_views)
-        if not (self._graphs_on and x.is_cuda):
-            flat = fn(x)
+    def _graph_for(self, site, x, n_views):
+        """The captured trunk for (call site, input shape, grad mode); captured on first use.  Returns (graph, fresh)."""
+        from ..utils.cuda_graphs import GraphedCallable
+        fn, _ = self._trunk_fn(site, n_views)
+        need_grad = torch.is_grad_enabled() and self.training
+        key = (site, tuple(x.shape), n_views, need_grad)
+        g = self._graphs.get(key)
+        if g is not None:
+            return g, False
+        if len(self._graphs) >= 8:
+            raise RuntimeError("more than 8 distinct (call site, input shape) trunks captured; CUDA graphs are meant "
+                               "for fixed-size crops — call enable_cuda_graphs(False) for variable-size input")
+        g = GraphedCallable(fn, [x], backward=need_grad, on_backward=self._graph_on_backward)
+        self._graphs[key] = g
+        return g, True
+
+    @staticmethod
+    def _aug_batch(tensors, teacher):
+        """Stacked trunk input of extract_aug_feat: teacher = every view followed by its h-flip; student = odd views flipped."""
+        out = []
+        for i, t in enumerate(tensors):
+            if teacher:
+                out += [t, torch.flip(t, (3,))]
+            else:
+                out.append(torch.flip(t, (3,)) if i % 2 == 1 else t)
+        return (out[0] if len(out) == 1 else torch.cat(out, 0)), len(out)
+
+    def prefetch_trunk(self, site, tensors):
+        """Enqueue the trunk of `site` ('sup': the labeled batch; 'aug' / 'unl': list of colour views) on the side
+        stream NOW; the matching call inside forward / forward_teacher / forward_student then only waits for its
+        completion event.  The three trunks of an iteration are independent, so the host-side glue of one pass (RPN
+        selection, samplers, target assignment: dozens of tiny launches and a few read-backs) overlaps the conv work
+        of the next instead of serialising with it.  No-op without CUDA graphs."""
+        if not self._graphs_on:
+            return
+        if site == "sup":
+            x, n_views, first = tensors, 1, tensors
         else:
-            from ..utils.cuda_graphs import GraphedCallable
-            need_grad = torch.is_grad_enabled() and self.training
-            key = (site, tuple(x.shape), n_views, need_grad)
-            g = self._graphs.get(key)
-            if g is None:
-                if len(self._graphs) >= 8:
-                    raise RuntimeError("more than 8 distinct (call site, input shape) trunks captured; CUDA graphs are meant "
-                                       "for fixed-size crops — call enable_cuda_graphs(False) for variable-size input")
-                g = GraphedCallable(fn, [x], backward=need_grad, on_backward=self._graph_on_backward)
-                self._graphs[key] = g
-            flat = tuple(g(x))
+            x, n_views = self._aug_batch(list(tensors), teacher=(site == "aug"))
+            first = tensors[0]
+        if not x.is_cuda:
+            return
+        g, fresh = self._graph_for(site, x, n_views)
+        if fresh:
+            return  # captured just now (with warm-up runs); the regular call replays it
+        cur = torch.cuda.current_stream(x.device)
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=x.device)
+        self._side.wait_stream(cur)
+        g.launch_forward([x], self._side)
+        self._pending[site] = (g, first.data_ptr(), tuple(x.shape), x)
+
+    def _trunk(self, site, x, n_views=1, first_ptr=None):
+        """Runs (or replays from a CUDA graph / picks up the prefetched replay of) the trunk of call site `site`;
+        returns dict(features, emb, rpn).  `x` may be a callable building the input (skipped when prefetched)."""
+        fn, want_emb = self._trunk_fn(site, n_views)
+        pend = self._pending.pop(site, None)
+        if pend is not None and first_ptr is not None and pend[1] == first_ptr:
+            g, _, shape, keep_alive = pend
+            flat = tuple(g(keep_alive, prefetched=True))
+        else:
+            x = x() if callable(x) else x
+            if not (self._graphs_on and x.is_cuda):
+                flat = fn(x)
+            else:
+                g, _ = self._graph_for(site, x, n_views)
+                flat = tuple(g(x))
         n = len(flat) // (1 + int(want_emb) + int(site != "unl"))
         out = {"features": flat[:n], "emb": None, "rpn": None}
         rest = flat[n:]
@@ -137,7 +189,7 @@ class GeneralizedRCNN(nn.Module):
             raise ValueError("In training mode, targets should be passed")
         images = to_image_list(images)
         if _features is None:
-            t = self._trunk("sup", images.tensors)
+            t = self._trunk("sup", images.tensors, first_ptr=images.tensors.data_ptr())
             _features, _rpn_head = t["features"], t["rpn"]
         features = _features
         proposals, proposal_losses = self.rpn(images, features, targets, head_out=_rpn_head)
@@ -154,22 +206,14 @@ class GeneralizedRCNN(nn.Module):
     def extract_aug_feat(self, imglist, teacher=True):
         """Teacher: every view and its h-flip (the reference flips the ImageList in place and leaves it flipped,
         generalized_rcnn.py:201-208 — reproduced).  One batched backbone pass, split back per view."""
-        if teacher:
-            tensors = []
-            for img in imglist:
-                tensors.append(img.tensors)
+        first = imglist[0].tensors
+        B, n = first.shape[0], (2 * len(imglist) if teacher else len(imglist))
+        plain = [img.tensors for img in imglist]
+        for i, img in enumerate(imglist):   # the reference flips the ImageLists in place and leaves them flipped
+            if teacher or i % 2 == 1:
                 img.hflip()
-                tensors.append(img.tensors)
-        else:
-            tensors = []
-            for i, img in enumerate(imglist):
-                if i % 2 == 1:
-                    img.hflip()
-                tensors.append(img.tensors)
-        n = len(tensors)
         site = "aug" if teacher else "unl"
-        B = tensors[0].shape[0]
-        t = self._trunk(site, tensors[0] if n == 1 else torch.cat(tensors, 0), n_views=n)
+        t = self._trunk(site, lambda: self._aug_batch(plain, teacher)[0], n_views=n, first_ptr=first.data_ptr())
         split = lambda maps: [tuple(f[i * B:(i + 1) * B] for f in maps) for i in range(n)]
         self._last_emb = split(t["emb"]) if t["emb"] is not None else None   # adaptor outputs computed with the trunk
         self._last_rpn = t["rpn"]

@@ -18,14 +18,15 @@ class Matcher(object):
             which = "ground-truth" if quality.shape[0] == 0 else "proposal"
             raise ValueError("No %s boxes available for one of the images during training" % which)
         vals, matches = quality.max(dim=0)
-        all_matches = matches.clone() if self.allow_low_quality_matches else None
+        all_matches = matches
+        # same assignments as the reference's masked writes (matcher.py:56-66), as selects: no index lists, no host sync
         below = vals < self.low_threshold
         between = (vals >= self.low_threshold) & (vals < self.high_threshold)
-        matches[below] = Matcher.BELOW_LOW_THRESHOLD
-        matches[between] = Matcher.BETWEEN_THRESHOLDS
+        matches = torch.where(below, matches.new_full((), Matcher.BELOW_LOW_THRESHOLD), matches)
+        matches = torch.where(between, matches.new_full((), Matcher.BETWEEN_THRESHOLDS), matches)
         if self.allow_low_quality_matches:
+            # every prediction that attains some ground truth's best IoU gets its arg-max match back (matcher.py:68-138)
             best_per_gt, _ = quality.max(dim=1)
-            pairs = torch.nonzero(quality == best_per_gt[:, None])
-            upd = pairs[:, 1]
-            matches[upd] = all_matches[upd]
+            restore = (quality == best_per_gt[:, None]).any(dim=0)
+            matches = torch.where(restore, all_matches, matches)
         return matches

@@ -206,29 +206,41 @@ class RPNLossComputation(object):
         return matched
 
     def prepare_targets(self, anchors, targets):
+        """Reference rpn/loss.py:47-83; the masked writes are selects (no index lists -> no host sync)."""
         labels, regression_targets = [], []
         for a, t in zip(anchors, targets):
-            matched = self.match_targets_to_anchors(a, t)
-            midx = matched.get_field("matched_idxs")
+            midx = self.proposal_matcher(boxlist_iou(t, a))
+            gt = t.bbox[midx.clamp(min=0)]
             lab = (midx >= 0).to(dtype=torch.float32)
-            lab[~a.get_field("visibility").bool()] = -1
-            lab[midx == Matcher.BETWEEN_THRESHOLDS] = -1
-            labels.append(lab)
-            regression_targets.append(self.box_coder.encode(matched.bbox, a.bbox))
+            ignore = ~a.get_field("visibility").bool() | (midx == Matcher.BETWEEN_THRESHOLDS)
+            labels.append(torch.where(ignore, lab.new_full((), -1.0), lab))
+            regression_targets.append(self.box_coder.encode(gt, a.bbox))
         return labels, regression_targets
 
+    def _cat_anchors(self, anchors):
+        """cat_boxlist over the levels of every image, cached on the (cached) anchor grids."""
+        key = tuple(id(a) for per_image in anchors for a in per_image)
+        if getattr(self, "_anchor_cat", None) is None or self._anchor_cat[0] != key:
+            self._anchor_cat = (key, [cat_boxlist(a) for a in anchors], anchors)  # keeps the keyed objects alive
+        return self._anchor_cat[1]
+
     def _sample(self, anchors, targets):
-        anchors = [cat_boxlist(a) for a in anchors]
+        """labels / regression targets per anchor and the sampled positive / negative MASKS over the whole batch."""
+        anchors = self._cat_anchors(anchors)
         labels, regression_targets = self.prepare_targets(anchors, targets)
         pos, neg = self.fg_bg_sampler(labels)
-        pos = torch.nonzero(torch.cat(pos, dim=0)).squeeze(1)
-        neg = torch.nonzero(torch.cat(neg, dim=0)).squeeze(1)
-        return labels, regression_targets, pos, neg
+        return labels, regression_targets, torch.cat(pos, dim=0), torch.cat(neg, dim=0)
 
     def teacher_sample_selection(self, anchors, objectness, box_regression, targets):
-        """Reference rpn/loss.py:85-136.  Its outputs are unused downstream but it draws from the
-        sampler's random stream, so it is kept to leave the RNG sequence of an iteration unchanged."""
+        """Reference rpn/loss.py:85-136.  Its outputs are never used downstream; the only observable
+        effect is the sampler's draw from the random stream.  When the sampler draws on the host (parity mode,
+        `BalancedPositiveNegativeSampler.rng_device = "cpu"`) the draw is reproduced so the iteration consumes the
+        reference's random sequence; with the device generator there is no sequence to preserve and the dead
+        matching + sampling work is skipped."""
+        if self.fg_bg_sampler.rng_device is None:
+            return None, None, None, None
         labels, _, pos, neg = self._sample(anchors, targets)
+        pos, neg = torch.nonzero(pos).squeeze(1), torch.nonzero(neg).squeeze(1)
         sampled = torch.cat([pos, neg], dim=0)
         obj = cat([o.reshape(o.shape[0], -1) for o in objectness], dim=1).reshape(-1)
         reg = cat([b.reshape(b.shape[0], -1, 4) for b in box_regression], dim=1).reshape(-1, 4)
@@ -236,15 +248,23 @@ class RPNLossComputation(object):
         return obj[sampled], reg[pos], (sampled, pos.shape), labels[sampled]
 
     def __call__(self, anchors, objectness, box_regression, targets):
+        """Reference rpn/loss.py:138-196.  The reference gathers the sampled anchors into index lists (two
+        `nonzero`s = two host syncs) and reduces over them; here the same sums run over all anchors under the
+        sampling masks: identical terms, no data-dependent shapes."""
         labels, regression_targets, pos, neg = self._sample(anchors, targets)
-        sampled = torch.cat([pos, neg], dim=0)
+        sampled = pos | neg
+        n_sampled = sampled.sum().to(torch.float32)
         # NHWC maps flatten directly to the (h, w, anchor) order of the labels
         obj = cat([o.reshape(o.shape[0], -1) for o in objectness], dim=1).reshape(-1)
         reg = cat([b.reshape(b.shape[0], -1, 4) for b in box_regression], dim=1).reshape(-1, 4)
         labels = torch.cat(labels, dim=0)
         regression_targets = torch.cat(regression_targets, dim=0)
-        box_loss = smooth_l1_loss(reg[pos], regression_targets[pos], beta=1.0 / 9, size_average=False) / sampled.numel()
-        objectness_loss = F.binary_cross_entropy_with_logits(obj[sampled], labels[sampled])
+        beta = 1.0 / 9
+        n = torch.abs(reg - regression_targets)
+        l1 = torch.where(n < beta, 0.5 * n ** 2 / beta, n - 0.5 * beta)
+        box_loss = torch.where(pos[:, None], l1, l1.new_zeros(())).sum() / n_sampled
+        bce = F.binary_cross_entropy_with_logits(obj, labels.clamp(min=0), reduction="none")
+        objectness_loss = torch.where(sampled, bce, bce.new_zeros(())).sum() / n_sampled
         return objectness_loss, box_loss
 
 

@@ -21,6 +21,10 @@ from mmt_psm_b200.utils.synthetic_init import init_model
 iters = int(sys.argv[1]) if len(sys.argv) > 1 else 3
 prefix = sys.argv[2] if len(sys.argv) > 2 else "gpurun_out/profile_step"
 dev = torch.device("cuda:0")
+if os.environ.get("MMT_CONV_MAX_CTAS"):
+    from mmt_psm_b200 import lib as _lib
+    _lib.check(_lib.lib().mmt_conv_set_max_ctas(int(os.environ["MMT_CONV_MAX_CTAS"])))
+QUICK = os.environ.get("MMT_PROFILE_QUICK") == "1"
 cfg = mt_psm_cfg(start_mt=0)
 torch.manual_seed(0)
 student = build_detection_model(cfg, is_student=True).to(dev)
@@ -93,6 +97,8 @@ torch.cuda.synchronize()
 t2 = time.perf_counter()
 print("free-running: enqueue %.2f ms/step, wall %.2f ms/step" % ((t1 - t0) / iters * 1e3, (t2 - t0) / iters * 1e3))
 
+if QUICK:
+    sys.exit(0)
 from torch.profiler import ProfilerActivity, profile
 
 with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:

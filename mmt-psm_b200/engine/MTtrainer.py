@@ -142,14 +142,30 @@ class MTtrainer(object):
                     with torch.no_grad():
                         self.teacher.prefetch_trunk("aug", data_u_list[:self.teacher_bs])
                     self.student.prefetch_trunk("unl", data_u_list[-self.student_bs:])
-        loss_dict = self.forward_source(data_s, target_s)
-        if mt_on:
-            loss_dict.update(self.forward_unlabel(data_u_list))
         self.scheduler.step()
-        losses_dict = self.weight_sum_loss(loss_dict, iteration)
-        losses = sum(v for v in losses_dict.values())
         self.optimizer.zero_grad()
-        losses.backward()
+        loss_dict = self.forward_source(data_s, target_s)
+        # The supervised terms carry weight 1 (no 'mt' in their keys, MTtrainer.py:99 of the reference), so their
+        # backward does not depend on the consistency ramp: run it NOW — its device work overlaps the teacher pass's
+        # host-side glue — and back-propagate the consistency terms after the unlabeled pass.  Gradients of both
+        # passes accumulate in the flat arena: d(sum)/dw = sum of d/dw, the reference's single backward.
+        sup_weighted = self.weight_sum_loss(loss_dict, iteration)
+        sup_total = sum(v for v in sup_weighted.values())
+        if mt_on:
+            sup_total.backward()
+            mt_dict = self.forward_unlabel(data_u_list)
+            mt_weighted = self.weight_sum_loss(mt_dict, iteration)
+            losses_dict = dict(sup_weighted)
+            losses_dict.update(mt_weighted)
+            if mt_weighted:
+                mt_total = sum(v for v in mt_weighted.values())
+                mt_total.backward()
+                losses = sup_total.detach() + mt_total.detach()
+            else:
+                losses = sup_total.detach()
+        else:
+            losses_dict, losses = sup_weighted, sup_total
+            losses.backward()
         if self.world > 1:
             dist.all_reduce(self.optimizer.flat_g)  # one NCCL all-reduce over the whole student gradient arena
         ema = None

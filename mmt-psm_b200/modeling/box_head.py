@@ -134,46 +134,67 @@ class PostProcessor(nn.Module):
         class_prob = F.softmax(class_logits, -1)
         image_shapes = [b.size for b in boxes]
         per_image = [len(b) for b in boxes]
+        device = class_logits.device
         concat = torch.cat([b.bbox for b in boxes], dim=0)
         decoded = self.box_coder.decode(box_regression.reshape(sum(per_image), -1), concat)
         C = class_prob.shape[1]
         decoded = decoded.split(per_image, dim=0)
         class_prob = class_prob.split(per_image, dim=0)
-        seg_boxes, seg_scores, offs, meta = [], [], [0], []
-        for img, (prob, bx, (w, h)) in enumerate(zip(class_prob, decoded, image_shapes)):
-            bx = bx.reshape(-1, C, 4).clone()
+        # segments in (image, class) order, class-major inside an image: row = class block + roi
+        seg_boxes, seg_scores, offs, img_bounds = [], [], [0], [0]
+        for prob, bx, (w, h), r in zip(class_prob, decoded, image_shapes, per_image):
+            bx = bx.reshape(-1, C, 4)[:, 1:].permute(1, 0, 2).clone()          # [C-1, R, 4]
             bx[..., 0].clamp_(min=0, max=w - 1)
             bx[..., 1].clamp_(min=0, max=h - 1)
             bx[..., 2].clamp_(min=0, max=w - 1)
             bx[..., 3].clamp_(min=0, max=h - 1)
-            for j in range(1, C):
-                sc = prob[:, j]
-                seg_boxes.append(bx[:, j])
-                seg_scores.append(torch.where(sc > self.score_thresh, sc, sc.new_full((), -1.0)))
-                offs.append(offs[-1] + sc.shape[0])
-                meta.append((img, j))
+            sc = prob[:, 1:].t()                                                # [C-1, R]
+            seg_boxes.append(bx.reshape(-1, 4))
+            seg_scores.append(torch.where(sc > self.score_thresh, sc, sc.new_full((), -1.0)).reshape(-1))
+            for _ in range(C - 1):
+                offs.append(offs[-1] + r)
+            img_bounds.append(offs[-1])
         flat_b, flat_s = torch.cat(seg_boxes, 0), torch.cat(seg_scores, 0)
+        T = flat_s.shape[0]
         keep, counts = K.nms_segmented(flat_b, flat_s, offs, self.nms)
-        counts_host = counts.cpu().tolist()
-        results = [[] for _ in boxes]
-        for s, (img, j) in enumerate(meta):
-            idx = keep[offs[s]: offs[s] + counts_host[s]] + offs[s]
-            idx = idx[flat_s[idx] > 0]
-            bl = BoxList(flat_b[idx], image_shapes[img], mode="xyxy")
+        # kept flags per row on the device (entry p of segment s is live iff p < counts[s]); thresholded rows carry
+        # score -1: they sort behind — and so never suppress — a valid detection, and are dropped here
+        seg_id, seg_start, pos = self._segment_rows(tuple(offs), device)
+        live = pos < counts.to(torch.int64)[seg_id]
+        flags = torch.zeros(T + 1, dtype=torch.bool, device=device)
+        flags.index_fill_(0, torch.where(live, keep + seg_start, torch.full_like(keep, T)), True)
+        flags = flags[:T] & (flat_s > 0)
+        if self.detections_per_img > 0:   # keep the detections_per_img best of an image, ties included (kthvalue rule)
+            masked = torch.where(flags, flat_s, flat_s.new_full((), -1.0))
+            for i in range(len(boxes)):
+                a, b = img_bounds[i], img_bounds[i + 1]
+                if b - a > self.detections_per_img:
+                    thresh = torch.topk(masked[a:b], self.detections_per_img, sorted=True)[0][-1]
+                    flags[a:b] &= masked[a:b] >= thresh
+        kept = flags.nonzero().squeeze(1)
+        bounds = torch.searchsorted(kept, torch.tensor(img_bounds, dtype=torch.int64, device=device)).tolist()
+        seg_label = (seg_id % (C - 1) + 1) if C > 1 else seg_id
+        out = []
+        for i in range(len(boxes)):
+            idx = kept[bounds[i]:bounds[i + 1]]
+            bl = BoxList(flat_b[idx], image_shapes[i], mode="xyxy")
             bl.add_field("scores", flat_s[idx])
             bl.add_field("objectness", flat_s[idx])
-            bl.add_field("labels", torch.full((idx.shape[0],), j, dtype=torch.int64, device=flat_b.device))
-            results[img].append(bl)
-        out = []
-        for r in results:
-            r = cat_boxlist(r)
-            n = len(r)
-            if n > self.detections_per_img > 0:
-                sc = r.get_field("scores")
-                thresh, _ = torch.kthvalue(sc, n - self.detections_per_img + 1)
-                r = r[torch.nonzero(sc >= thresh).squeeze(1)]
-            out.append(r)
+            bl.add_field("labels", seg_label[idx])
+            out.append(bl)
         return out
+
+    def _segment_rows(self, offs, device):
+        key = (offs, str(device))
+        cache = self.__dict__.setdefault("_seg_cache", {})
+        if key not in cache:
+            if len(cache) > 16:
+                cache.clear()
+            seg_id = torch.repeat_interleave(torch.arange(len(offs) - 1), torch.tensor([offs[i + 1] - offs[i] for i in range(len(offs) - 1)]))
+            seg_start = torch.tensor(offs[:-1], dtype=torch.int64)[seg_id]
+            pos = torch.arange(offs[-1], dtype=torch.int64) - seg_start
+            cache[key] = (seg_id.to(device), seg_start.to(device), pos.to(device))
+        return cache[key]
 
 
 def make_roi_box_post_processor(cfg):
@@ -283,10 +304,22 @@ class ROIBoxHead(nn.Module):
         loss_classifier, loss_box_reg = self.loss_evaluator([class_logits], [box_regression])
         return x, proposals, dict(loss_classifier=loss_classifier, loss_box_reg=loss_box_reg), class_logits, box_regression
 
-    def _forward_single(self, proposals, targets, feats_list, istrain=False):
+    def _forward_single(self, proposals, targets, feats_list, istrain=False, batched_feats=None):
         if targets is not None:
             proposals = self.loss_evaluator.subsample(proposals, targets)
         proposals_B = [p.transpose(0) for p in proposals]  # h-flipped boxes for the flipped views
+        n_views = len(feats_list)
+        if batched_feats is not None and not istrain and n_views > 1:
+            # the views are slices of ONE stacked trunk output [n_views*B, ...]: pool / fc6 / fc7 / predict all views in
+            # one launch each (image index = view * B + b); rows of a GEMM are independent, so every view's logits
+            # are the numbers the per-view loop below produces
+            boxes = []
+            for i in range(n_views):
+                boxes += proposals if i % 2 == 0 else proposals_B
+            x = self.feature_extractor(batched_feats, boxes, istrain=False)
+            c, r = self.predictor(x)
+            per_view = x.shape[0] // n_views
+            return (list(x.split(per_view)), list(c.split(per_view)), list(r.split(per_view)), proposals)
         feats, logits, regs = [], [], []
         for i, feat in enumerate(feats_list):
             x = self.feature_extractor(feat, proposals if i % 2 == 0 else proposals_B, istrain=istrain)
@@ -296,8 +329,9 @@ class ROIBoxHead(nn.Module):
             regs.append(r)
         return feats, logits, regs, proposals
 
-    def forward_teacher(self, feature_tuple, proposals, targets):
-        feats, logits, regs, proposals = self._forward_single(proposals, targets, feature_tuple, istrain=False)
+    def forward_teacher(self, feature_tuple, proposals, targets, batched_feats=None):
+        feats, logits, regs, proposals = self._forward_single(proposals, targets, feature_tuple, istrain=False,
+                                                              batched_feats=batched_feats)
         return feats, proposals, {}, logits, regs
 
     def forward_student(self, features, proposals, class_logits_t):

@@ -32,9 +32,9 @@ class BoxROIHeads(nn.ModuleDict):
     def forward_student(self, features, proposals, class_logits_t):
         return self.box.forward_student(features, proposals, class_logits_t)
 
-    def forward_teacher(self, feature_tuple, proposals, teacher_infer):
+    def forward_teacher(self, feature_tuple, proposals, teacher_infer, batched_feats=None):
         x, detections, loss_box, class_logits, box_regression = self.box.forward_teacher(
-            feature_tuple, proposals, targets=teacher_infer)
+            feature_tuple, proposals, targets=teacher_infer, batched_feats=batched_feats)
         return x, detections, dict(loss_box), class_logits, box_regression
 
 
@@ -217,6 +217,7 @@ class GeneralizedRCNN(nn.Module):
         split = lambda maps: [tuple(f[i * B:(i + 1) * B] for f in maps) for i in range(n)]
         self._last_emb = split(t["emb"]) if t["emb"] is not None else None   # adaptor outputs computed with the trunk
         self._last_rpn = t["rpn"]
+        self._last_stacked = t["features"]   # the un-split [n_views*B, ...] maps
         return split(t["features"])
 
     def get_emb_feature(self, feature_list):
@@ -244,7 +245,8 @@ class GeneralizedRCNN(nn.Module):
             embeddings = [list(e) for e in self._last_emb]
         result = class_logits = None
         if self.cfg.MT.CLS_LOSS or self.cfg.MT.ODKD:
-            _, result, _, class_logits, _ = self.box_heads.forward_teacher(aug_features, proposals, teacher_infer)
+            _, result, _, class_logits, _ = self.box_heads.forward_teacher(aug_features, proposals, teacher_infer,
+                                                                          batched_feats=self._last_stacked)
         return {"result_t": result, "class_logit_t": class_logits, "embedding": embeddings,
                 "seg_mask": integral, "ffi_boxes": ffi_boxes}
 

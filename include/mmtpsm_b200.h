@@ -297,6 +297,14 @@ int mmt_conv_fprop_f32(const float* x_nhwc, const float* w_ohwi, const float* sc
                        float* y_nhwc, const mmt_conv_shape* shape, int epilogue_flags, int impl,
                        void* stream);
 /* dx = conv_transpose(dy, w): data gradient.  dx is fully overwritten. */
+/* ResNet stem (reference modeling/backbone/resnet.py:288-293: Conv2d(3, 64, 7, stride 2, pad 3) + FrozenBN + ReLU):
+ * the 7x7 / stride-2 convolution over 3 channels runs on the tensor cores as a 4x4 implicit GEMM over the 2x2
+ * space-to-depth image (12 channels padded to one 32-wide K block).  x NHWC [B,H,W,3], w OHWI [out_c,7,7,3];
+ * workspace (256-byte aligned) >= mmt_conv_stem_workspace_bytes() holds the space-to-depth image and filter. */
+size_t mmt_conv_stem_workspace_bytes(const mmt_conv_shape* shape);
+int mmt_conv_stem_fprop_f32(const float* x_nhwc, const float* w_ohwi, const float* scale /*nullable*/,
+                            const float* bias /*nullable*/, float* y_nhwc, const mmt_conv_shape* shape, int flags,
+                            void* workspace, size_t workspace_bytes, void* stream);
 int mmt_conv_dgrad_f32(const float* dy_nhwc, const float* w_ohwi, float* dx_nhwc,
                        const mmt_conv_shape* shape, int impl, void* workspace,
                        size_t workspace_bytes, void* stream);

@@ -41,6 +41,23 @@ extern "C" int mmt_conv_fprop_f32(const float* x, const float* w, const float* s
   return mmt::conv_fprop_tc(x, w, scale, bias, residual, y, *s, flags, stream);
 }
 
+extern "C" size_t mmt_conv_stem_workspace_bytes(const mmt_conv_shape* s) {
+  if (!s || !mmt::conv_stem_tc_supported(*s)) return 0;
+  return mmt::conv_stem_tc_workspace(*s);
+}
+
+extern "C" int mmt_conv_stem_fprop_f32(const float* x, const float* w, const float* scale, const float* bias, float* y,
+                                       const mmt_conv_shape* s, int flags, void* workspace, size_t workspace_bytes,
+                                       void* stream_) {
+  if (int rc = check_shape(s, "conv_stem_fprop")) return rc;
+  if (s->batch == 0) return MMT_OK;
+  MMT_REQUIRE(x && w && y, "conv_stem_fprop: null pointer");
+  if (!mmt::conv_stem_tc_supported(*s))
+    return mmt::fail(MMT_ERR_UNSUPPORTED, "conv_stem_fprop: only 7x7 / stride 2 / pad 3 over 3 input channels");
+  MMT_REQUIRE(((uintptr_t)workspace & 255) == 0, "conv_stem_fprop: workspace must be 256-byte aligned");
+  return mmt::conv_stem_tc(x, w, scale, bias, y, *s, flags, workspace, workspace_bytes, (cudaStream_t)stream_);
+}
+
 extern "C" int mmt_conv_dgrad_f32(const float* dy, const float* w, float* dx, const mmt_conv_shape* s, int impl,
                                   void* workspace, size_t workspace_bytes, void* stream_) {
   if (int rc = check_shape(s, "conv_dgrad")) return rc;

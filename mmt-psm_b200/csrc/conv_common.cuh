@@ -24,6 +24,11 @@ bool conv_tc_supported_wgrad(const mmt_conv_shape& s);
 int conv_fprop_tc(const float* x, const float* w, const float* scale, const float* bias,
                   const float* residual, float* y, const mmt_conv_shape& s, int flags,
                   cudaStream_t stream);
+// 7x7 / stride-2 / pad-3 stem over 3 input channels as a 4x4 implicit GEMM over the space-to-depth image
+bool conv_stem_tc_supported(const mmt_conv_shape& s);
+size_t conv_stem_tc_workspace(const mmt_conv_shape& s);
+int conv_stem_tc(const float* x, const float* w, const float* scale, const float* bias, float* y,
+                 const mmt_conv_shape& s, int flags, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 // w_t must hold the dgrad-transformed filter [in_c][k_h][k_w][out_c] (rotated 180 degrees)
 int conv_dgrad_tc(const float* dy, const float* w_t, float* dx, const mmt_conv_shape& s,
                   cudaStream_t stream);

@@ -532,6 +532,47 @@ __global__ void __launch_bounds__(256) filter_dgrad_kernel(const float* __restri
   }
 }
 
+// ---------------------------------------------------------------------- stem (7x7 / stride 2, 3 channels)
+// A 7x7 stride-2 convolution over C_in = 3 is a 4x4 stride-1 convolution over the 2x2 space-to-depth image
+// (12 channels, zero-padded to one 32-channel K block): in[2y + r - 3] with r - 3 = 2a + dy, a in {-2..1}, dy in {0,1}
+// -> s2d[y + a][dy] — which is a shape the implicit-GEMM kernel above runs as is (taps -2..+1 = "pad 2", TMA
+// zero-fills the border).  x NHWC [B,H,W,3] -> s [B,ceil(H/2),ceil(W/2),32], channel = (dy*2 + dx)*3 + c.
+__global__ void __launch_bounds__(256) stem_s2d_kernel(const float* __restrict__ x, float4* __restrict__ s, int B,
+                                                       int H, int W, int H2, int W2) {
+  const long long total = (long long)B * H2 * W2 * 8;  // float4 slots: 8 per pixel
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int q = (int)(i & 7);
+    const long long pix = i >> 3;
+    const int x2 = (int)(pix % W2), y2 = (int)((pix / W2) % H2), b = (int)(pix / ((long long)W2 * H2));
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (q < 3) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int ch = q * 4 + e;  // < 12
+        const int c = ch % 3, dx = (ch / 3) & 1, dy = ch / 6;
+        const int yy = 2 * y2 + dy, xx = 2 * x2 + dx;
+        if (yy < H && xx < W) v[e] = __ldg(x + (((long long)b * H + yy) * W + xx) * 3 + c);
+      }
+    }
+    s[i] = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+// w [out_c][7][7][3] -> w4 [out_c][4][4][32]
+__global__ void __launch_bounds__(256) stem_filter_kernel(const float* __restrict__ w, float* __restrict__ w4, int out_c) {
+  const int total = out_c * 16 * 32;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int ch = i & 31, tap = (i >> 5) & 15, o = i >> 9;
+    float v = 0.f;
+    if (ch < 12) {
+      const int c = ch % 3, dx = (ch / 3) & 1, dy = ch / 6;
+      const int r = 2 * ((tap >> 2) - 2) + dy + 3, t = 2 * ((tap & 3) - 2) + dx + 3;
+      if (r >= 0 && r < 7 && t >= 0 && t < 7) v = __ldg(w + ((o * 7 + r) * 7 + t) * 3 + c);
+    }
+    w4[i] = v;
+  }
+}
+
 // ------------------------------------------------------------------------------- host side
 // Persistent-grid size.  One CTA per SM by default; mmt_conv_set_max_ctas(n) leaves 148 - n SMs to whatever runs on
 // other streams (the trainer replays the conv trunks on a side stream while the latency-bound proposal / sampling
@@ -621,10 +662,12 @@ struct GemmProblem {
   long long r_sw, r_sh, r_sn;
   int relu;
   int prof_family;  // MMT_PROF_CONV_FPROP / MMT_PROF_CONV_DGRAD
+  double flops_override = 0.0;  // algorithmic flops when the GEMM is padded (stem)
 };
 
 // algorithmic cost of one implicit GEMM: 2*M*N*K flops; bytes = A read once + filter + output (+ residual)
 inline double gemm_flops(const GemmProblem& g) {
+  if (g.flops_override > 0.0) return g.flops_override;
   return 2.0 * (double)g.y.n * g.y.h * g.y.w * g.n_out * g.kh * g.kw * g.a.c;
 }
 inline double gemm_bytes(const GemmProblem& g) {
@@ -749,6 +792,45 @@ int conv_fprop_tc(const float* x, const float* w, const float* scale, const floa
   g.scale = scale; g.bias = bias; g.residual = residual;
   g.relu = (flags & MMT_EPI_RELU) ? 1 : 0;
   g.prof_family = MMT_PROF_CONV_FPROP;
+  return dispatch_gemm(g, stream);
+}
+
+size_t conv_stem_tc_workspace(const mmt_conv_shape& s) {
+  const size_t h2 = (s.in_h + 1) / 2, w2 = (s.in_w + 1) / 2;
+  return align_up(sizeof(float) * (size_t)s.batch * h2 * w2 * 32, 256) + align_up(sizeof(float) * (size_t)s.out_c * 512, 256);
+}
+
+bool conv_stem_tc_supported(const mmt_conv_shape& s) {
+  return s.in_c == 3 && s.k_h == 7 && s.k_w == 7 && s.stride == 2 && s.pad == 3 && s.out_c % 4 == 0 &&
+         s.out_h == (s.in_h + 1) / 2 && s.out_w == (s.in_w + 1) / 2;
+}
+
+int conv_stem_tc(const float* x, const float* w, const float* scale, const float* bias, float* y,
+                 const mmt_conv_shape& s, int flags, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  if (workspace == nullptr || workspace_bytes < conv_stem_tc_workspace(s))
+    return fail(MMT_ERR_WORKSPACE_TOO_SMALL, "conv_stem: workspace %zu < required %zu", workspace_bytes,
+                conv_stem_tc_workspace(s));
+  const int h2 = (s.in_h + 1) / 2, w2 = (s.in_w + 1) / 2;
+  float* s2d = (float*)workspace;
+  float* w4 = (float*)((char*)workspace + align_up(sizeof(float) * (size_t)s.batch * h2 * w2 * 32, 256));
+  {
+    const long long slots = (long long)s.batch * h2 * w2 * 8;
+    const int grid = (int)std::min<long long>((slots + 255) / 256, (long long)kNumSMs * 16);
+    stem_s2d_kernel<<<grid, 256, 0, stream>>>(x, reinterpret_cast<float4*>(s2d), s.batch, s.in_h, s.in_w, h2, w2);
+    if (int rc = check_launch("stem_s2d")) return rc;
+    stem_filter_kernel<<<(s.out_c * 512 + 255) / 256, 256, 0, stream>>>(w, w4, s.out_c);
+    if (int rc = check_launch("stem_filter")) return rc;
+  }
+  GemmProblem g;
+  g.a = dense_nhwc(s2d, s.batch, h2, w2, 32);
+  g.y = dense_nhwc(y, s.batch, s.out_h, s.out_w, s.out_c);
+  g.r_sw = g.r_sh = g.r_sn = 0;
+  g.b = w4; g.n_out = s.out_c;
+  g.kh = 4; g.kw = 4; g.pad_h = 2; g.pad_w = 2;
+  g.scale = scale; g.bias = bias; g.residual = nullptr;
+  g.relu = (flags & MMT_EPI_RELU) ? 1 : 0;
+  g.prof_family = MMT_PROF_CONV_FPROP;
+  g.flops_override = 2.0 * s.batch * s.out_h * s.out_w * (double)s.out_c * 147.0;  // algorithmic: the 7x7x3 taps
   return dispatch_gemm(g, stream);
 }
 

@@ -72,6 +72,8 @@ _PROTOS = {
     "mmt_conv_set_max_ctas": (c_int, [c_int]),
     "mmt_conv_workspace_bytes": (c_size_t, [POINTER(ConvShape)]),
     "mmt_conv_fprop_f32": (c_int, [P, P, P, P, P, P, POINTER(ConvShape), c_int, c_int, P]),
+    "mmt_conv_stem_workspace_bytes": (c_size_t, [POINTER(ConvShape)]),
+    "mmt_conv_stem_fprop_f32": (c_int, [P, P, P, P, P, POINTER(ConvShape), c_int, P, c_size_t, P]),
     "mmt_conv_dgrad_f32": (c_int, [P, P, P, POINTER(ConvShape), c_int, P, c_size_t, P]),
     "mmt_conv_wgrad_f32": (c_int, [P, P, P, P, POINTER(ConvShape), c_int, P, c_size_t, P]),
     "mmt_bn_relu_backward_f32": (c_int, [P, P, P, P, c_int64, c_int, c_int, P]),

@@ -56,7 +56,16 @@ class StemWithFixedBatchNorm(nn.Module):
         self.bn1 = FrozenBatchNorm2d(out_channels)
 
     def forward(self, x):
-        x = self.conv1(x, bn=self.bn1, relu=True)
+        c = self.conv1
+        if (K.get_conv_math() == "tf32" and not c.weight.requires_grad and not x.requires_grad
+                and (c.in_channels, c.kernel_size, c.stride, c.padding) == (3, 7, 2, 3)):
+            # frozen stem: forward only, on the tensor cores (space-to-depth implicit GEMM, csrc/conv_tc.cu)
+            B, H, W, _ = x.shape
+            scale, shift = self.bn1.affine()
+            shape = K.conv_shape(B, H, W, 3, c.out_channels, 7, 2, 3)
+            x = K.conv_stem_fprop(x, c.weight.detach(), shape, scale, shift, relu=True)
+        else:
+            x = self.conv1(x, bn=self.bn1, relu=True)
         if x.requires_grad:
             raise NotImplementedError("the stem is frozen on this path (FREEZE_CONV_BODY_AT >= 1): no max-pool backward")
         return K.maxpool3x3s2(x)

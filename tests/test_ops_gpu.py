@@ -405,6 +405,24 @@ def test_conv_stem_7x7_simt(cuda):
     assert _rel(y.permute(0, 3, 1, 2).cpu(), torch.relu(Fn.conv2d(x, w, None, 2, 3))) < 1e-5
 
 
+def test_conv_stem_7x7_tensor_core(cuda):
+    """The space-to-depth tensor-core stem == Conv2d(3, 64, 7, 2, 3) + frozen-BN affine + ReLU (TF32 operands), on an
+    even and an odd-sized image (the odd last row / column pairs with a zero)."""
+    import torch.nn.functional as Fn
+    kn = K()
+    gen = torch.Generator().manual_seed(31)
+    for (B, H, W) in ((2, 64, 96), (1, 67, 95)):
+        x = torch.randn(B, 3, H, W, generator=gen) * 50
+        w = torch.randn(64, 3, 7, 7, generator=gen) / (3 * 49) ** 0.5
+        sc, sh = torch.rand(64, generator=gen) * 0.02 + 0.01, torch.randn(64, generator=gen) * 0.1
+        shape = kn.conv_shape(B, H, W, 3, 64, 7, 2, 3)
+        y = kn.conv_stem_fprop(x.permute(0, 2, 3, 1).contiguous().to(cuda), w.permute(0, 2, 3, 1).contiguous().to(cuda),
+                               shape, sc.to(cuda), sh.to(cuda), relu=True).permute(0, 3, 1, 2).cpu()
+        ref = torch.relu(Fn.conv2d(x.double(), w.double(), None, 2, 3) * sc.double().view(1, -1, 1, 1) + sh.double().view(1, -1, 1, 1))
+        assert y.shape == ref.shape, (y.shape, ref.shape)
+        assert _rel(y.double(), ref) < 3e-3, _rel(y.double(), ref)
+
+
 def test_conv_full_size_tc_vs_simt(cuda):
     """BASELINE-size layer (fpn_layer1: 2x200x200x256 -> 256, 3x3): tensor-core path vs the fp32 SIMT kernel."""
     kn = K()

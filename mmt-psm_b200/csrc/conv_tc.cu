@@ -25,6 +25,7 @@
 //   into dw by TMA reduce-add (cp.reduce.async.bulk.tensor ... .add) — no atomics in SM code.
 #include <cuda.h>
 #include <atomic>
+#include <cmath>
 #include <mutex>
 
 #include "common.cuh"
@@ -35,7 +36,8 @@ namespace {
 
 using namespace tc;
 
-constexpr int kThreads = 192;
+constexpr int kThreads = 192;       // wgrad: TMA warp + MMA warp + 4 epilogue warps
+constexpr int kFpropThreads = 320;  // fprop / dgrad: TMA warp + MMA warp + 8 epilogue warps (two per TMEM lane quadrant)
 constexpr int kTileM = 128;
 constexpr int kABytes = kTileM * 128;  // 128 rows x 32 fp32
 constexpr int kStagingBytes = kTileM * 128;
@@ -124,12 +126,15 @@ __device__ __forceinline__ float4 ld_shared_v4(uint32_t addr) {
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
   return v;
 }
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
 __device__ __forceinline__ void st_shared_f32(uint32_t addr, float x) {
   asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(x) : "memory");
 }
 
 template <int BN>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kFpropThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmY, const FpropParams p) {
   using C = Cfg<BN>;
@@ -151,8 +156,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       mbar_init(L.tfull[0], 1);
       mbar_init(L.tfull[1], 1);
-      mbar_init(L.tempty[0], 4);  // one arrival per epilogue warp
-      mbar_init(L.tempty[1], 4);
+      mbar_init(L.tempty[0], 8);  // one arrival per epilogue warp
+      mbar_init(L.tempty[1], 8);
       fence_barrier_init();
     }
     __syncwarp();
@@ -217,14 +222,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     __syncwarp();
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..5)
-    // Each warp owns one TMEM lane quadrant = 32 pixels of the tile and runs on its own: private staging
-    // buffers, private TMA stores (bulk groups are per thread: lane 0), no CTA-wide barrier per chunk.
-    const int q = warp & 3;         // TMEM lane quadrant this warp may access
-    const int row = q * 32 + lane;  // pixel index inside the tile (this thread's accumulator row)
+    // ------------------------------------------------------------------ epilogue (warps 2..9)
+    // Two warps per TMEM lane quadrant (= 32 pixels of the tile), taking alternate 32-column chunks, so every SM
+    // sub-partition has two epilogue warps to hide each other's TMEM / shared-memory / residual-load latencies.
+    // Each warp runs on its own: one private 4 KB staging buffer, private TMA stores (bulk groups are per thread:
+    // lane 0), no CTA-wide barrier per chunk.
+    const int q = warp & 3;            // TMEM lane quadrant this warp may access
+    const int half = (warp - 2) >> 2;  // which of the quadrant's two warps: chunks half, half + 2, ...
     const int epi_tid = threadIdx.x - 64;
-    const uint32_t stage0 = L.staging + (uint32_t)q * 8192u;
-    const int tw = row % p.TW, th = row / p.TW;
+    const uint32_t buf = L.staging + (uint32_t)(warp - 2) * 4096u;
     const int sub_tw0 = (q * 32) % p.TW, sub_th0 = (q * 32) / p.TW;  // origin of this warp's 32-pixel store box
     const bool affine = (p.scale != nullptr) || (p.bias != nullptr);
     const bool has_res = p.residual != nullptr;
@@ -239,7 +245,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     int it = 0;
     int affine_nt = -1;
-    uint32_t chunk_counter = 0;
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
       const int nt = t % p.n_tiles, mt = t / p.n_tiles;
       const int b = mt / tiles_per_img, rem = mt % tiles_per_img;
@@ -249,15 +254,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int n0 = nt * BN;
       const int chunks = min(BN / 32, (p.n_out - n0 + 31) / 32);
 
-      if (affine && nt != affine_nt) {  // (re)load this column block's scale / shift: uniform over the 4 warps
-        named_bar_sync(1, 128);         // every warp is done reading the previous block's values
-        for (int c = epi_tid; c < BN; c += 128) {
+      if (affine && nt != affine_nt) {  // (re)load this column block's scale / shift: uniform over the 8 warps
+        named_bar_sync(1, 256);         // every warp is done reading the previous block's values
+        for (int c = epi_tid; c < BN; c += 256) {
           const int col = n0 + c;
           const bool ok = col < p.n_out;
           st_shared_f32(L.affine + 4 * c, (ok && p.scale) ? __ldg(p.scale + col) : 1.f);
           st_shared_f32(L.affine + 4 * (BN + c), (ok && p.bias) ? __ldg(p.bias + col) : 0.f);
         }
-        named_bar_sync(1, 128);
+        named_bar_sync(1, 256);
         affine_nt = nt;
       }
 
@@ -271,19 +276,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           rok[i] = (w0 + rtw[i] < p.y_w) && (h0 + rth[i] < p.y_h);
           roff[i] = b * p.r_sb + (long long)(h0 + rth[i]) * p.r_sh + (long long)(w0 + rtw[i]) * p.r_sw + col4 * 4;
         }
+        // pull this warp's share of the residual slab (32 rows x its chunks x 128 B) towards L2 now: the per-chunk
+        // loads below then see L2 latency instead of DRAM latency
+        if (col4 < chunks && (col4 & 1) == half) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (rok[i]) prefetch_l2(p.residual + roff[i] - col4 * 4 + n0 + col4 * 32);
+        }
+        const int cfirst = n0 + half * 32;
 #pragma unroll
         for (int i = 0; i < 8; ++i)
-          rr[i] = (rok[i] && n0 + col4 * 4 < p.n_out) ? __ldg(reinterpret_cast<const float4*>(p.residual + roff[i] + n0))
-                                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+          rr[i] = (rok[i] && half < chunks && cfirst + col4 * 4 < p.n_out)
+                      ? __ldg(reinterpret_cast<const float4*>(p.residual + roff[i] + cfirst))
+                      : make_float4(0.f, 0.f, 0.f, 0.f);
       }
 
       mbar_wait(L.tfull[acc], acc_phase);
       tc_fence_after();
 #pragma unroll 1
-      for (int j = 0; j < chunks; ++j, ++chunk_counter) {
-        const uint32_t buf = stage0 + (chunk_counter & 1u) * 4096u;
+      for (int j = half; j < chunks; j += 2) {
         const int c0 = n0 + j * 32;
-        if (lane == 0) tma_wait_group_read<1>();  // the store that used this buffer two chunks ago has read it
+        if (lane == 0) tma_wait_group_read<0>();  // this warp's previous store has read the staging buffer
         __syncwarp();
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + j * 32), v);
@@ -293,11 +306,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int r = 4 * i + (lane >> 3);
             st_shared_v4(buf + r * 128 + ((col4 ^ (r & 7)) << 4), rr[i].x, rr[i].y, rr[i].z, rr[i].w);
           }
-          if (j + 1 < chunks) {  // prefetch the next chunk's residual while this one is processed
+          if (j + 2 < chunks) {  // prefetch this warp's next chunk of the residual while this one is processed
 #pragma unroll
             for (int i = 0; i < 8; ++i)
-              rr[i] = (rok[i] && c0 + 32 + col4 * 4 < p.n_out)
-                          ? __ldg(reinterpret_cast<const float4*>(p.residual + roff[i] + c0 + 32))
+              rr[i] = (rok[i] && c0 + 64 + col4 * 4 < p.n_out)
+                          ? __ldg(reinterpret_cast<const float4*>(p.residual + roff[i] + c0 + 64))
                           : make_float4(0.f, 0.f, 0.f, 0.f);
           }
           __syncwarp();
@@ -336,7 +349,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (lane == 0) mbar_arrive(L.tempty[acc]);
     }
     if (lane == 0) tma_wait_group<0>();
-    (void)tw; (void)th;
   }
 
   tc_fence_before();
@@ -709,16 +721,36 @@ int launch_gemm(const GemmProblem& g, cudaStream_t stream) {
   }
   const int grid = persistent_grid(total);
   mmt::ProfScope prof(g.prof_family, gemm_flops(g), gemm_bytes(g), stream);
-  conv_tc_kernel<BN><<<grid, kThreads, C::kSmemBytes, stream>>>(tmA, tmB, tmY, p);
+  conv_tc_kernel<BN><<<grid, kFpropThreads, C::kSmemBytes, stream>>>(tmA, tmB, tmY, p);
   return mmt::check_launch("conv_tc_kernel");
 }
 
+// Column-tile width.  Every BN handles every n_out (weights beyond n_out are zero-filled by TMA, stores are clipped),
+// so the choice is purely a cost question: per tile the K loop streams (128 + BN) * 128 B per 32-channel block from L2
+// (~85 GB/s per SM measured) and the epilogue moves 128 * BN * 4 B (x2 with a residual) at the SM's share of HBM
+// (~44 GB/s); the kernel takes ceil(tiles / CTAs) rounds of that.  Narrow tiles lose on operand re-reads, wide tiles
+// on wave quantisation when there are few pixel tiles.
+int pick_bn(const GemmProblem& g) {
+  // Measured (profiles/r01_conv_layers_v3.log): with >= one full round of 128 x 256 tiles the widest tile wins
+  // (fewest re-reads of the A operand through the ~85 GB/s-per-SM L2 path); with fewer tiles than half the SMs a
+  // narrower tile doubles the CTAs — and with them the bytes in flight chip-wide — for the same total traffic.
+  int TW, TH;
+  pick_patch(g.y.w, g.y.h, kTileM, TW, TH);
+  const long long m_tiles = mmt::ceil_div<long long>(g.y.w, TW) * mmt::ceil_div<long long>(g.y.h, TH) * g.y.n;
+  const int ctas = g_max_ctas.load(std::memory_order_relaxed);
+  int bn = 256;
+  while (bn > 32 && bn / 2 >= g.n_out) bn /= 2;                                      // no tile that is mostly padding
+  while (bn > 64 && m_tiles * ((g.n_out + bn - 1) / bn) * 2 <= ctas) bn /= 2;       // fill the machine
+  return bn;
+}
+
 int dispatch_gemm(const GemmProblem& g, cudaStream_t stream) {
-  // out channels beyond n_out are zero-filled on load (weights) and clipped on store by TMA
-  if (g.n_out % 256 == 0) return launch_gemm<256>(g, stream);
-  if (g.n_out % 128 == 0) return launch_gemm<128>(g, stream);
-  if (g.n_out <= 32) return launch_gemm<32>(g, stream);
-  return launch_gemm<64>(g, stream);
+  switch (pick_bn(g)) {
+    case 256: return launch_gemm<256>(g, stream);
+    case 128: return launch_gemm<128>(g, stream);
+    case 64: return launch_gemm<64>(g, stream);
+    default: return launch_gemm<32>(g, stream);
+  }
 }
 
 View4 dense_nhwc(const float* base, long long n, long long h, long long w, long long c) {

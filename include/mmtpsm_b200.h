@@ -313,6 +313,10 @@ int mmt_conv_dgrad_f32(const float* dy_nhwc, const float* w_ohwi, float* dx_nhwc
 int mmt_conv_wgrad_f32(const float* x_nhwc, const float* dy_nhwc, float* dw_ohwi,
                        float* dbias /*nullable*/, const mmt_conv_shape* shape, int impl,
                        void* workspace, size_t workspace_bytes, void* stream);
+/* dw += wgrad(x, dy) into a live gradient buffer (tcgen05 path only; MMT_ERR_UNSUPPORTED otherwise): no memset, no
+ * temporary, no separate accumulation pass. */
+int mmt_conv_wgrad_accumulate_f32(const float* x_nhwc, const float* dy_nhwc, float* dw_ohwi, const mmt_conv_shape* shape,
+                                  void* stream);
 
 /* Fused elementwise helpers around the convs (all NHWC fp32, contiguous) ------------------- */
 /* g_out = g_in * (y > 0) * scale[c]  (ReLU + FrozenBN backward; scale nullable, relu optional) */

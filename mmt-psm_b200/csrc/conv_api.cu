@@ -97,3 +97,17 @@ extern "C" int mmt_conv_wgrad_f32(const float* x, const float* dy, float* dw, fl
   if (dbias) return mmt::conv_bias_grad(dy, (long long)s->batch * s->out_h * s->out_w, s->out_c, dbias, stream);
   return MMT_OK;
 }
+
+// dw += wgrad(x, dy): the tensor-core kernel's split-K partial tiles are reduced into dw by TMA anyway, so accumulating
+// into a live gradient buffer (the optimizer's flat arena) costs nothing and saves the memset, the temporary and the
+// `grad += dw` pass an autograd AccumulateGrad node would launch.  tcgen05 path only.
+extern "C" int mmt_conv_wgrad_accumulate_f32(const float* x, const float* dy, float* dw, const mmt_conv_shape* s,
+                                             void* stream_) {
+  if (int rc = check_shape(s, "conv_wgrad_accumulate")) return rc;
+  MMT_REQUIRE(dw != nullptr, "conv_wgrad_accumulate: null dw");
+  if (s->batch == 0) return MMT_OK;
+  MMT_REQUIRE(x && dy, "conv_wgrad_accumulate: null pointer");
+  if (!mmt::conv_tc_supported_wgrad(*s))
+    return mmt::fail(MMT_ERR_UNSUPPORTED, "conv_wgrad_accumulate: shape not supported by the tcgen05 kernel");
+  return mmt::conv_wgrad_tc(x, dy, dw, nullptr, *s, nullptr, 0, (cudaStream_t)stream_, true);
+}

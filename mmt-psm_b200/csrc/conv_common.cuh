@@ -33,7 +33,7 @@ int conv_stem_tc(const float* x, const float* w, const float* scale, const float
 int conv_dgrad_tc(const float* dy, const float* w_t, float* dx, const mmt_conv_shape& s,
                   cudaStream_t stream);
 int conv_wgrad_tc(const float* x, const float* dy, float* dw, float* dbias, const mmt_conv_shape& s,
-                  void* workspace, size_t workspace_bytes, cudaStream_t stream);
+                  void* workspace, size_t workspace_bytes, cudaStream_t stream, bool accumulate = false);
 // [out_c][k_h][k_w][in_c] -> [in_c][k_h][k_w][out_c] with the taps rotated by 180 degrees
 int conv_filter_for_dgrad(const float* w, float* w_t, const mmt_conv_shape& s, cudaStream_t stream);
 

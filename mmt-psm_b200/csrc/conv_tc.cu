@@ -899,7 +899,7 @@ int conv_filter_for_dgrad(const float* w, float* w_t, const mmt_conv_shape& s, c
 }
 
 int conv_wgrad_tc(const float* x, const float* dy, float* dw, float* dbias, const mmt_conv_shape& s,
-                  void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+                  void* workspace, size_t workspace_bytes, cudaStream_t stream, bool accumulate) {
   (void)workspace; (void)workspace_bytes; (void)dbias;
   const bool pointwise = s.k_h == 1 && s.k_w == 1 && s.pad == 0;
   View4 vdy, vx;
@@ -924,7 +924,8 @@ int conv_wgrad_tc(const float* x, const float* dy, float* dw, float* dbias, cons
   if (int rc = make_map(&tmX, vx, 32, TW, TH, "wgrad x", CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return rc;
   const long long Ktot = (long long)s.k_h * s.k_w * s.in_c;
   if (int rc = make_map_2d(&tmDW, dw, Ktot, s.out_c, Ktot, 32, 128, "wgrad dw")) return rc;
-  MMT_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)s.out_c * Ktot, stream));
+  // every partial tile is ADDED into dw by TMA reduce: zero it first, unless the caller accumulates (dw += ...)
+  if (!accumulate) MMT_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)s.out_c * Ktot, stream));
   WgradParams p;
   p.tiles_w = (int)ceil_div<long long>(vdy.w, TW);
   p.tiles_h = (int)ceil_div<long long>(vdy.h, TH);

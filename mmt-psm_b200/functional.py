@@ -38,9 +38,24 @@ class _ConvBnAct(torch.autograd.Function):
         need_x, need_w, _, need_b, need_r = ctx.needs_input_grad[:5]
         dx = K.conv_dgrad(g_conv, w, shape) if need_x else None
         dw = db = None
-        if need_w or need_b:
+        if (need_w and not need_b and _fused_grad_sink is not None and w.is_leaf and w.grad is not None
+                and K.conv_wgrad_accumulate_(x, g_conv, shape, w.grad)):
+            _fused_grad_sink([w])     # dW went straight into the optimizer's gradient arena
+            need_w = False
+        elif need_w or need_b:
             dw, db = K.conv_wgrad(x, g_conv, shape, want_dbias=need_b)
         return dx, (dw if need_w else None), None, db, (g_res if (need_r and ctx.has_res) else None), None, None, None
+
+
+# When set (solver.FusedSGDEMA does it), weight gradients of the tcgen05 convs are accumulated IN PLACE into `w.grad`
+# (a persistent view of the flat gradient arena) and the callback is told which parameters were written — autograd
+# then sees no gradient for w, so no AccumulateGrad add and no post-accumulate hook runs for it.
+_fused_grad_sink = None
+
+
+def set_fused_grad_sink(callback):
+    global _fused_grad_sink
+    _fused_grad_sink = callback
 
 
 def conv_bn_act(x, w, scale=None, bias=None, residual=None, relu=False, stride=1, pad=0):

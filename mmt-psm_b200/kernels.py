@@ -462,6 +462,21 @@ def conv_wgrad(x, dy, shape, want_dbias=False, impl=None):
     return dw, db
 
 
+def conv_wgrad_accumulate_(x, dy, shape, dw):
+    """dw += wgrad(x, dy) in place (tcgen05 path).  Returns False — nothing done — when the shape or the conv math mode
+    needs the generic path."""
+    if _conv_impl != CONV_AUTO or not (dw.is_contiguous() and dw.dtype == torch.float32):
+        return False
+    _need_cuda(x, dy, dw)
+    L = _l.lib()
+    assert x.is_contiguous() and dy.is_contiguous()
+    rc = L.mmt_conv_wgrad_accumulate_f32(_p(x), _p(dy), _p(dw), ctypes.byref(shape), _stream())
+    if rc == 4:  # MMT_ERR_UNSUPPORTED
+        return False
+    check(rc, "conv_wgrad_accumulate")
+    return True
+
+
 def bn_relu_backward(grad_y, y, scale, relu):
     _need_cuda(grad_y, y, scale)
     L = _l.lib()

@@ -76,6 +76,7 @@ _PROTOS = {
     "mmt_conv_stem_fprop_f32": (c_int, [P, P, P, P, P, POINTER(ConvShape), c_int, P, c_size_t, P]),
     "mmt_conv_dgrad_f32": (c_int, [P, P, P, POINTER(ConvShape), c_int, P, c_size_t, P]),
     "mmt_conv_wgrad_f32": (c_int, [P, P, P, P, POINTER(ConvShape), c_int, P, c_size_t, P]),
+    "mmt_conv_wgrad_accumulate_f32": (c_int, [P, P, P, POINTER(ConvShape), P]),
     "mmt_bn_relu_backward_f32": (c_int, [P, P, P, P, c_int64, c_int, c_int, P]),
     "mmt_maxpool3x3s2_forward_f32": (c_int, [P, P, c_int, c_int, c_int, c_int, P]),
     "mmt_subsample2_forward_f32": (c_int, [P, P, c_int, c_int, c_int, c_int, P]),

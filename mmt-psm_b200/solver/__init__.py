@@ -46,6 +46,8 @@ class FusedSGDEMA(object):
                 view = self.flat_t[e["begin"]:e["end"]].view_as(p)
                 view.copy_(p.data)
                 p.data = view
+        from .. import functional as Fk
+        Fk.set_fused_grad_sink(self.mark_touched)   # bias-free tcgen05 convs write dW into flat_g directly
         self.base_lr = s.BASE_LR
         self.lr = s.BASE_LR
         self.param_groups = [{"lr": self.lr}]  # for the reference's log line (MTtrainer.py:218)

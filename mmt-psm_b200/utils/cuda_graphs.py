@@ -61,10 +61,19 @@ class GraphedCallable(object):
             params = self._leaf_params(live)
             for p in params:
                 hooks.append(p.register_post_accumulate_grad_hook(lambda q, seen=seen: seen.append(q)))
+            # weight gradients written straight into the arena (functional._fused_grad_sink) bypass AccumulateGrad:
+            # record those parameters too, they must be reported on every replay
+            from .. import functional as Fk
+            orig_sink = Fk._fused_grad_sink
+            if orig_sink is not None:
+                Fk.set_fused_grad_sink(lambda ps: (seen.extend(ps), orig_sink(ps)))
             n0 = _l.launch_count()
             self.g_bwd = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.g_bwd, pool=self.pool):
-                torch.autograd.backward(live, self.static_gout)
+            try:
+                with torch.cuda.graph(self.g_bwd, pool=self.pool):
+                    torch.autograd.backward(live, self.static_gout)
+            finally:
+                Fk.set_fused_grad_sink(orig_sink)
             self.bwd_launches = _l.launch_count() - n0
             for h in hooks:
                 h.remove()

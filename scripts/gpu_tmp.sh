@@ -1,7 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:conv_tc_kernel -c 2 -f -o gpurun_out/ncu_epi_res2 \
-   python scripts/conv_one.py 2 200 200 64 256 1 1 0 res fprop 2 > gpurun_out/ncu_epi_res2.log 2>&1
-tail -n 2 gpurun_out/ncu_epi_res2.log
-timeout 600 python scripts/conv_bench.py --all > gpurun_out/conv_bench.log 2>&1
-tail -n 1 gpurun_out/conv_bench.log
+timeout 1200 python -m pytest tests -m gpu -q --timeout 600 2>&1 | grep -v "^E   *\[" > gpurun_out/pytest_gpu.log
+grep -n "Error\|^E \|passed\|failed" gpurun_out/pytest_gpu.log | head -30
+MMT_PROFILE_QUICK=1 timeout 600 python scripts/profile_step.py 8 2>&1 | grep -v Warn | tail -3
+timeout 300 python scripts/loss_trace.py 30 2000 2>/dev/null | cut -c1-230 | tail -2

@@ -55,6 +55,17 @@ def peaks():
     return dict(hbm=6650.0, tensor_burst=1590.0, tensor=1400.0, source="fallback (B200_PROFILING.md)")
 
 
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the tcgen05 conv family, from the committed ncu capture
+    of this command (profiles/r01_conv_traffic_v3.json); None if the summary is absent."""
+    p = os.path.join(ROOT, "profiles", "r01_conv_traffic_v3.json")
+    try:
+        fam = json.load(open(p))["families"]
+        return [f for f in fam if f["kernel"].startswith("all")][0]["dram_bytes_per_launch"]
+    except (OSError, KeyError, IndexError, ValueError):
+        return None
+
+
 def workload_name(args):
     if args.workload == "mt":
         return ("MMT-PSM mean-teacher (MT.AUG_K=2, AUG_S=1, LAMBDA=5, CLS_LOSS=0.2, FG_HINT=1, relation off), R50-FPN, "
@@ -313,7 +324,8 @@ def run_ours(args):
                 "achieved": achieved, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": achieved / pk["tensor"],
                 "peak_source": pk["source"] + ": bf16 cuBLAS sustained; the kernel feeds TF32 operands (fp32 storage), whose "
                 "hardware rate is half the bf16 rate, so frac <= 0.5 by construction",
-                "frac_of_tf32_rate": achieved / (pk["tensor"] / 2), "traffic": None,
+                "frac_of_tf32_rate": achieved / (pk["tensor"] / 2), "traffic": ncu_traffic(),
+                "algorithmic_bytes_per_launch": sum(f["bytes"] for f in tc) / max(n_tc, 1),
                 "launches_per_step": n_tc / nprof, "avg_launch_us": ms_tc / max(n_tc, 1) * 1e3,
                 "gflop_per_launch": fl_tc / max(n_tc, 1) / 1e9,
                 "share_of_step": ms_tc / nprof / step_ms_prof,

@@ -85,6 +85,16 @@ int mmt_decode_clip_boxes_f32(const float* deltas, const float* anchors, const f
                               const float* image_wh, int n_images, int per_image, float wx, float wy,
                               float ww, float wh, float xform_clip, float min_size, float* boxes,
                               float* scores_nms, unsigned char* valid, void* stream);
+/* ------------------------------------------------------------------------------------------
+ * Fused boxlist_iou + Matcher (reference structures/boxlist_ops.py:57-92, modeling/matcher.py:44-138, top_k < 2):
+ * matches_out[a] = index of the ground-truth box with the highest IoU (+1 extents) for prediction a, or -1 (best IoU
+ * below low_threshold) / -2 (between the thresholds); with allow_low_quality_matches every prediction that attains
+ * some ground truth's maximum IoU gets its arg-max back.  The [n_gt, n_boxes] IoU matrix is never materialised.
+ * gt / boxes: xyxy fp32, 16-byte aligned; n_gt <= 1024; workspace >= mmt_match_workspace_bytes(). */
+size_t mmt_match_workspace_bytes(int n_gt, int n_boxes);
+int mmt_match_boxes_f32(const float* gt_xyxy, int n_gt, const float* boxes_xyxy, int n_boxes, float high_threshold,
+                        float low_threshold, int allow_low_quality_matches, int64_t* matches_out, void* workspace,
+                        size_t workspace_bytes, void* stream);
 /* Single problem convenience form (exactly `_C.nms(dets, scores, thr)` minus the tensor plumbing). */
 int mmt_nms_f32(const float* boxes_xyxy, const float* scores, int n, float iou_threshold,
                 int64_t* keep_out, int* n_keep_out, void* workspace, size_t workspace_bytes,

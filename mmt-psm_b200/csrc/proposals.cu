@@ -74,3 +74,135 @@ extern "C" int mmt_decode_clip_boxes_f32(const float* deltas, const float* ancho
       total, wx, wy, ww, wh, xform_clip, min_size, reinterpret_cast<float4*>(boxes), scores_nms, valid);
   return mmt::check_launch("decode_clip_boxes");
 }
+
+// ------------------------------------------------------------------------------------------------------------
+// Fused IoU + Matcher: for every prediction (anchor / proposal) the best-overlapping ground-truth box and the
+// Matcher's threshold codes, without materialising the [G, A] IoU matrix.
+//
+// Reference chain:  structures/boxlist_ops.py:57-92 (boxlist_iou: +1 extents, [G,A] matrix through ~10 elementwise
+// passes) -> modeling/matcher.py:44-138 (max over G, BELOW_LOW_THRESHOLD = -1, BETWEEN_THRESHOLDS = -2, and with
+// allow_low_quality_matches every prediction attaining some ground truth's best IoU gets its arg-max back).
+// At RPN scale that matrix is 40 x 159 882 floats per image; here each thread owns one prediction and walks the G
+// boxes held in shared memory.  Same fp32 expression per pair as the reference, so `==` against the per-GT maxima
+// selects exactly the pairs the reference's `quality == highest_quality_foreach_gt[:, None]` selects.
+namespace {
+
+constexpr int kMaxGtSmem = 1024;
+
+__device__ __forceinline__ float pair_iou(const float4 g, const float ga, const float4 b, const float ba) {
+  const float lx = fmaxf(g.x, b.x), ly = fmaxf(g.y, b.y);
+  const float rx = fminf(g.z, b.z), ry = fminf(g.w, b.w);
+  const float w = fmaxf(__fadd_rn(__fsub_rn(rx, lx), 1.f), 0.f), h = fmaxf(__fadd_rn(__fsub_rn(ry, ly), 1.f), 0.f);
+  const float inter = __fmul_rn(w, h);
+  return __fdiv_rn(inter, __fsub_rn(__fadd_rn(ga, ba), inter));
+}
+__device__ __forceinline__ float box_area(const float4 b) {
+  return __fmul_rn(__fadd_rn(__fsub_rn(b.z, b.x), 1.f), __fadd_rn(__fsub_rn(b.w, b.y), 1.f));
+}
+
+// pass 1: per prediction max / arg-max over the ground truth (first maximum wins, like torch.max) + per-GT maxima
+__global__ void __launch_bounds__(256) match_pass1_kernel(const float4* __restrict__ gt, int G,
+                                                          const float4* __restrict__ boxes, int A,
+                                                          float* __restrict__ best_val, int* __restrict__ best_idx,
+                                                          unsigned int* __restrict__ best_per_gt) {
+  extern __shared__ float4 s_gt[];  // G boxes then G areas (as float)
+  float* s_area = reinterpret_cast<float*>(s_gt + G);
+  for (int g = threadIdx.x; g < G; g += blockDim.x) {
+    const float4 b = __ldg(gt + g);
+    s_gt[g] = b;
+    s_area[g] = box_area(b);
+  }
+  __syncthreads();
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = a < A;
+  float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (live) b = __ldg(boxes + a);
+  const float ba = box_area(b);
+  float best = -1.f;
+  int arg = 0;
+  const int lane = threadIdx.x & 31;
+  for (int g = 0; g < G; ++g) {
+    const float v = live ? pair_iou(s_gt[g], s_area[g], b, ba) : 0.f;
+    if (v > best) { best = v; arg = g; }
+    // IoU >= 0: the IEEE bit pattern orders like the value, so an unsigned max is a float max
+    unsigned int m = __float_as_uint(v);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0 && m != 0u) atomicMax(best_per_gt + g, m);
+  }
+  if (live) { best_val[a] = best; best_idx[a] = arg; }
+}
+
+// pass 2: threshold codes, and the low-quality restore
+__global__ void __launch_bounds__(256) match_pass2_kernel(const float4* __restrict__ gt, int G,
+                                                          const float4* __restrict__ boxes, int A,
+                                                          const float* __restrict__ best_val,
+                                                          const int* __restrict__ best_idx,
+                                                          const unsigned int* __restrict__ best_per_gt, float high_thr,
+                                                          float low_thr, int allow_low_quality,
+                                                          long long* __restrict__ matches) {
+  extern __shared__ float4 s_gt[];
+  float* s_area = reinterpret_cast<float*>(s_gt + G);
+  float* s_best = s_area + G;
+  if (allow_low_quality) {
+    for (int g = threadIdx.x; g < G; g += blockDim.x) {
+      const float4 b = __ldg(gt + g);
+      s_gt[g] = b;
+      s_area[g] = box_area(b);
+      s_best[g] = __uint_as_float(best_per_gt[g]);
+    }
+    __syncthreads();
+  }
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= A) return;
+  const float v = best_val[a];
+  long long m = best_idx[a];
+  const long long all_m = m;
+  if (v < low_thr) m = -1;
+  else if (v < high_thr) m = -2;
+  if (allow_low_quality) {
+    const float4 b = __ldg(boxes + a);
+    const float ba = box_area(b);
+    bool restore = false;
+    for (int g = 0; g < G; ++g) restore |= (pair_iou(s_gt[g], s_area[g], b, ba) == s_best[g]);
+    if (restore) m = all_m;
+  }
+  matches[a] = m;
+}
+
+}  // namespace
+
+extern "C" size_t mmt_match_workspace_bytes(int n_gt, int n_boxes) {
+  return mmt::align_up(sizeof(float) * (size_t)n_boxes, 256) + mmt::align_up(sizeof(int) * (size_t)n_boxes, 256) +
+         mmt::align_up(sizeof(unsigned int) * (size_t)(n_gt > 0 ? n_gt : 1), 256);
+}
+
+extern "C" int mmt_match_boxes_f32(const float* gt_xyxy, int n_gt, const float* boxes_xyxy, int n_boxes,
+                                   float high_threshold, float low_threshold, int allow_low_quality_matches,
+                                   int64_t* matches_out, void* workspace, size_t workspace_bytes, void* stream_) {
+  MMT_REQUIRE(n_gt > 0 && n_boxes > 0, "match_boxes: empty ground truth or prediction set (the reference raises too)");
+  MMT_REQUIRE(n_gt <= kMaxGtSmem, "match_boxes: more than %d ground-truth boxes per image", kMaxGtSmem);
+  MMT_REQUIRE(gt_xyxy && boxes_xyxy && matches_out, "match_boxes: null pointer");
+  MMT_REQUIRE((((uintptr_t)gt_xyxy | (uintptr_t)boxes_xyxy) & 15) == 0, "match_boxes: boxes must be 16-byte aligned");
+  if (workspace == nullptr || workspace_bytes < mmt_match_workspace_bytes(n_gt, n_boxes))
+    return mmt::fail(MMT_ERR_WORKSPACE_TOO_SMALL, "match_boxes: workspace too small");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  char* w = (char*)workspace;
+  float* best_val = (float*)w;
+  w += mmt::align_up(sizeof(float) * (size_t)n_boxes, 256);
+  int* best_idx = (int*)w;
+  w += mmt::align_up(sizeof(int) * (size_t)n_boxes, 256);
+  unsigned int* best_per_gt = (unsigned int*)w;
+  MMT_CUDA(cudaMemsetAsync(best_per_gt, 0, sizeof(unsigned int) * (size_t)n_gt, stream));
+  const int blocks = (n_boxes + 255) / 256;
+  const size_t smem = (size_t)n_gt * (sizeof(float4) + 2 * sizeof(float));
+  match_pass1_kernel<<<blocks, 256, smem, stream>>>(reinterpret_cast<const float4*>(gt_xyxy), n_gt,
+                                                    reinterpret_cast<const float4*>(boxes_xyxy), n_boxes, best_val,
+                                                    best_idx, best_per_gt);
+  if (int rc = mmt::check_launch("match_pass1")) return rc;
+  match_pass2_kernel<<<blocks, 256, smem, stream>>>(reinterpret_cast<const float4*>(gt_xyxy), n_gt,
+                                                    reinterpret_cast<const float4*>(boxes_xyxy), n_boxes, best_val,
+                                                    best_idx, best_per_gt, high_threshold, low_threshold,
+                                                    allow_low_quality_matches, (long long*)matches_out);
+  return mmt::check_launch("match_pass2");
+}

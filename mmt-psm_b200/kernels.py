@@ -123,6 +123,20 @@ def decode_clip_boxes(deltas, anchors, weights, xform_clip, image_wh=None, per_i
     return boxes, s_nms, valid
 
 
+def match_boxes(gt, boxes, high_threshold, low_threshold, allow_low_quality_matches):
+    """Fused boxlist_iou + Matcher: gt [G,4], boxes [A,4] xyxy -> matches [A] int64 (gt index, -1 below, -2 between)."""
+    _need_cuda(gt, boxes)
+    L = _l.lib()
+    gt, boxes = _f32c(gt), _f32c(boxes)
+    G, A = gt.shape[0], boxes.shape[0]
+    out = torch.empty(A, dtype=torch.int64, device=boxes.device)
+    wsb = L.mmt_match_workspace_bytes(G, A)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=boxes.device)
+    check(L.mmt_match_boxes_f32(_p(gt), G, _p(boxes), A, float(high_threshold), float(low_threshold),
+                                int(bool(allow_low_quality_matches)), _p(out), _p(ws), wsb, _stream()), "match_boxes")
+    return out
+
+
 # ---------------------------------------------------------------------------------- ROIAlign
 def roi_align_forward(input, rois, spatial_scale, pooled_h, pooled_w, sampling_ratio):
     """`_C.roi_align_forward` (reference csrc/ROIAlign.h:11-26): NCHW in -> [K,C,ph,pw] out.

@@ -207,7 +207,7 @@ class FastRCNNLossComputation(object):
         self.proposal_matcher, self.fg_bg_sampler, self.box_coder, self.cfg = proposal_matcher, fg_bg_sampler, box_coder, cfg
 
     def match_targets_to_proposals(self, proposal, target):
-        matched_idxs = self.proposal_matcher(boxlist_iou(target, proposal))
+        matched_idxs = self.proposal_matcher.match(target, proposal)
         target = target.copy_with_fields(["labels"])
         matched = target[matched_idxs.clamp(min=0)]
         matched.add_field("matched_idxs", matched_idxs)

@@ -109,27 +109,33 @@ class MaskRCNNLossComputation(object):
         self.cfg, self.proposal_matcher, self.discretization_size = cfg, proposal_matcher, discretization_size
 
     def prepare_targets(self, proposals, targets):
+        """Reference mask_head/loss.py:101-149.  The reference rasterises only the rows whose re-matched label is
+        positive (a `nonzero` per image = a host sync); here every row gets a target and `__call__` weights the rows:
+        the mask head is only ever handed the box head's positive ROIs (keep_only_positive_boxes) and both heads match
+        with the same thresholds, so the weights are all ones in practice and the sums are the reference's."""
         labels, masks = [], []
         for p, t in zip(proposals, targets):
-            matched_idxs = self.proposal_matcher(boxlist_iou(t, p))
+            matched_idxs = self.proposal_matcher.match(t, p)
             lab = t.get_field("labels")[matched_idxs.clamp(min=0)].to(dtype=torch.int64)
-            lab[matched_idxs == Matcher.BELOW_LOW_THRESHOLD] = 0
-            pos = torch.nonzero(lab > 0).squeeze(1)
-            masks.append(project_masks_on_boxes(t.get_field("masks"), p[pos], matched_idxs[pos],
+            lab = torch.where(matched_idxs == Matcher.BELOW_LOW_THRESHOLD, lab.new_zeros(()), lab)
+            masks.append(project_masks_on_boxes(t.get_field("masks"), p, matched_idxs.clamp(min=0),
                                                 self.discretization_size))
             labels.append(lab)
         return labels, masks
 
     def __call__(self, proposals, mask_logits, targets):
         """mask_logits NHWC [P, M, M, num_classes]."""
+        if mask_logits.shape[0] == 0:
+            return mask_logits.sum() * 0
         labels, mask_targets = self.prepare_targets(proposals, targets)
         labels = cat(labels, dim=0)
         mask_targets = cat(mask_targets, dim=0)
-        pos = torch.nonzero(labels > 0).squeeze(1)
-        if mask_targets.numel() == 0:
-            return mask_logits.sum() * 0
-        sel = mask_logits[pos, :, :, labels[pos]]
-        return F.binary_cross_entropy_with_logits(sel, mask_targets)
+        rows = torch.arange(labels.shape[0], device=labels.device)
+        sel = mask_logits[rows, :, :, labels]
+        w = (labels > 0).to(sel.dtype)
+        bce = F.binary_cross_entropy_with_logits(sel, mask_targets, reduction="none")
+        # mean over the positive rows' pixels == the reference's BCE over the gathered positive rows
+        return (bce * w[:, None, None]).sum() / (w.sum() * (sel.shape[1] * sel.shape[2])).clamp(min=1)
 
 
 def make_roi_mask_loss_evaluator(cfg):

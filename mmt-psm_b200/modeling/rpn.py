@@ -138,6 +138,21 @@ class RPNPostProcessor(nn.Module):
                 if k > self.post_nms_top_n:
                     f2[:, a:a + k] &= f2[:, a:a + k].cumsum(1) <= self.post_nms_top_n
                 a += k
+        if num_levels > 1 and not self.training:
+            # per-image top-k in score order (reference :236-243) straight on the masked score rows: dropped rows
+            # carry -1 (< any sigmoid score), so the first n_valid entries of the sorted top-k are the reference's
+            # selection; ONE read-back (the per-image counts) for the whole pass
+            f2, s2 = flags.view(N, K_), flat_scores.view(N, K_)
+            k = min(self.fpn_post_nms_top_n, K_)
+            vals, inds = torch.where(f2, s2, s2.new_full((), -1.0)).topk(k, dim=1, sorted=True)
+            n_valid = (vals >= 0).sum(1).tolist()
+            boxlists = []
+            for j in range(N):
+                idx = inds[j, :n_valid[j]] + j * K_
+                bl = BoxList(boxes[idx], image_shapes[j], mode="xyxy")
+                bl.add_field("objectness", flat_scores[idx])
+                boxlists.append(bl)
+            return boxlists
         # ascending row index = image-major, level-major, descending score inside a level: the reference's cat order
         kept = flags.nonzero().squeeze(1)
         if num_levels > 1 and self.training:
@@ -150,11 +165,6 @@ class RPNPostProcessor(nn.Module):
         for j in range(N):
             idx = kept[a:a + per_image[j]]
             a += per_image[j]
-            if num_levels > 1 and not self.training:   # per-image top-k, score order (reference :236-243)
-                obj = flat_scores[idx]
-                k = min(self.fpn_post_nms_top_n, per_image[j])
-                _, inds = torch.topk(obj, k, dim=0, sorted=True)
-                idx = idx[inds]
             bl = BoxList(boxes[idx], image_shapes[j], mode="xyxy")
             bl.add_field("objectness", flat_scores[idx])
             boxlists.append(bl)
@@ -199,7 +209,7 @@ class RPNLossComputation(object):
         self.box_coder = box_coder
 
     def match_targets_to_anchors(self, anchor, target):
-        matched_idxs = self.proposal_matcher(boxlist_iou(target, anchor))
+        matched_idxs = self.proposal_matcher.match(target, anchor)
         target = target.copy_with_fields([])
         matched = target[matched_idxs.clamp(min=0)]
         matched.add_field("matched_idxs", matched_idxs)
@@ -209,7 +219,7 @@ class RPNLossComputation(object):
         """Reference rpn/loss.py:47-83; the masked writes are selects (no index lists -> no host sync)."""
         labels, regression_targets = [], []
         for a, t in zip(anchors, targets):
-            midx = self.proposal_matcher(boxlist_iou(t, a))
+            midx = self.proposal_matcher.match(t, a)
             gt = t.bbox[midx.clamp(min=0)]
             lab = (midx >= 0).to(dtype=torch.float32)
             ignore = ~a.get_field("visibility").bool() | (midx == Matcher.BETWEEN_THRESHOLDS)

@@ -277,6 +277,38 @@ def test_elementwise_vs_torch(cuda):
     assert torch.equal(K().nhwc_to_nchw(K().nchw_to_nhwc(a)), a)
 
 
+# ------------------------------------------------------------------------------ fused matcher
+def test_match_boxes_golden_and_matrix_path(cuda):
+    """mmt_match_boxes_f32 == Matcher(boxlist_iou(gt, pr)) of the reference: the golden assignments for both Matcher
+    configurations (glue.npz, produced by the reference), and the in-package matrix path on a larger random problem
+    with duplicated boxes (ties) and a ground truth nobody overlaps (the IoU == 0 low-quality quirk)."""
+    from mmt_psm_b200.modeling.matcher import Matcher
+    from mmt_psm_b200.structures.bounding_box import BoxList
+    from mmt_psm_b200.structures.boxlist_ops import boxlist_iou
+    kn = K()
+    g = golden("glue")
+    gt, pr = torch.from_numpy(g["iou_gt"]).to(cuda), torch.from_numpy(g["iou_pr"]).to(cuda)
+    for key, (hi, lo, lq) in (("match_rpn", (0.7, 0.3, True)), ("match_box", (0.5, 0.5, False))):
+        got = kn.match_boxes(gt, pr, hi, lo, lq).cpu().numpy()
+        assert np.array_equal(got, g[key]), key
+    gen = torch.Generator().manual_seed(77)
+    base = torch.rand(60, 2, generator=gen) * 700
+    gts = torch.cat([base, base + 20 + torch.rand(60, 2, generator=gen) * 80], 1)
+    gts[7] = gts[3]                                            # duplicate ground truth: arg-max tie
+    gts[11] = torch.tensor([5000., 5000., 5040., 5040.])       # overlaps nothing
+    ctr = torch.rand(30000, 2, generator=gen) * 800
+    boxes = torch.cat([ctr, ctr + 8 + torch.rand(30000, 2, generator=gen) * 120], 1)
+    boxes[:60] = gts                                           # exact hits
+    a, b = BoxList(gts.to(cuda), (800, 800)), BoxList(boxes.to(cuda), (800, 800))
+    for hi, lo, lq in ((0.7, 0.3, True), (0.5, 0.5, False)):
+        m = Matcher(hi, lo, allow_low_quality_matches=lq)
+        got = m.match(a, b)
+        assert torch.equal(got, m(boxlist_iou(a, b)))
+        assert np.array_equal(got.cpu().numpy(), R.matcher_ref(R.boxlist_iou_ref(gts, boxes), hi, lo, lq))
+    with pytest.raises(ValueError):
+        Matcher(0.5, 0.5).match(BoxList(torch.zeros(0, 4, device=cuda), (800, 800)), b)
+
+
 # ------------------------------------------------------------------------- proposal decoding
 def test_decode_clip_boxes_golden_and_oracle(cuda):
     kn = K()

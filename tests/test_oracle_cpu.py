@@ -106,6 +106,14 @@ def test_level_mapper_oracle():
     assert np.array_equal(R.level_mapper_ref(g["lvl_boxes"]), g["lvl"])
 
 
+def test_iou_and_matcher_oracle_match_reference():
+    g = golden("glue")
+    iou = R.boxlist_iou_ref(g["iou_gt"], g["iou_pr"])
+    assert np.array_equal(iou.numpy(), g["iou"])
+    assert np.array_equal(R.matcher_ref(iou, 0.7, 0.3, True), g["match_rpn"])
+    assert np.array_equal(R.matcher_ref(iou, 0.5, 0.5, False), g["match_box"])
+
+
 def test_decode_oracle_matches_reference_box_coder():
     """oracle decode == the reference's BoxCoder.decode on the golden pairs (both weight sets), bit for bit."""
     g = golden("glue")

@@ -95,6 +95,18 @@ size_t mmt_match_workspace_bytes(int n_gt, int n_boxes);
 int mmt_match_boxes_f32(const float* gt_xyxy, int n_gt, const float* boxes_xyxy, int n_boxes, float high_threshold,
                         float low_threshold, int allow_low_quality_matches, int64_t* matches_out, void* workspace,
                         size_t workspace_bytes, void* stream);
+/* BoxCoder.encode fused with the gather of the matched ground truth (reference modeling/box_coder.py:22-54; call sites
+ * rpn/loss.py:79-82, roi_heads/box_head/loss.py:75-78): targets[t] = encode(gt[max(matched_idx[t], 0)], boxes[t]);
+ * matched_idx NULL = row-wise pairs.  16-byte aligned box arrays. */
+int mmt_encode_boxes_f32(const float* gt_xyxy, const int64_t* matched_idx, const float* boxes_xyxy, int64_t n_boxes,
+                         float wx, float wy, float ww, float wh, float* targets_out, void* stream);
+/* ROI table + FPN level of every box of a pooler call in one launch (reference modeling/poolers.py:78-89
+ * convert_to_roi_format and :31-42 LevelMapper): boxes = the per-image box lists concatenated, image_counts_host[i]
+ * boxes belong to image i (<= 64 images).  rois_out [K,5] = (image index, x1, y1, x2, y2), levels_out [K] int32 =
+ * clamp(floor(canonical_level + log2(sqrt(area) / canonical_scale + eps)), k_min, k_max) - k_min. */
+int mmt_fpn_rois_f32(const float* boxes_xyxy, const int* image_counts_host, int n_images, float k_min, float k_max,
+                     float canonical_scale, float canonical_level, float eps, float* rois_out, int* levels_out,
+                     void* stream);
 /* Single problem convenience form (exactly `_C.nms(dets, scores, thr)` minus the tensor plumbing). */
 int mmt_nms_f32(const float* boxes_xyxy, const float* scores, int n, float iou_threshold,
                 int64_t* keep_out, int* n_keep_out, void* workspace, size_t workspace_bytes,

@@ -206,3 +206,88 @@ extern "C" int mmt_match_boxes_f32(const float* gt_xyxy, int n_gt, const float* 
                                                     allow_low_quality_matches, (long long*)matches_out);
   return mmt::check_launch("match_pass2");
 }
+
+// ------------------------------------------------------------------------------------------------------------
+// BoxCoder.encode fused with the gather of the matched ground-truth box
+// (reference modeling/box_coder.py:22-54: ~25 elementwise launches per call; called per image from
+//  rpn/loss.py:79-82 and roi_heads/box_head/loss.py:75-78).  targets[t] = encode(gt[max(match[t], 0)], boxes[t]).
+namespace {
+__global__ void __launch_bounds__(256) encode_kernel(const float4* __restrict__ gt, const long long* __restrict__ match,
+                                                     const float4* __restrict__ boxes, long long total, float wx,
+                                                     float wy, float ww, float wh, float4* __restrict__ out) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    long long m = match ? match[i] : i;
+    if (m < 0) m = 0;
+    const float4 g = __ldg(gt + m), p = __ldg(boxes + i);
+    const float ex_w = __fadd_rn(__fsub_rn(p.z, p.x), 1.f), ex_h = __fadd_rn(__fsub_rn(p.w, p.y), 1.f);
+    const float ex_cx = __fadd_rn(p.x, __fmul_rn(0.5f, ex_w)), ex_cy = __fadd_rn(p.y, __fmul_rn(0.5f, ex_h));
+    const float gt_w = __fadd_rn(__fsub_rn(g.z, g.x), 1.f), gt_h = __fadd_rn(__fsub_rn(g.w, g.y), 1.f);
+    const float gt_cx = __fadd_rn(g.x, __fmul_rn(0.5f, gt_w)), gt_cy = __fadd_rn(g.y, __fmul_rn(0.5f, gt_h));
+    float4 o;
+    o.x = __fdiv_rn(__fmul_rn(wx, __fsub_rn(gt_cx, ex_cx)), ex_w);
+    o.y = __fdiv_rn(__fmul_rn(wy, __fsub_rn(gt_cy, ex_cy)), ex_h);
+    o.z = __fmul_rn(ww, logf(__fdiv_rn(gt_w, ex_w)));
+    o.w = __fmul_rn(wh, logf(__fdiv_rn(gt_h, ex_h)));
+    out[i] = o;
+  }
+}
+
+// ROI table of the FPN pooler: rois[k] = (image index as float, x1, y1, x2, y2) and the pyramid level of
+// modeling/poolers.py:31-42 (LevelMapper: floor(lvl0 + log2(sqrt(area) / s0 + eps)) clamped to [k_min, k_max], minus
+// k_min; area with +1 extents) — reference poolers.py:78-89 + :31-42: ~15 launches per pooler call.
+struct ImageOffsets { int n; int start[65]; };
+__global__ void __launch_bounds__(256) fpn_rois_kernel(const float4* __restrict__ boxes, int total, ImageOffsets off,
+                                                       float k_min, float k_max, float s0, float lvl0, float eps,
+                                                       float* __restrict__ rois, int* __restrict__ levels) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int img = 0;
+  while (img + 1 < off.n && i >= off.start[img + 1]) ++img;
+  const float4 b = __ldg(boxes + i);
+  float* r = rois + 5ll * i;
+  r[0] = (float)img; r[1] = b.x; r[2] = b.y; r[3] = b.z; r[4] = b.w;
+  const float area = __fmul_rn(__fadd_rn(__fsub_rn(b.z, b.x), 1.f), __fadd_rn(__fsub_rn(b.w, b.y), 1.f));
+  float lv = floorf(__fadd_rn(lvl0, log2f(__fadd_rn(__fdiv_rn(sqrtf(area), s0), eps))));
+  lv = fminf(fmaxf(lv, k_min), k_max);
+  levels[i] = (int)((long long)lv - (long long)k_min);
+}
+}  // namespace
+
+extern "C" int mmt_encode_boxes_f32(const float* gt_xyxy, const int64_t* matched_idx, const float* boxes_xyxy,
+                                    int64_t n_boxes, float wx, float wy, float ww, float wh, float* targets_out,
+                                    void* stream_) {
+  MMT_REQUIRE(n_boxes >= 0, "encode_boxes: negative size");
+  if (n_boxes == 0) return MMT_OK;
+  MMT_REQUIRE(gt_xyxy && boxes_xyxy && targets_out, "encode_boxes: null pointer");
+  MMT_REQUIRE((((uintptr_t)gt_xyxy | (uintptr_t)boxes_xyxy | (uintptr_t)targets_out) & 15) == 0,
+              "encode_boxes: box arrays must be 16-byte aligned");
+  long long blocks = (n_boxes + 255) / 256;
+  if (blocks > mmt::kNumSMs * 8) blocks = mmt::kNumSMs * 8;
+  encode_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream_>>>(
+      reinterpret_cast<const float4*>(gt_xyxy), (const long long*)matched_idx,
+      reinterpret_cast<const float4*>(boxes_xyxy), n_boxes, wx, wy, ww, wh, reinterpret_cast<float4*>(targets_out));
+  return mmt::check_launch("encode_boxes");
+}
+
+extern "C" int mmt_fpn_rois_f32(const float* boxes_xyxy, const int* image_counts_host, int n_images, float k_min,
+                                float k_max, float canonical_scale, float canonical_level, float eps, float* rois_out,
+                                int* levels_out, void* stream_) {
+  MMT_REQUIRE(n_images >= 0 && n_images <= 64, "fpn_rois: at most 64 images per call (got %d)", n_images);
+  ImageOffsets off;
+  off.n = n_images;
+  int total = 0;
+  for (int i = 0; i < n_images; ++i) {
+    MMT_REQUIRE(image_counts_host[i] >= 0, "fpn_rois: negative count");
+    off.start[i] = total;
+    total += image_counts_host[i];
+  }
+  off.start[n_images] = total;
+  if (total == 0) return MMT_OK;
+  MMT_REQUIRE(boxes_xyxy && rois_out && levels_out, "fpn_rois: null pointer");
+  MMT_REQUIRE(((uintptr_t)boxes_xyxy & 15) == 0, "fpn_rois: boxes must be 16-byte aligned");
+  fpn_rois_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream_>>>(
+      reinterpret_cast<const float4*>(boxes_xyxy), total, off, k_min, k_max, canonical_scale, canonical_level, eps,
+      rois_out, levels_out);
+  return mmt::check_launch("fpn_rois");
+}

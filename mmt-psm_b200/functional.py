@@ -33,8 +33,12 @@ class _ConvBnAct(torch.autograd.Function):
         x, w, scale, y = ctx.saved_tensors
         shape = ctx.shape
         gy = gy.contiguous()
-        g_res = K.bn_relu_backward(gy, y, None, True) if ctx.relu else gy      # d/d(pre-activation)
-        g_conv = K.bn_relu_backward(g_res, None, scale, False) if scale is not None else g_res
+        if ctx.relu and scale is not None and not ctx.has_res:
+            g_res = None
+            g_conv = K.bn_relu_backward(gy, y, scale, True)                    # ReLU mask and BN scale in one pass
+        else:
+            g_res = K.bn_relu_backward(gy, y, None, True) if ctx.relu else gy  # d/d(pre-activation)
+            g_conv = K.bn_relu_backward(g_res, None, scale, False) if scale is not None else g_res
         need_x, need_w, _, need_b, need_r = ctx.needs_input_grad[:5]
         dx = K.conv_dgrad(g_conv, w, shape) if need_x else None
         dw = db = None

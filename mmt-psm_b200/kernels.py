@@ -137,6 +137,36 @@ def match_boxes(gt, boxes, high_threshold, low_threshold, allow_low_quality_matc
     return out
 
 
+def encode_boxes(gt, matched_idx, boxes, weights):
+    """targets[t] = BoxCoder(weights).encode(gt[max(matched_idx[t], 0)], boxes[t]) in one launch."""
+    _need_cuda(gt, boxes, matched_idx)
+    L = _l.lib()
+    gt, boxes = _f32c(gt), _f32c(boxes)
+    if matched_idx is not None:
+        matched_idx = matched_idx.to(torch.int64).contiguous()
+        assert matched_idx.shape[0] == boxes.shape[0]
+    out = torch.empty_like(boxes)
+    wx, wy, ww, wh = weights
+    check(L.mmt_encode_boxes_f32(_p(gt), _p(matched_idx), _p(boxes), boxes.shape[0], float(wx), float(wy), float(ww),
+                                 float(wh), _p(out), _stream()), "encode_boxes")
+    return out
+
+
+def fpn_rois(boxes_cat, image_counts, k_min, k_max, canonical_scale=224.0, canonical_level=4.0, eps=1e-6):
+    """boxes_cat [K,4] (per-image lists concatenated), image_counts python ints -> (rois [K,5], levels [K] int32)."""
+    _need_cuda(boxes_cat)
+    L = _l.lib()
+    boxes_cat = _f32c(boxes_cat)
+    Kn = boxes_cat.shape[0]
+    assert sum(image_counts) == Kn
+    rois = torch.empty((Kn, 5), dtype=torch.float32, device=boxes_cat.device)
+    levels = torch.empty(Kn, dtype=torch.int32, device=boxes_cat.device)
+    counts = (c_int * len(image_counts))(*[int(c) for c in image_counts])
+    check(L.mmt_fpn_rois_f32(_p(boxes_cat), counts, len(image_counts), float(k_min), float(k_max), float(canonical_scale),
+                             float(canonical_level), float(eps), _p(rois), _p(levels), _stream()), "fpn_rois")
+    return rois, levels
+
+
 # ---------------------------------------------------------------------------------- ROIAlign
 def roi_align_forward(input, rois, spatial_scale, pooled_h, pooled_w, sampling_ratio):
     """`_C.roi_align_forward` (reference csrc/ROIAlign.h:11-26): NCHW in -> [K,C,ph,pw] out.

@@ -43,6 +43,8 @@ _PROTOS = {
                                           c_float, P, P, P, P]),
     "mmt_match_workspace_bytes": (c_size_t, [c_int, c_int]),
     "mmt_match_boxes_f32": (c_int, [P, c_int, P, c_int, c_float, c_float, c_int, P, P, c_size_t, P]),
+    "mmt_encode_boxes_f32": (c_int, [P, P, P, c_int64, c_float, c_float, c_float, c_float, P, P]),
+    "mmt_fpn_rois_f32": (c_int, [P, POINTER(c_int), c_int, c_float, c_float, c_float, c_float, c_float, P, P, P]),
     "mmt_roi_align_forward_f32": (c_int, [P, Strides4, c_int, c_int, c_int, c_int, P, c_int, c_float,
                                           c_int, c_int, c_int, P, Strides4, P]),
     "mmt_roi_align_backward_f32": (c_int, [P, Strides4, P, c_int, c_float, c_int, c_int, c_int, P,

@@ -136,8 +136,11 @@ class PostProcessor(nn.Module):
         per_image = [len(b) for b in boxes]
         device = class_logits.device
         concat = torch.cat([b.bbox for b in boxes], dim=0)
-        decoded = self.box_coder.decode(box_regression.reshape(sum(per_image), -1), concat)
         C = class_prob.shape[1]
+        # BoxCoder.decode of every class's deltas against its ROI, one launch (clipping happens per image below)
+        decoded, _, _ = K.decode_clip_boxes(box_regression.reshape(-1, 4), concat.repeat_interleave(C, dim=0),
+                                            self.box_coder.weights, self.box_coder.bbox_xform_clip)
+        decoded = decoded.reshape(sum(per_image), -1)
         decoded = decoded.split(per_image, dim=0)
         class_prob = class_prob.split(per_image, dim=0)
         # segments in (image, class) order, class-major inside an image: row = class block + roi
@@ -216,13 +219,12 @@ class FastRCNNLossComputation(object):
     def prepare_targets(self, proposals, targets):
         labels, regression_targets = [], []
         for p, t in zip(proposals, targets):
-            matched = self.match_targets_to_proposals(p, t)
-            midx = matched.get_field("matched_idxs")
-            lab = matched.get_field("labels").to(dtype=torch.int64)
+            midx = self.proposal_matcher.match(t, p)
+            lab = t.get_field("labels")[midx.clamp(min=0)].to(dtype=torch.int64)
             lab[midx == Matcher.BELOW_LOW_THRESHOLD] = 0
             lab[midx == Matcher.BETWEEN_THRESHOLDS] = -1
             labels.append(lab)
-            regression_targets.append(self.box_coder.encode(matched.bbox, p.bbox))
+            regression_targets.append(K.encode_boxes(t.bbox, midx, p.bbox, self.box_coder.weights))
         return labels, regression_targets
 
     def subsample(self, proposals, targets):

@@ -4,6 +4,7 @@ import torch
 from torch import nn
 
 from .. import functional as Fk
+from .. import kernels as K
 from .utils import cat
 
 
@@ -38,9 +39,12 @@ class Pooler(nn.Module):
         """x: list of NHWC level maps (only the first len(scales) are used); boxes: list[BoxList].
         Returns NHWC [K, R, R, C]."""
         n = len(self.scales)
-        rois = self.convert_to_roi_format(boxes)
         if n == 1:
+            rois = self.convert_to_roi_format(boxes)
             levels = torch.zeros(rois.shape[0], dtype=torch.int32, device=rois.device)
         else:
-            levels = self.map_levels(boxes).to(torch.int32)
+            # ROI table (convert_to_roi_format) and LevelMapper in ONE launch instead of ~15 elementwise ones
+            m = self.map_levels
+            rois, levels = K.fpn_rois(cat([b.bbox for b in boxes], dim=0), [len(b) for b in boxes], m.k_min, m.k_max,
+                                      m.s0, m.lvl0, m.eps)
         return Fk.fpn_roi_align(list(x[:n]), self.scales, rois, levels, self.output_size[0], self.sampling_ratio)

@@ -220,11 +220,11 @@ class RPNLossComputation(object):
         labels, regression_targets = [], []
         for a, t in zip(anchors, targets):
             midx = self.proposal_matcher.match(t, a)
-            gt = t.bbox[midx.clamp(min=0)]
             lab = (midx >= 0).to(dtype=torch.float32)
             ignore = ~a.get_field("visibility").bool() | (midx == Matcher.BETWEEN_THRESHOLDS)
             labels.append(torch.where(ignore, lab.new_full((), -1.0), lab))
-            regression_targets.append(self.box_coder.encode(gt, a.bbox))
+            # BoxCoder.encode(target[midx.clamp(0)], anchors) — gather + ~25 elementwise ops — as one launch
+            regression_targets.append(K.encode_boxes(t.bbox, midx, a.bbox, self.box_coder.weights))
         return labels, regression_targets
 
     def _cat_anchors(self, anchors):

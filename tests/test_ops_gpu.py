@@ -277,6 +277,33 @@ def test_elementwise_vs_torch(cuda):
     assert torch.equal(K().nhwc_to_nchw(K().nchw_to_nhwc(a)), a)
 
 
+# --------------------------------------------------------------------- encode / FPN ROI table
+def test_encode_boxes_and_fpn_rois_golden(cuda):
+    kn = K()
+    g = golden("glue")
+    ref, prop = torch.from_numpy(g["coder_ref"]).to(cuda), torch.from_numpy(g["coder_prop"]).to(cuda)
+    for name, w in (("rpn", (1., 1., 1., 1.)), ("box", (10., 10., 5., 5.))):
+        enc = kn.encode_boxes(ref, None, prop, w).cpu().numpy()
+        np.testing.assert_allclose(enc, g["coder_%s_enc" % name], rtol=2e-6, atol=2e-6)   # logf vs the CPU's log
+    # gather form: shuffled ground truth addressed through matched indices; negative codes clamp to entry 0
+    perm = torch.randperm(200, generator=torch.Generator().manual_seed(5))
+    midx = torch.empty(200, dtype=torch.int64)
+    midx[perm] = torch.arange(200)
+    shuffled = ref.cpu()[perm]                       # shuffled[midx[i]] == ref[i]
+    midx2 = midx.clone()
+    midx2[:5] = torch.tensor([-1, -2, -1, -2, -1])
+    enc = kn.encode_boxes(shuffled.to(cuda), midx2.to(cuda), prop, (1., 1., 1., 1.)).cpu().numpy()
+    np.testing.assert_allclose(enc[5:], g["coder_rpn_enc"][5:], rtol=2e-6, atol=2e-6)
+    want0 = kn.encode_boxes(shuffled[:1].repeat(5, 1).to(cuda), None, prop[:5], (1., 1., 1., 1.)).cpu().numpy()
+    assert np.array_equal(enc[:5], want0)
+    # ROI table + level mapper: golden levels of the reference's LevelMapper(2, 5); image index column
+    boxes = torch.from_numpy(g["lvl_boxes"]).to(cuda)
+    rois, levels = kn.fpn_rois(boxes, [100, 0, 205], 2.0, 5.0)
+    assert np.array_equal(levels.cpu().numpy().astype(np.int64), g["lvl"])
+    r = rois.cpu().numpy()
+    assert np.array_equal(r[:, 1:], g["lvl_boxes"]) and np.array_equal(r[:, 0], np.r_[np.zeros(100), np.full(205, 2.0)])
+
+
 # ------------------------------------------------------------------------------ fused matcher
 def test_match_boxes_golden_and_matrix_path(cuda):
     """mmt_match_boxes_f32 == Matcher(boxlist_iou(gt, pr)) of the reference: the golden assignments for both Matcher

@@ -134,10 +134,10 @@ class MTtrainer(object):
         if self.cuda_graphs:
             # the three conv trunks of the iteration are independent: enqueue them all on the side stream first, so the
             # host-side glue of each pass overlaps the conv work of the next (detector.prefetch_trunk)
-            data_s = data_s.to(self.device)
+            data_s = data_s.to(self.device, non_blocking=True)   # pinned host batches: the copy overlaps the host's next work
             self.student.prefetch_trunk("sup", data_s.tensors if hasattr(data_s, "tensors") else data_s)
             if mt_on and data_u_list is not None and self.n_step_unlabel == 1:
-                data_u_list = [d.to(self.device) for d in data_u_list]
+                data_u_list = [d.to(self.device, non_blocking=True) for d in data_u_list]
                 if all(isinstance(d, torch.Tensor) for d in data_u_list):
                     with torch.no_grad():
                         self.teacher.prefetch_trunk("aug", data_u_list[:self.teacher_bs])

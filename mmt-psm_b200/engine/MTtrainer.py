@@ -131,24 +131,33 @@ class MTtrainer(object):
     # ---- one iteration ------------------------------------------------------------------------
     def train_step(self, iteration, data_s, target_s, data_u_list=None):
         mt_on = iteration > self.start_mt and self.lambda_value > 0 and bool(self.cfg.DATASETS.NO_LABEL)
+        stacked = False
         if self.cuda_graphs:
-            # the three conv trunks of the iteration are independent: enqueue them all on the side stream first, so the
-            # host-side glue of each pass overlaps the conv work of the next (detector.prefetch_trunk)
+            # the conv trunks of the iteration are independent: enqueue them all on the side stream first, so the
+            # host-side glue of each pass overlaps the conv work of the next (detector.prefetch_trunk / prefetch_student)
             data_s = data_s.to(self.device, non_blocking=True)   # pinned host batches: the copy overlaps the host's next work
-            self.student.prefetch_trunk("sup", data_s.tensors if hasattr(data_s, "tensors") else data_s)
+            img_s = data_s.tensors if hasattr(data_s, "tensors") else data_s
             if mt_on and data_u_list is not None and self.n_step_unlabel == 1:
                 data_u_list = [d.to(self.device, non_blocking=True) for d in data_u_list]
                 if all(isinstance(d, torch.Tensor) for d in data_u_list):
+                    stacked = self.student.prefetch_student(img_s, data_u_list[-self.student_bs:])
+                    if not stacked:
+                        self.student.prefetch_trunk("sup", img_s)
                     with torch.no_grad():
                         self.teacher.prefetch_trunk("aug", data_u_list[:self.teacher_bs])
-                    self.student.prefetch_trunk("unl", data_u_list[-self.student_bs:])
+                    if not stacked:
+                        self.student.prefetch_trunk("unl", data_u_list[-self.student_bs:])
+            else:
+                self.student.prefetch_trunk("sup", img_s)
         self.scheduler.step()
         self.optimizer.zero_grad()
         loss_dict = self.forward_source(data_s, target_s)
         # The supervised terms carry weight 1 (no 'mt' in their keys, MTtrainer.py:99 of the reference), so their
         # backward does not depend on the consistency ramp: run it NOW — its device work overlaps the teacher pass's
         # host-side glue — and back-propagate the consistency terms after the unlabeled pass.  Gradients of both
-        # passes accumulate in the flat arena: d(sum)/dw = sum of d/dw, the reference's single backward.
+        # passes accumulate in the flat arena: d(sum)/dw = sum of d/dw, the reference's single backward.  With the
+        # stacked student trunk the early backward stops at the trunk boundary (detached leaves) and the backbone's
+        # backward runs once, at the end, with both branches' gradients (detector.backward_deferred).
         sup_weighted = self.weight_sum_loss(loss_dict, iteration)
         sup_total = sum(v for v in sup_weighted.values())
         if mt_on:
@@ -157,12 +166,12 @@ class MTtrainer(object):
             mt_weighted = self.weight_sum_loss(mt_dict, iteration)
             losses_dict = dict(sup_weighted)
             losses_dict.update(mt_weighted)
-            if mt_weighted:
-                mt_total = sum(v for v in mt_weighted.values())
+            mt_total = sum(v for v in mt_weighted.values()) if mt_weighted else None
+            if stacked:
+                self.student.backward_deferred(mt_total)
+            elif mt_total is not None:
                 mt_total.backward()
-                losses = sup_total.detach() + mt_total.detach()
-            else:
-                losses = sup_total.detach()
+            losses = sup_total.detach() + (mt_total.detach() if mt_total is not None else 0)
         else:
             losses_dict, losses = sup_weighted, sup_total
             losses.backward()

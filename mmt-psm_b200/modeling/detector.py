@@ -74,6 +74,7 @@ class GeneralizedRCNN(nn.Module):
         self.hint_adaptor = MaskRCNNFPNAdaptor(cfg)
         self._graphs, self._graphs_on, self._graph_on_backward = {}, False, None
         self._pending, self._side = {}, None
+        self._stu, self._stu_ptrs, self._deferred = None, {}, []
 
     # ------------------------------------------------------------------------------ CUDA graphs
     def enable_cuda_graphs(self, on=True, on_backward=None):
@@ -90,6 +91,18 @@ class GeneralizedRCNN(nn.Module):
         'sup': the RPN head;  'aug' (teacher, n_views stacked views): MGD adaptors on every view and the RPN head on
         view 0;  'unl' (student, unlabeled view): MGD adaptors.  Returns a flat tuple (5 features [+5 emb] [+5 rpn])."""
         want_emb = site != "sup" and bool(self.cfg.MT.FG_HINT or self.cfg.MT.HINT or self.cfg.MT.ODKD)
+
+        if site == "stu":
+            # student, labeled batch and unlabeled view stacked ([2B,...], same weights): ONE backbone pass serves the
+            # supervised and the consistency branch; RPN head on the labeled half, MGD adaptors on the unlabeled half
+            def fn_stu(x):
+                feats = tuple(self.backbone(x))
+                B = x.shape[0] // 2
+                out = feats + tuple(self.rpn.head.forward_fused([f[:B] for f in feats]))
+                if want_emb:
+                    out = out + tuple(self.hint_adaptor([f[B:] for f in feats]))
+                return out
+            return fn_stu, want_emb
 
         def fn(x):
             feats = tuple(self.backbone(x))
@@ -154,10 +167,67 @@ class GeneralizedRCNN(nn.Module):
         g.launch_forward([x], self._side)
         self._pending[site] = (g, first.data_ptr(), tuple(x.shape), x)
 
+    def prefetch_student(self, images, views):
+        """Stacked student trunk: the labeled batch and the (single, AUG_S = 1) unlabeled view go through the backbone
+        as ONE [2B,3,H,W] pass on the side stream.  `forward` then picks up the labeled half — as detached leaves, so
+        that the supervised backward issued right after it stops at the trunk boundary — and `forward_student` the
+        unlabeled half; `backward_deferred` finally runs the trunk's backward ONCE with both halves' gradients."""
+        if not (self._graphs_on and self.training and images.is_cuda and len(views) == 1
+                and tuple(views[0].shape) == tuple(images.shape)):
+            return False
+        x = torch.cat([images, views[0]], 0)
+        g, _ = self._graph_for("stu", x, 1)
+        cur = torch.cuda.current_stream(x.device)
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=x.device)
+        self._side.wait_stream(cur)
+        g.launch_forward([x], self._side)
+        self._pending["stu"] = (g, images.data_ptr(), views[0].data_ptr(), x)
+        self._stu, self._deferred = None, []
+        return True
+
+    def _stu_outputs(self):
+        if self._stu is None:
+            g, _, _, x = self._pending.pop("stu")
+            flat = tuple(g(x, prefetched=True))
+            want_emb = self._trunk_fn("stu")[1]
+            n = len(flat) // (2 + int(want_emb))      # feature levels | fused RPN head maps | [adaptor embeddings]
+            self._stu = (flat[:n], flat[n:2 * n], flat[2 * n:] if want_emb else None, x.shape[0] // 2)
+        return self._stu
+
+    def backward_deferred(self, extra_losses=None):
+        """Trunk backward of the stacked student pass: the supervised branch's gradients (already sitting on the detached
+        leaves) and the consistency losses go through the backbone in one replay."""
+        tensors, grads = [], []
+        if extra_losses is not None:
+            tensors.append(extra_losses)
+            grads.append(None)
+        for attached, leaf in self._deferred:
+            if leaf.grad is not None:
+                tensors.append(attached)
+                grads.append(leaf.grad)
+        self._deferred, self._stu = [], None
+        if tensors:
+            torch.autograd.backward(tensors, grads)
+
     def _trunk(self, site, x, n_views=1, first_ptr=None):
         """Runs (or replays from a CUDA graph / picks up the prefetched replay of) the trunk of call site `site`;
         returns dict(features, emb, rpn).  `x` may be a callable building the input (skipped when prefetched)."""
         fn, want_emb = self._trunk_fn(site, n_views)
+        stu = self._pending.get("stu") if site in ("sup", "unl") else None
+        if (stu is not None or self._stu is not None) and first_ptr is not None and n_views == 1:
+            key_ptr = (self._pending["stu"][1 if site == "sup" else 2]) if stu is not None else self._stu_ptrs[site]
+            if key_ptr == first_ptr:
+                if stu is not None:
+                    self._stu_ptrs = {"sup": stu[1], "unl": stu[2]}
+                feats, rpn, emb, B = self._stu_outputs()
+                if site == "sup":
+                    pairs = [(t, t.detach().requires_grad_(True)) for t in [f[:B] for f in feats] + list(rpn)]
+                    self._deferred += pairs
+                    leaves = [leaf for _, leaf in pairs]
+                    return {"features": tuple(leaves[:len(feats)]), "emb": None, "rpn": tuple(leaves[len(feats):])}
+                out = {"features": tuple(f[B:] for f in feats), "emb": emb, "rpn": None}
+                return out
         pend = self._pending.pop(site, None)
         if pend is not None and first_ptr is not None and pend[1] == first_ptr:
             g, _, shape, keep_alive = pend

@@ -172,7 +172,8 @@ def test_cuda_graph_trunks_match_eager(cuda, restore):
         n1 = lib.launch_count()
         results.append((first, second, p1, t1, start, n1))
         if graphs:
-            assert len(student._graphs) == 2 and len(teacher._graphs) == 1, (student._graphs.keys(), teacher._graphs.keys())
+            # one stacked student trunk (labeled batch + unlabeled view) and one stacked teacher trunk (2K views)
+            assert len(student._graphs) == 1 and len(teacher._graphs) == 1, (student._graphs.keys(), teacher._graphs.keys())
     (f0, s0, p0, t0, start, n0), (f1, s1, p1, t1, _, n1) = results
     for k in f0:   # same weights, same inputs, same random stream: the first iteration's losses coincide
         assert abs(f0[k] - f1[k]) <= 1e-5 * max(abs(f0[k]), 1e-2), (k, f0[k], f1[k])
@@ -183,4 +184,5 @@ def test_cuda_graph_trunks_match_eager(cuda, restore):
     assert err_p <= 2e-3 * upd and err_t <= 2e-3 * upd, (err_p, err_t, upd)
     for k in s0:   # second iteration: discrete sampling decisions may flip on 1e-7 weight differences
         assert abs(s0[k] - s1[k]) <= 2e-2 * max(abs(s0[k]), 1e-2), (k, s0[k], s1[k])
-    assert abs(n0 - n1) <= 0.05 * n0, (n0, n1)   # replayed launches are accounted for (ROI counts may differ slightly)
+    # replayed launches are accounted for; the graphed run stacks the two student trunks into one pass (fewer launches)
+    assert 0.5 * n0 <= n1 <= 1.05 * n0, (n0, n1)

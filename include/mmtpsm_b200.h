@@ -107,6 +107,15 @@ int mmt_encode_boxes_f32(const float* gt_xyxy, const int64_t* matched_idx, const
 int mmt_fpn_rois_f32(const float* boxes_xyxy, const int* image_counts_host, int n_images, float k_min, float k_max,
                      float canonical_scale, float canonical_level, float eps, float* rois_out, int* levels_out,
                      void* stream);
+/* Balanced positive / negative sampling for a batch of images in one launch (reference
+ * modeling/balanced_positive_negative_sampler.py:16-71): labels [total] fp32 (>= 1 positive, 0 negative, anything else
+ * ignored), image i owns rows [image_offsets_dev[i], image_offsets_dev[i+1]) (device int32 array of n_images + 1).
+ * Per image a uniformly random min(#pos, quota_pos) positives and min(#neg, batch_size_per_image - taken positives)
+ * negatives are flagged in pos_mask_out / neg_mask_out (uint8 [total]).  Counter-based random keys from `seed`: the
+ * same distribution as the reference's randperm(...)[:n] draws, a different stream (no host round trip). */
+int mmt_balanced_sample_f32(const float* labels, const int* image_offsets_dev, int n_images, int batch_size_per_image,
+                            int quota_pos, unsigned long long seed, unsigned char* pos_mask_out,
+                            unsigned char* neg_mask_out, void* stream);
 /* Single problem convenience form (exactly `_C.nms(dets, scores, thr)` minus the tensor plumbing). */
 int mmt_nms_f32(const float* boxes_xyxy, const float* scores, int n, float iou_threshold,
                 int64_t* keep_out, int* n_keep_out, void* workspace, size_t workspace_bytes,

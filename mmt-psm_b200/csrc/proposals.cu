@@ -291,3 +291,127 @@ extern "C" int mmt_fpn_rois_f32(const float* boxes_xyxy, const int* image_counts
       rois_out, levels_out);
   return mmt::check_launch("fpn_rois");
 }
+
+// ------------------------------------------------------------------------------------------------------------
+// Balanced positive / negative sampling (reference modeling/balanced_positive_negative_sampler.py:16-71): per image
+// a uniformly random subset of min(#pos, quota_pos) positives (label >= 1) and min(#neg, batch - #pos_taken)
+// negatives (label == 0).  The reference draws torch.randperm(count)[:n] — which needs the counts on the host (a sync
+// per image) and ~30 launches.  Here: every candidate gets a counter-based random 32-bit key (hash of seed, image,
+// index); the n smallest keys of a class are its sample, found by a bitwise threshold search on the key value
+// (32 counting passes over the image's labels, one CTA per image), ties resolved by index.  Same distribution
+// (every subset of the required size is equally likely), no host round trip, one launch for the whole batch.
+namespace {
+
+__device__ __forceinline__ unsigned int hash_key(unsigned long long seed, unsigned int img, unsigned int i) {
+  unsigned long long z = seed + 0x9E3779B97F4A7C15ull * ((unsigned long long)img * 0x100000001B3ull + i + 1ull);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;   // splitmix64 finaliser
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return (unsigned int)((z ^ (z >> 31)) >> 32);
+}
+
+__device__ int block_count(int v, int* s_part) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  v = mmt::warp_sum_int(v);
+  __syncthreads();
+  if (lane == 0) s_part[wid] = v;
+  __syncthreads();
+  int r = (lane < (int)(blockDim.x >> 5)) ? s_part[lane] : 0;
+  r = mmt::warp_sum_int(r);
+  return r;  // valid in every thread of warp 0..; broadcast below
+}
+
+// smallest threshold T such that #{i in class : key_i <= T} >= want  (want >= 1)
+__device__ unsigned int select_threshold(const float* __restrict__ labels, int n, int cls_pos, unsigned long long seed,
+                                         unsigned int img, int want, int* s_part, int* s_bcast) {
+  unsigned int T = 0u;
+  for (int bit = 31; bit >= 0; --bit) {
+    const unsigned int trial = T | ((1u << bit) - 1u);   // all keys <= trial have the decided prefix and this bit 0
+    int c = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const float l = labels[i];
+      const bool in_cls = cls_pos ? (l >= 1.f) : (l == 0.f);
+      if (in_cls && hash_key(seed, img, (unsigned int)i) <= trial) ++c;
+    }
+    c = block_count(c, s_part);
+    if (threadIdx.x == 0) *s_bcast = c;
+    __syncthreads();
+    c = *s_bcast;
+    __syncthreads();
+    if (c < want) T |= (1u << bit);
+  }
+  return T;
+}
+
+__global__ void __launch_bounds__(1024) balanced_sample_kernel(const float* __restrict__ labels,
+                                                               const int* __restrict__ offsets, int batch_per_image,
+                                                               int quota_pos, unsigned long long seed,
+                                                               unsigned char* __restrict__ pos_mask,
+                                                               unsigned char* __restrict__ neg_mask) {
+  __shared__ int s_part[32];
+  __shared__ int s_bcast;
+  const unsigned int img = blockIdx.x;
+  const int base = offsets[img], n = offsets[img + 1] - base;
+  const float* lab = labels + base;
+  // class sizes
+  int cp = 0, cn = 0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float l = lab[i];
+    cp += (l >= 1.f);
+    cn += (l == 0.f);
+  }
+  cp = block_count(cp, s_part);
+  if (threadIdx.x == 0) s_bcast = cp;
+  __syncthreads();
+  cp = s_bcast;
+  __syncthreads();
+  cn = block_count(cn, s_part);
+  if (threadIdx.x == 0) s_bcast = cn;
+  __syncthreads();
+  cn = s_bcast;
+  __syncthreads();
+  const int num_pos = min(cp, quota_pos);
+  const int num_neg = min(cn, batch_per_image - num_pos);
+  const bool all_pos = num_pos == cp, all_neg = num_neg == cn;
+  unsigned int tp = 0xffffffffu, tn = 0xffffffffu;
+  if (!all_pos && num_pos > 0) tp = select_threshold(lab, n, 1, seed, img, num_pos, s_part, &s_bcast);
+  if (!all_neg && num_neg > 0) tn = select_threshold(lab, n, 0, seed, img, num_neg, s_part, &s_bcast);
+  // keys strictly below the threshold are in; the keys equal to it (the threshold element itself, plus ties — a 2^-32
+  // event per pair) are admitted by ticket until the quota is met
+  __shared__ int s_tie_p, s_tie_n;
+  int below_p = 0, below_n = 0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float l = lab[i];
+    const unsigned int k = hash_key(seed, img, (unsigned int)i);
+    below_p += (l >= 1.f) && num_pos > 0 && (all_pos || k < tp);
+    below_n += (l == 0.f) && num_neg > 0 && (all_neg || k < tn);
+  }
+  below_p = block_count(below_p, s_part);
+  __syncthreads();
+  below_n = block_count(below_n, s_part);
+  if (threadIdx.x == 0) { s_tie_p = 0; s_tie_n = 0; }
+  __syncthreads();
+  const int need_p = num_pos - below_p, need_n = num_neg - below_n;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float l = lab[i];
+    const unsigned int k = hash_key(seed, img, (unsigned int)i);
+    bool p = (l >= 1.f) && num_pos > 0 && (all_pos || k < tp);
+    bool q = (l == 0.f) && num_neg > 0 && (all_neg || k < tn);
+    if (!p && (l >= 1.f) && !all_pos && num_pos > 0 && k == tp) p = atomicAdd(&s_tie_p, 1) < need_p;
+    if (!q && (l == 0.f) && !all_neg && num_neg > 0 && k == tn) q = atomicAdd(&s_tie_n, 1) < need_n;
+    pos_mask[base + i] = p;
+    neg_mask[base + i] = q;
+  }
+}
+
+}  // namespace
+
+extern "C" int mmt_balanced_sample_f32(const float* labels, const int* image_offsets_dev, int n_images,
+                                       int batch_size_per_image, int quota_pos, unsigned long long seed,
+                                       unsigned char* pos_mask_out, unsigned char* neg_mask_out, void* stream_) {
+  MMT_REQUIRE(n_images >= 0 && batch_size_per_image >= 0 && quota_pos >= 0, "balanced_sample: negative argument");
+  if (n_images == 0) return MMT_OK;
+  MMT_REQUIRE(labels && image_offsets_dev && pos_mask_out && neg_mask_out, "balanced_sample: null pointer");
+  balanced_sample_kernel<<<n_images, 1024, 0, (cudaStream_t)stream_>>>(labels, image_offsets_dev, batch_size_per_image,
+                                                                       quota_pos, seed, pos_mask_out, neg_mask_out);
+  return mmt::check_launch("balanced_sample");
+}

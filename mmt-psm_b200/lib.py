@@ -45,6 +45,7 @@ _PROTOS = {
     "mmt_match_boxes_f32": (c_int, [P, c_int, P, c_int, c_float, c_float, c_int, P, P, c_size_t, P]),
     "mmt_encode_boxes_f32": (c_int, [P, P, P, c_int64, c_float, c_float, c_float, c_float, P, P]),
     "mmt_fpn_rois_f32": (c_int, [P, POINTER(c_int), c_int, c_float, c_float, c_float, c_float, c_float, P, P, P]),
+    "mmt_balanced_sample_f32": (c_int, [P, P, c_int, c_int, c_int, ctypes.c_uint64, P, P, P]),
     "mmt_roi_align_forward_f32": (c_int, [P, Strides4, c_int, c_int, c_int, c_int, P, c_int, c_float,
                                           c_int, c_int, c_int, P, Strides4, P]),
     "mmt_roi_align_backward_f32": (c_int, [P, Strides4, P, c_int, c_float, c_int, c_int, c_int, P,

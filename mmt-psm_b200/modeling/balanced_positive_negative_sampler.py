@@ -11,11 +11,37 @@ class BalancedPositiveNegativeSampler(object):
         self.batch_size_per_image = batch_size_per_image
         self.positive_fraction = positive_fraction
 
-    def _sample_on_device(self, m):
-        """Uniformly random min(#pos, quota) positives and min(#neg, batch - #pos_taken) negatives, the distribution of
-        the reference's randperm(...)[:n] draws (balanced_positive_negative_sampler.py:41-54), computed without
-        learning the counts on the host: random keys, the `quota` smallest per class, a device-side count for the
-        negative quota."""
+    _calls = 0          # stream position of the device-side sampler (with torch.initial_seed() = its seed)
+    _offset_cache = {}
+
+    def _sample_on_device(self, matched_idxs):
+        """One launch for the whole batch (libmmtpsm_b200 `mmt_balanced_sample_f32`): per image a uniformly random
+        min(#pos, quota) positives and min(#neg, batch - #pos_taken) negatives — the distribution of the reference's
+        randperm(...)[:n] draws (balanced_positive_negative_sampler.py:41-54) without learning the counts on the host.
+        Counter-based keys: reproducible under torch.manual_seed, a different stream than torch.randperm."""
+        from .. import kernels as K
+        sizes = tuple(int(m.numel()) for m in matched_idxs)
+        dev = matched_idxs[0].device
+        key = (sizes, str(dev))
+        offs = self._offset_cache.get(key)
+        if offs is None:
+            if len(self._offset_cache) > 32:
+                self._offset_cache.clear()
+            acc = [0]
+            for n in sizes:
+                acc.append(acc[-1] + n)
+            offs = torch.tensor(acc, dtype=torch.int32, device=dev)
+            BalancedPositiveNegativeSampler._offset_cache[key] = offs
+        labels = matched_idxs[0] if len(matched_idxs) == 1 else torch.cat(list(matched_idxs))
+        BalancedPositiveNegativeSampler._calls += 1
+        seed = (torch.initial_seed() * 0x9E3779B1 + BalancedPositiveNegativeSampler._calls * 0x85EBCA77) & 0xFFFFFFFFFFFFFFFF
+        pos, neg = K.balanced_sample(labels.to(torch.float32), offs, len(sizes), self.batch_size_per_image,
+                                     int(self.batch_size_per_image * self.positive_fraction), seed)
+        return list(pos.split(sizes)), list(neg.split(sizes))
+
+    def _sample_topk(self, m):
+        """Same draw with torch ops (random keys, the quota smallest per class via top-k, device-side negative quota):
+        used for the RPN's ~160 K anchors per image, where a full-GPU top-k beats the one-CTA-per-image kernel."""
         n = m.numel()
         quota_pos = int(self.batch_size_per_image * self.positive_fraction)
         pos, neg = m >= 1, m == 0
@@ -35,8 +61,10 @@ class BalancedPositiveNegativeSampler(object):
     def __call__(self, matched_idxs):
         pos_idx, neg_idx = [], []
         if self.rng_device is None and matched_idxs and matched_idxs[0].is_cuda:
+            if max(int(m.numel()) for m in matched_idxs) <= 16384:
+                return self._sample_on_device(matched_idxs)
             for m in matched_idxs:
-                p, q = self._sample_on_device(m)
+                p, q = self._sample_topk(m)
                 pos_idx.append(p)
                 neg_idx.append(q)
             return pos_idx, neg_idx

@@ -277,6 +277,51 @@ def test_elementwise_vs_torch(cuda):
     assert torch.equal(K().nhwc_to_nchw(K().nchw_to_nhwc(a)), a)
 
 
+# ------------------------------------------------------------------------- balanced sampler
+def test_balanced_sample_counts_and_uniformity(cuda):
+    """mmt_balanced_sample_f32: exact class sizes per image (min(#pos, quota), min(#neg, batch - taken)), only
+    eligible rows selected, ignore rows never; and the draw is uniform: over many seeds every positive of an
+    over-full image is picked with frequency quota / #pos (4-sigma band)."""
+    kn = K()
+    gen = torch.Generator().manual_seed(9)
+    sizes = [5000, 37, 160000]
+    labs = []
+    labs.append(torch.where(torch.rand(5000, generator=gen) < 0.1, 1.0, 0.0))            # 500 pos > quota 128
+    labs.append(torch.tensor([1.0] * 5 + [0.0] * 20 + [-1.0] * 12))                      # fewer than either quota
+    big = torch.zeros(160000)
+    big[torch.randperm(160000, generator=gen)[:60]] = 2.0                                 # 60 pos (< quota), label 2
+    big[torch.randperm(160000, generator=gen)[:5000]] = -1.0
+    labs.append(big)
+    labels = torch.cat(labs).to(cuda)
+    offs = torch.tensor([0, 5000, 5037, 165037], dtype=torch.int32, device=cuda)
+    pos, neg = kn.balanced_sample(labels, offs, 3, 512, 128, seed=1234)
+    pos, neg = pos.cpu(), neg.cpu()
+    lab = labels.cpu()
+    assert not (pos & (lab < 1)).any() and not (neg & (lab != 0)).any()
+    a = 0
+    for n, l in zip(sizes, labs):
+        p, q = pos[a:a + n], neg[a:a + n]
+        want_p = min(int((l >= 1).sum()), 128)
+        want_n = min(int((l == 0).sum()), 512 - want_p)
+        assert int(p.sum()) == want_p and int(q.sum()) == want_n, (n, int(p.sum()), want_p, int(q.sum()), want_n)
+        a += n
+    # different seeds give different draws; the same seed the same draw
+    pos2, _ = kn.balanced_sample(labels, offs, 3, 512, 128, seed=1234)
+    pos3, _ = kn.balanced_sample(labels, offs, 3, 512, 128, seed=99)
+    assert torch.equal(pos2.cpu(), pos) and not torch.equal(pos3.cpu(), pos)
+    # uniformity on image 0: 500 positives, 128 drawn, 400 seeds -> each picked ~ Binomial(400, 0.256)
+    hits = torch.zeros(5000)
+    l0 = labs[0].to(cuda)
+    o0 = torch.tensor([0, 5000], dtype=torch.int32, device=cuda)
+    for s in range(400):
+        p, _ = kn.balanced_sample(l0, o0, 1, 512, 128, seed=1000 + s)
+        hits += p.cpu().float()
+    f = hits[labs[0] >= 1] / 400.0
+    exp = 128.0 / float((labs[0] >= 1).sum())
+    sigma = (exp * (1 - exp) / 400.0) ** 0.5
+    assert abs(float(f.mean()) - exp) < 1e-6 and float((f - exp).abs().max()) < 4.5 * sigma, (float(f.min()), float(f.max()), exp, sigma)
+
+
 # --------------------------------------------------------------------- encode / FPN ROI table
 def test_encode_boxes_and_fpn_rois_golden(cuda):
     kn = K()

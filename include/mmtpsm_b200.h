@@ -116,6 +116,20 @@ int mmt_fpn_rois_f32(const float* boxes_xyxy, const int* image_counts_host, int 
 int mmt_balanced_sample_f32(const float* labels, const int* image_offsets_dev, int n_images, int batch_size_per_image,
                             int quota_pos, unsigned long long seed, unsigned char* pos_mask_out,
                             unsigned char* neg_mask_out, void* stream);
+/* Same, additionally writing keep_flags_out [total] uint8: 1 for every kept row (original row order), 0 otherwise —
+ * what a caller needs to select survivors with masks instead of index lists (no count read-back). */
+int mmt_nms_segmented_flags_f32(const float* boxes_xyxy, const float* scores, const int* seg_offsets_host,
+                                int n_segments, float iou_threshold, int64_t* keep_out, int* n_keep_out,
+                                unsigned char* keep_flags_out, void* workspace, size_t workspace_bytes, void* stream);
+/* RPN candidate gather for one pyramid level (reference modeling/rpn/inference.py:86-105): given the top-k anchor
+ * indices topk_idx [n_images, k] (index = pixel * num_anchors + anchor) and their scores, fetch the deltas from the
+ * fused head map fused_nhwc [n_images, pixels, padded_channels] (channels [A, 5A) = deltas of anchor 0..A-1), the
+ * anchors from level_anchors [pixels * A, 4], and write deltas / anchors / scores at columns [col_offset, col_offset + k)
+ * of the [n_images, k_total, ...] candidate tables. */
+int mmt_rpn_gather_f32(const float* fused_nhwc, int padded_channels, int num_anchors, int64_t pixels,
+                       const int64_t* topk_idx, const float* topk_vals, const float* level_anchors, int n_images,
+                       int k, int k_total, int col_offset, float* deltas_out, float* anchors_out, float* scores_out,
+                       void* stream);
 /* Single problem convenience form (exactly `_C.nms(dets, scores, thr)` minus the tensor plumbing). */
 int mmt_nms_f32(const float* boxes_xyxy, const float* scores, int n, float iou_threshold,
                 int64_t* keep_out, int* n_keep_out, void* workspace, size_t workspace_bytes,

@@ -216,9 +216,9 @@ extern "C" size_t mmt_nms_workspace_bytes(int total_boxes, int n_segments, int m
          mmt::align_up((size_t)total_boxes, 256) + mmt::align_up(words * 8, 256) + 256;
 }
 
-extern "C" int mmt_nms_segmented_f32(const float* boxes, const float* scores, const int* seg_off,
-                                     int n_segments, float thr, int64_t* keep_out, int* n_keep_out,
-                                     void* workspace, size_t workspace_bytes, void* stream_) {
+static int nms_segmented_impl(const float* boxes, const float* scores, const int* seg_off, int n_segments, float thr,
+                              int64_t* keep_out, int* n_keep_out, unsigned char* flags_ext, void* workspace,
+                              size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   MMT_REQUIRE(n_segments >= 0 && seg_off != nullptr, "nms: bad segment table");
   if (n_segments == 0) return MMT_OK;
@@ -254,7 +254,7 @@ extern "C" int mmt_nms_segmented_f32(const float* boxes, const float* scores, co
   p += mmt::align_up((size_t)total * sizeof(int), 256);
   ws.sorted = (float4*)p;
   p += mmt::align_up((size_t)total * sizeof(float4), 256);
-  ws.flags = (unsigned char*)p;
+  ws.flags = flags_ext ? flags_ext : (unsigned char*)p;   // per-row keep flags, original row order
   p += mmt::align_up((size_t)total, 256);
   ws.mask = (unsigned long long*)p;
 
@@ -291,6 +291,22 @@ extern "C" int mmt_nms_segmented_f32(const float* boxes, const float* scores, co
     if (int rc = mmt::check_launch("nms greedy_scan")) return rc;
   }
   return MMT_OK;
+}
+
+extern "C" int mmt_nms_segmented_f32(const float* boxes, const float* scores, const int* seg_off,
+                                     int n_segments, float thr, int64_t* keep_out, int* n_keep_out,
+                                     void* workspace, size_t workspace_bytes, void* stream_) {
+  return nms_segmented_impl(boxes, scores, seg_off, n_segments, thr, keep_out, n_keep_out, nullptr, workspace,
+                            workspace_bytes, stream_);
+}
+
+extern "C" int mmt_nms_segmented_flags_f32(const float* boxes, const float* scores, const int* seg_off,
+                                           int n_segments, float thr, int64_t* keep_out, int* n_keep_out,
+                                           unsigned char* keep_flags_out, void* workspace, size_t workspace_bytes,
+                                           void* stream_) {
+  MMT_REQUIRE(keep_flags_out != nullptr, "nms: keep_flags_out is null");
+  return nms_segmented_impl(boxes, scores, seg_off, n_segments, thr, keep_out, n_keep_out, keep_flags_out, workspace,
+                            workspace_bytes, stream_);
 }
 
 extern "C" int mmt_nms_f32(const float* boxes, const float* scores, int n, float thr,

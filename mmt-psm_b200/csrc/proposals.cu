@@ -415,3 +415,49 @@ extern "C" int mmt_balanced_sample_f32(const float* labels, const int* image_off
                                                                        quota_pos, seed, pos_mask_out, neg_mask_out);
   return mmt::check_launch("balanced_sample");
 }
+
+// ------------------------------------------------------------------------------------------------------------
+// RPN candidate gather: for the top-k anchor indices of one pyramid level, fetch the box deltas straight from the
+// fused head map [N, HW, Cp] (channels [A, 5A) hold the 4A deltas), the anchor boxes and the (sorted) scores, and
+// write them into the pass-wide candidate tables at this level's column offset.  Replaces, per level, the reference's
+// permute/reshape copy of the delta map, two advanced-index gathers and three concatenations
+// (modeling/rpn/inference.py:86-105).
+namespace {
+__global__ void __launch_bounds__(256) rpn_gather_kernel(const float* __restrict__ fused, int Cp, int A, long long HW,
+                                                         const long long* __restrict__ idx,
+                                                         const float* __restrict__ vals,
+                                                         const float4* __restrict__ anchors, int N, int k,
+                                                         int K_total, int col_off, float4* __restrict__ deltas,
+                                                         float4* __restrict__ anch, float* __restrict__ scores) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= N * k) return;
+  const int n = t / k, j = t - n * k;
+  const long long i = idx[t];
+  const long long pix = i / A;
+  const int a = (int)(i - pix * A);
+  const float* src = fused + ((long long)n * HW + pix) * Cp + A + 4 * a;
+  const long long o = (long long)n * K_total + col_off + j;
+  deltas[o] = make_float4(__ldg(src), __ldg(src + 1), __ldg(src + 2), __ldg(src + 3));
+  anch[o] = __ldg(anchors + i);
+  scores[o] = vals[t];
+}
+}  // namespace
+
+extern "C" int mmt_rpn_gather_f32(const float* fused_nhwc, int padded_channels, int num_anchors, int64_t pixels,
+                                  const int64_t* topk_idx, const float* topk_vals, const float* level_anchors,
+                                  int n_images, int k, int k_total, int col_offset, float* deltas_out,
+                                  float* anchors_out, float* scores_out, void* stream_) {
+  MMT_REQUIRE(n_images >= 0 && k >= 0 && col_offset >= 0 && col_offset + k <= k_total, "rpn_gather: bad sizes");
+  if (n_images == 0 || k == 0) return MMT_OK;
+  MMT_REQUIRE(fused_nhwc && topk_idx && topk_vals && level_anchors && deltas_out && anchors_out && scores_out,
+              "rpn_gather: null pointer");
+  MMT_REQUIRE(padded_channels >= 5 * num_anchors && num_anchors > 0, "rpn_gather: head map narrower than 5 x anchors");
+  MMT_REQUIRE((((uintptr_t)level_anchors | (uintptr_t)deltas_out | (uintptr_t)anchors_out) & 15) == 0,
+              "rpn_gather: box arrays must be 16-byte aligned");
+  const int total = n_images * k;
+  rpn_gather_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream_>>>(
+      fused_nhwc, padded_channels, num_anchors, pixels, (const long long*)topk_idx, topk_vals,
+      reinterpret_cast<const float4*>(level_anchors), n_images, k, k_total, col_offset,
+      reinterpret_cast<float4*>(deltas_out), reinterpret_cast<float4*>(anchors_out), scores_out);
+  return mmt::check_launch("rpn_gather");
+}

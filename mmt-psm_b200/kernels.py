@@ -93,6 +93,39 @@ def nms_segmented(boxes, scores, seg_offsets, iou_threshold):
     return keep[:total], counts[:S]
 
 
+def nms_segmented_flags(boxes, scores, seg_offsets, iou_threshold):
+    """As nms_segmented, returning only the per-row keep flags (bool [T], original row order): survivors are selected
+    with masks, nothing is read back."""
+    _need_cuda(boxes, scores)
+    L = _l.lib()
+    boxes, scores = _f32c(boxes), _f32c(scores)
+    S = len(seg_offsets) - 1
+    total = int(seg_offsets[-1])
+    flags = torch.empty(total, dtype=torch.bool, device=boxes.device)
+    if S == 0 or total == 0:
+        return flags
+    keep = torch.empty(total, dtype=torch.int64, device=boxes.device)
+    counts = torch.empty(S, dtype=torch.int32, device=boxes.device)
+    max_n = max(seg_offsets[i + 1] - seg_offsets[i] for i in range(S))
+    ws_bytes = L.mmt_nms_workspace_bytes(total, S, max_n)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=boxes.device)
+    offs = seg_offsets if isinstance(seg_offsets, ctypes.Array) else (c_int * (S + 1))(*[int(o) for o in seg_offsets])
+    check(L.mmt_nms_segmented_flags_f32(_p(boxes), _p(scores), offs, S, float(iou_threshold), _p(keep), _p(counts),
+                                        _p(flags), _p(ws), ws_bytes, _stream()), "nms_flags")
+    return flags
+
+
+def rpn_gather(fused, num_anchors, topk_idx, topk_vals, level_anchors, deltas_out, anchors_out, scores_out, col_offset):
+    """Candidates of one pyramid level into the pass-wide tables (see mmt_rpn_gather_f32)."""
+    L = _l.lib()
+    N, k = topk_idx.shape
+    assert fused.is_contiguous() and topk_idx.is_contiguous() and topk_vals.is_contiguous()
+    pixels = fused.shape[1] * fused.shape[2]
+    check(L.mmt_rpn_gather_f32(_p(fused), fused.shape[3], num_anchors, pixels, _p(topk_idx), _p(topk_vals),
+                               _p(level_anchors), N, k, deltas_out.shape[1], col_offset, _p(deltas_out), _p(anchors_out),
+                               _p(scores_out), _stream()), "rpn_gather")
+
+
 def nms(dets, scores, iou_threshold):
     """`_C.nms(dets, scores, thr)` (reference csrc/nms.h:10-28): int64 kept indices, ascending.
     Empty input returns an empty int64 CPU tensor exactly like the reference (nms.h:17-18)."""

@@ -38,6 +38,8 @@ _PROTOS = {
                                  POINTER(c_int64), c_int]),
     "mmt_nms_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "mmt_nms_segmented_f32": (c_int, [P, P, POINTER(c_int), c_int, c_float, P, P, P, c_size_t, P]),
+    "mmt_nms_segmented_flags_f32": (c_int, [P, P, POINTER(c_int), c_int, c_float, P, P, P, P, c_size_t, P]),
+    "mmt_rpn_gather_f32": (c_int, [P, c_int, c_int, c_int64, P, P, P, c_int, c_int, c_int, c_int, P, P, P, P]),
     "mmt_nms_f32": (c_int, [P, P, c_int, c_float, P, P, P, c_size_t, P]),
     "mmt_decode_clip_boxes_f32": (c_int, [P, P, P, P, c_int, c_int, c_float, c_float, c_float, c_float, c_float,
                                           c_float, P, P, P, P]),

@@ -98,7 +98,8 @@ class GeneralizedRCNN(nn.Module):
             def fn_stu(x):
                 feats = tuple(self.backbone(x))
                 B = x.shape[0] // 2
-                out = feats + tuple(self.rpn.head.forward_fused([f[:B] for f in feats]))
+                fused = self.rpn.head.forward_fused([f[:B] for f in feats])
+                out = feats + tuple(fused) + tuple(self.rpn.head.proposal_scores(fused))
                 if want_emb:
                     out = out + tuple(self.hint_adaptor([f[B:] for f in feats]))
                 return out
@@ -111,7 +112,8 @@ class GeneralizedRCNN(nn.Module):
                 out = out + tuple(self.hint_adaptor(feats))
             if site != "unl":
                 B = x.shape[0] // n_views
-                out = out + tuple(self.rpn.head.forward_fused([f[:B] for f in feats] if n_views > 1 else list(feats)))
+                fused = self.rpn.head.forward_fused([f[:B] for f in feats] if n_views > 1 else list(feats))
+                out = out + tuple(fused) + tuple(self.rpn.head.proposal_scores(fused))
             return out
         return fn, want_emb
 
@@ -191,8 +193,8 @@ class GeneralizedRCNN(nn.Module):
             g, _, _, x = self._pending.pop("stu")
             flat = tuple(g(x, prefetched=True))
             want_emb = self._trunk_fn("stu")[1]
-            n = len(flat) // (2 + int(want_emb))      # feature levels | fused RPN head maps | [adaptor embeddings]
-            self._stu = (flat[:n], flat[n:2 * n], flat[2 * n:] if want_emb else None, x.shape[0] // 2)
+            n = len(flat) // (3 + int(want_emb))      # feature levels | fused RPN maps | proposal scores | [embeddings]
+            self._stu = (flat[:n], (flat[n:2 * n], flat[2 * n:3 * n]), flat[3 * n:] if want_emb else None, x.shape[0] // 2)
         return self._stu
 
     def backward_deferred(self, extra_losses=None):
@@ -222,10 +224,12 @@ class GeneralizedRCNN(nn.Module):
                     self._stu_ptrs = {"sup": stu[1], "unl": stu[2]}
                 feats, rpn, emb, B = self._stu_outputs()
                 if site == "sup":
-                    pairs = [(t, t.detach().requires_grad_(True)) for t in [f[:B] for f in feats] + list(rpn)]
+                    fused, scores = rpn
+                    pairs = [(t, t.detach().requires_grad_(True)) for t in [f[:B] for f in feats] + list(fused)]
                     self._deferred += pairs
                     leaves = [leaf for _, leaf in pairs]
-                    return {"features": tuple(leaves[:len(feats)]), "emb": None, "rpn": tuple(leaves[len(feats):])}
+                    return {"features": tuple(leaves[:len(feats)]), "emb": None,
+                            "rpn": (tuple(leaves[len(feats):]), tuple(scores))}
                 out = {"features": tuple(f[B:] for f in feats), "emb": emb, "rpn": None}
                 return out
         pend = self._pending.pop(site, None)
@@ -239,13 +243,13 @@ class GeneralizedRCNN(nn.Module):
             else:
                 g, _ = self._graph_for(site, x, n_views)
                 flat = tuple(g(x))
-        n = len(flat) // (1 + int(want_emb) + int(site != "unl"))
+        n = len(flat) // (1 + int(want_emb) + 2 * int(site != "unl"))
         out = {"features": flat[:n], "emb": None, "rpn": None}
         rest = flat[n:]
         if want_emb:
             out["emb"], rest = rest[:n], rest[n:]
         if site != "unl":
-            out["rpn"] = rest[:n]
+            out["rpn"] = (rest[:n], rest[n:2 * n])     # (fused head maps, proposal scores)
         return out
 
     def set_module_mode(self, mode):

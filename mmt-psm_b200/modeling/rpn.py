@@ -48,6 +48,13 @@ class RPNHead(nn.Module):
         from .. import functional as Fk
         return [Fk.conv_bn_act(self.conv(feat, relu=True), w, None, b, None, False, 1, 0) for feat in x]
 
+    @torch.no_grad()
+    def proposal_scores(self, fused):
+        """sigmoid(objectness) of every anchor as dense [B, h*w*A] rows (h, w, anchor order) — what the proposal
+        selection ranks (reference rpn/inference.py:88-92); no gradient flows through proposals."""
+        A = self.num_anchors
+        return [torch.sigmoid(o[..., :A]).reshape(o.shape[0], -1) for o in fused]
+
     def split(self, fused):
         A = self.num_anchors
         return [o[..., :A] for o in fused], [o[..., A:5 * A] for o in fused]
@@ -76,6 +83,15 @@ class RPNPostProcessor(nn.Module):
             out.append(cat_boxlist((p, gt)))
         return out
 
+    def _c_offsets(self, offs):
+        import ctypes
+        cache = self.__dict__.setdefault("_c_off_cache", {})
+        if offs not in cache:
+            if len(cache) > 16:
+                cache.clear()
+            cache[offs] = (ctypes.c_int * len(offs))(*offs)
+        return cache[offs]
+
     def _segments(self, N, sizes, image_shapes, device):
         """Static description of the (image, level) NMS problems of a pass, cached per shape: host offsets plus, per
         candidate row, its segment id / segment start / position inside the segment (device int64)."""
@@ -98,38 +114,41 @@ class RPNPostProcessor(nn.Module):
         return cache[key]
 
     @torch.no_grad()
-    def forward(self, anchors, objectness, box_regression, targets=None):
+    def forward(self, anchors, objectness, box_regression, targets=None, head_out=None):
         """Reference rpn/inference.py:78-137 (per level and image: sigmoid, top-k, decode, clip, small-box filter, NMS,
         keep post_nms_top_n) + :216-244 (selection over levels), restructured so that every (image, level) problem of
-        the pass goes through the SAME few launches: per-level top-k, one fused decode/clip/filter kernel, one segmented
-        NMS, one compaction.  Two host read-backs per pass (sizes of the kept set), none per level or image."""
+        the pass goes through the SAME few launches: per level one top-k and one gather kernel (deltas from the fused
+        head map, anchors, scores -> pass-wide candidate tables), then one fused decode/clip/filter kernel, one
+        segmented NMS that returns per-row keep flags, one selection.  One or two host read-backs per pass."""
         num_levels = len(objectness)
         N = objectness[0].shape[0]
         device = objectness[0].device
         image_shapes = tuple(tuple(a[0].size) for a in anchors)
-        sc, dl, an, sizes = [], [], [], []
-        for l, (o, b) in enumerate(zip(objectness, box_regression)):
-            obj = o.reshape(N, -1).sigmoid()
-            k = min(self.pre_nms_top_n, obj.shape[1])
-            s, idx = obj.topk(k, dim=1, sorted=True)
-            sc.append(s)
-            dl.append(b.reshape(N, -1, 4).gather(1, idx[..., None].expand(-1, -1, 4)))
-            an.append(anchors[0][l].bbox[idx])  # one anchor grid for the whole (padded) batch
-            sizes.append(k)
+        if head_out is None:   # called with bare maps: rebuild the fused view of the head output
+            A_ = objectness[0].shape[-1]
+            fused = [torch.cat([o, b], -1).contiguous() for o, b in zip(objectness, box_regression)]
+            scores_l = [o.reshape(N, -1).sigmoid() for o in objectness]
+        else:
+            fused, scores_l = head_out
+            A_ = objectness[0].shape[-1]
+        sizes = [min(self.pre_nms_top_n, s.shape[1]) for s in scores_l]
         K_ = sum(sizes)
         T = N * K_
         offs, seg_id, seg_start, pos, image_wh = self._segments(N, tuple(sizes), image_shapes, device)
-        flat_scores = torch.cat(sc, 1).reshape(-1)            # image-major: row = j * K_ + (level offset + rank)
-        boxes, scores_nms, valid = K.decode_clip_boxes(
-            torch.cat(dl, 1).reshape(-1, 4), torch.cat(an, 1).reshape(-1, 4), self.box_coder.weights,
-            self.box_coder.bbox_xform_clip, image_wh, K_, flat_scores, self.min_size)
+        deltas = torch.empty((N, K_, 4), dtype=torch.float32, device=device)
+        anch = torch.empty((N, K_, 4), dtype=torch.float32, device=device)
+        cand_scores = torch.empty((N, K_), dtype=torch.float32, device=device)
+        col = 0
+        for l, (s_l, k) in enumerate(zip(scores_l, sizes)):
+            vals, idx = s_l.topk(k, dim=1, sorted=True)
+            K.rpn_gather(fused[l], A_, idx, vals, anchors[0][l].bbox, deltas, anch, cand_scores, col)
+            col += k
+        flat_scores = cand_scores.reshape(-1)                 # image-major: row = j * K_ + (level offset + rank)
+        boxes, scores_nms, valid = K.decode_clip_boxes(deltas.reshape(-1, 4), anch.reshape(-1, 4), self.box_coder.weights,
+                                                       self.box_coder.bbox_xform_clip, image_wh, K_, flat_scores,
+                                                       self.min_size)
         # filtered (too small) boxes carry score -1: they sort behind, and so can never suppress, a valid box
-        keep, counts = K.nms_segmented(boxes, scores_nms, offs, self.nms_thresh)
-        # kept flags per candidate row, on the device: entry p of segment s is live iff p < counts[s]
-        live = pos < counts.to(torch.int64)[seg_id]
-        flags = torch.zeros(T + 1, dtype=torch.bool, device=device)
-        flags.index_fill_(0, torch.where(live, keep + seg_start, torch.full_like(keep, T)), True)
-        flags = flags[:T]
+        flags = K.nms_segmented_flags(boxes, scores_nms, self._c_offsets(tuple(offs)), self.nms_thresh)
         if valid is not None:
             flags &= valid
         if self.post_nms_top_n > 0 and max(sizes) > self.post_nms_top_n:   # keep[:post_nms_top_n] per (image, level)
@@ -306,8 +325,12 @@ class RPNModule(nn.Module):
         if isinstance(features, list):
             raise NotImplementedError("multi-view RPN averaging is dead code on this path (SURVEY §2.3): the RPN is "
                                       "always handed ONE feature tuple")
-        # `head_out`: the fused head maps already computed with the trunk (same launches, inside its CUDA graph)
-        objectness, reg = self.head(features) if head_out is None else self.head.split(head_out)
+        # `head_out`: (fused head maps, proposal scores) already computed with the trunk (inside its CUDA graph)
+        if head_out is None:
+            fused = self.head.forward_fused(features)
+            head_out = (fused, self.head.proposal_scores(fused))
+        self._head_out = head_out
+        objectness, reg = self.head.split(head_out[0])
         anchors = self.anchor_generator(images, [f.shape[1:3] for f in features])
         return objectness, reg, anchors
 
@@ -322,7 +345,7 @@ class RPNModule(nn.Module):
         with torch.no_grad():
             if self.cfg.MT.FFI:
                 raise NotImplementedError("MT.FFI (comparison method) is out of scope")
-            boxes = self.box_selector_train(anchors, objectness, reg, targets)
+            boxes = self.box_selector_train(anchors, objectness, reg, targets, head_out=self._head_out)
             obj, box_reg, sample_idx, label = self.loss_evaluator.teacher_sample_selection(
                 anchors, objectness, reg, targets)
         return obj, box_reg, sample_idx, label, boxes, {}, None
@@ -332,12 +355,12 @@ class RPNModule(nn.Module):
             boxes = anchors
         else:
             with torch.no_grad():
-                boxes = self.box_selector_train(anchors, objectness, reg, targets)
+                boxes = self.box_selector_train(anchors, objectness, reg, targets, head_out=self._head_out)
         loss_objectness, loss_rpn_box_reg = self.loss_evaluator(anchors, objectness, reg, targets)
         return boxes, {"loss_objectness": loss_objectness, "loss_rpn_box_reg": loss_rpn_box_reg}
 
     def _forward_test(self, anchors, objectness, reg):
-        boxes = self.box_selector_test(anchors, objectness, reg)
+        boxes = self.box_selector_test(anchors, objectness, reg, head_out=self._head_out)
         if self.cfg.MODEL.RPN_ONLY:
             inds = [b.get_field("objectness").sort(descending=True)[1] for b in boxes]
             boxes = [b[i] for b, i in zip(boxes, inds)]

@@ -320,22 +320,53 @@ __device__ int block_count(int v, int* s_part) {
   return r;  // valid in every thread of warp 0..; broadcast below
 }
 
-// smallest threshold T such that #{i in class : key_i <= T} >= want  (want >= 1)
+constexpr int kSampleCap = 8192;   // candidate keys held in shared memory during the threshold search
+
+// smallest threshold T such that #{i in class : key_i <= T} >= want  (1 <= want < class size).
+// The class can be ~150 K anchors while want <= 512: one pass first collects the keys below a prefilter threshold
+// chosen to catch ~4 x want of them (uniform keys) into shared memory, and the 32-step bitwise search runs over that
+// list; only if the prefilter caught too few / too many (probability ~0) does the search stream the whole image.
 __device__ unsigned int select_threshold(const float* __restrict__ labels, int n, int cls_pos, unsigned long long seed,
-                                         unsigned int img, int want, int* s_part, int* s_bcast) {
+                                         unsigned int img, int want, int cls_size, int* s_part, int* s_bcast,
+                                         unsigned int* s_keys) {
+  const unsigned long long target = (unsigned long long)want * 4ull + 64ull;
+  const bool prefilter = target < (unsigned long long)cls_size;
+  unsigned int T0 = 0xffffffffu;
+  int m = 0;
+  if (prefilter) {
+    T0 = (unsigned int)((target << 32) / (unsigned long long)cls_size);
+    if (threadIdx.x == 0) *s_bcast = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const float l = labels[i];
+      const bool in_cls = cls_pos ? (l >= 1.f) : (l == 0.f);
+      if (in_cls) {
+        const unsigned int k = hash_key(seed, img, (unsigned int)i);
+        if (k <= T0) {
+          const int slot = atomicAdd(s_bcast, 1);
+          if (slot < kSampleCap) s_keys[slot] = k;
+        }
+      }
+    }
+    __syncthreads();
+    m = *s_bcast;
+    __syncthreads();
+  }
+  const bool use_list = prefilter && m >= want && m <= kSampleCap;
   unsigned int T = 0u;
   for (int bit = 31; bit >= 0; --bit) {
     const unsigned int trial = T | ((1u << bit) - 1u);   // all keys <= trial have the decided prefix and this bit 0
     int c = 0;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-      const float l = labels[i];
-      const bool in_cls = cls_pos ? (l >= 1.f) : (l == 0.f);
-      if (in_cls && hash_key(seed, img, (unsigned int)i) <= trial) ++c;
+    if (use_list) {
+      for (int i = threadIdx.x; i < m; i += blockDim.x) c += (s_keys[i] <= trial);
+    } else {
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const float l = labels[i];
+        const bool in_cls = cls_pos ? (l >= 1.f) : (l == 0.f);
+        if (in_cls && hash_key(seed, img, (unsigned int)i) <= trial) ++c;
+      }
     }
     c = block_count(c, s_part);
-    if (threadIdx.x == 0) *s_bcast = c;
-    __syncthreads();
-    c = *s_bcast;
     __syncthreads();
     if (c < want) T |= (1u << bit);
   }
@@ -349,6 +380,7 @@ __global__ void __launch_bounds__(1024) balanced_sample_kernel(const float* __re
                                                                unsigned char* __restrict__ neg_mask) {
   __shared__ int s_part[32];
   __shared__ int s_bcast;
+  __shared__ unsigned int s_keys[kSampleCap];
   const unsigned int img = blockIdx.x;
   const int base = offsets[img], n = offsets[img + 1] - base;
   const float* lab = labels + base;
@@ -373,8 +405,8 @@ __global__ void __launch_bounds__(1024) balanced_sample_kernel(const float* __re
   const int num_neg = min(cn, batch_per_image - num_pos);
   const bool all_pos = num_pos == cp, all_neg = num_neg == cn;
   unsigned int tp = 0xffffffffu, tn = 0xffffffffu;
-  if (!all_pos && num_pos > 0) tp = select_threshold(lab, n, 1, seed, img, num_pos, s_part, &s_bcast);
-  if (!all_neg && num_neg > 0) tn = select_threshold(lab, n, 0, seed, img, num_neg, s_part, &s_bcast);
+  if (!all_pos && num_pos > 0) tp = select_threshold(lab, n, 1, seed, img, num_pos, cp, s_part, &s_bcast, s_keys);
+  if (!all_neg && num_neg > 0) tn = select_threshold(lab, n, 0, seed, img, num_neg, cn, s_part, &s_bcast, s_keys);
   // keys strictly below the threshold are in; the keys equal to it (the threshold element itself, plus ties — a 2^-32
   // event per pair) are admitted by ticket until the quota is met
   __shared__ int s_tie_p, s_tie_n;

@@ -39,35 +39,10 @@ class BalancedPositiveNegativeSampler(object):
                                      int(self.batch_size_per_image * self.positive_fraction), seed)
         return list(pos.split(sizes)), list(neg.split(sizes))
 
-    def _sample_topk(self, m):
-        """Same draw with torch ops (random keys, the quota smallest per class via top-k, device-side negative quota):
-        used for the RPN's ~160 K anchors per image, where a full-GPU top-k beats the one-CTA-per-image kernel."""
-        n = m.numel()
-        quota_pos = int(self.batch_size_per_image * self.positive_fraction)
-        pos, neg = m >= 1, m == 0
-        keys = torch.rand(n, device=m.device)
-        inf = keys.new_full((), float("inf"))
-        kp = min(quota_pos, n)
-        _, ip = torch.topk(torch.where(pos, keys, inf), kp, largest=False, sorted=False)
-        pos_mask = torch.zeros(n, dtype=torch.bool, device=m.device).index_fill_(0, ip, True) & pos
-        num_pos = pos_mask.sum()
-        kn = min(self.batch_size_per_image, n)
-        _, ineg = torch.topk(torch.where(neg, keys, inf), kn, largest=False, sorted=True)
-        take = torch.arange(kn, device=m.device) < (self.batch_size_per_image - num_pos)
-        neg_mask = torch.zeros(n + 1, dtype=torch.bool, device=m.device)
-        neg_mask.index_fill_(0, torch.where(take, ineg, ineg.new_full((), n)), True)
-        return pos_mask, neg_mask[:n] & neg
-
     def __call__(self, matched_idxs):
         pos_idx, neg_idx = [], []
         if self.rng_device is None and matched_idxs and matched_idxs[0].is_cuda:
-            if max(int(m.numel()) for m in matched_idxs) <= 16384:
-                return self._sample_on_device(matched_idxs)
-            for m in matched_idxs:
-                p, q = self._sample_topk(m)
-                pos_idx.append(p)
-                neg_idx.append(q)
-            return pos_idx, neg_idx
+            return self._sample_on_device(matched_idxs)
         for m in matched_idxs:
             positive = torch.nonzero(m >= 1).squeeze(1)
             negative = torch.nonzero(m == 0).squeeze(1)

@@ -302,11 +302,17 @@ extern "C" int mmt_fpn_rois_f32(const float* boxes_xyxy, const int* image_counts
 // (every subset of the required size is equally likely), no host round trip, one launch for the whole batch.
 namespace {
 
+// 32-bit counter-based key: two rounds of the murmur3 finaliser over (seed, image, index) — ~12 integer instructions
+// (the sampler evaluates it for every anchor in each of its ~5 passes, so a 64-bit mixer would dominate the kernel)
+__device__ __forceinline__ unsigned int fmix32(unsigned int h) {
+  h ^= h >> 16; h *= 0x85EBCA6Bu;
+  h ^= h >> 13; h *= 0xC2B2AE35u;
+  h ^= h >> 16;
+  return h;
+}
 __device__ __forceinline__ unsigned int hash_key(unsigned long long seed, unsigned int img, unsigned int i) {
-  unsigned long long z = seed + 0x9E3779B97F4A7C15ull * ((unsigned long long)img * 0x100000001B3ull + i + 1ull);
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;   // splitmix64 finaliser
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  return (unsigned int)((z ^ (z >> 31)) >> 32);
+  const unsigned int s0 = (unsigned int)seed, s1 = (unsigned int)(seed >> 32);
+  return fmix32(fmix32(i * 0x9E3779B1u + s0) ^ (img * 0x7FEB352Du + s1));
 }
 
 __device__ int block_count(int v, int* s_part) {

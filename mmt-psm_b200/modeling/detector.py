@@ -191,26 +191,50 @@ class GeneralizedRCNN(nn.Module):
     def _stu_outputs(self):
         if self._stu is None:
             g, _, _, x = self._pending.pop("stu")
-            flat = tuple(g(x, prefetched=True))
+            # plain static buffers: the trunk boundary is handled by hand (leaves in, grad buffers out), which spares
+            # the zero-padded slice gradients autograd would build for the two halves of every pyramid level
+            flat = tuple(g.forward_detached([x], prefetched=True))
             want_emb = self._trunk_fn("stu")[1]
             n = len(flat) // (3 + int(want_emb))      # feature levels | fused RPN maps | proposal scores | [embeddings]
             self._stu = (flat[:n], (flat[n:2 * n], flat[2 * n:3 * n]), flat[3 * n:] if want_emb else None, x.shape[0] // 2)
+            self._stu_graph, self._stu_n = g, n
         return self._stu
 
+    def _leaf(self, tensor, out_index, lo, hi):
+        leaf = tensor.detach().requires_grad_(True)
+        self._deferred.append((out_index, lo, hi, leaf))
+        return leaf
+
     def backward_deferred(self, extra_losses=None):
-        """Trunk backward of the stacked student pass: the supervised branch's gradients (already sitting on the detached
-        leaves) and the consistency losses go through the backbone in one replay."""
-        tensors, grads = [], []
+        """Backward of the stacked student trunk: `extra_losses` (the consistency terms) are back-propagated through
+        their heads down to the boundary leaves; then every boundary gradient — the supervised branch's, produced by
+        the early supervised backward, and the consistency branch's — is written into its half of the trunk graph's
+        gradient buffers and the captured trunk backward is replayed ONCE."""
         if extra_losses is not None:
-            tensors.append(extra_losses)
-            grads.append(None)
-        for attached, leaf in self._deferred:
-            if leaf.grad is not None:
-                tensors.append(attached)
-                grads.append(leaf.grad)
+            extra_losses.backward()
+        g = self._stu_graph
+        covered = set()
+        for out_index, lo, hi, leaf in self._deferred:
+            buf = g.grad_buffer(out_index)
+            if buf is None:
+                continue
+            region = buf if lo is None else buf[lo:hi]
+            if leaf.grad is None:
+                region.zero_()
+            else:
+                region.copy_(leaf.grad)
+            covered.add((out_index, lo))
+        B = self._stu[3]
+        for i in g.grad_idx:   # halves nobody consumed this iteration (e.g. the teacher produced no boxes)
+            whole = g.static_gout[g.grad_idx.index(i)]
+            if i < self._stu_n:
+                for lo in (0, B):
+                    if (i, lo) not in covered:
+                        whole[lo:lo + B].zero_()
+            elif (i, None) not in covered:
+                whole.zero_()
         self._deferred, self._stu = [], None
-        if tensors:
-            torch.autograd.backward(tensors, grads)
+        g.backward_direct()
 
     def _trunk(self, site, x, n_views=1, first_ptr=None):
         """Runs (or replays from a CUDA graph / picks up the prefetched replay of) the trunk of call site `site`;
@@ -223,15 +247,15 @@ class GeneralizedRCNN(nn.Module):
                 if stu is not None:
                     self._stu_ptrs = {"sup": stu[1], "unl": stu[2]}
                 feats, rpn, emb, B = self._stu_outputs()
+                n = len(feats)
                 if site == "sup":
                     fused, scores = rpn
-                    pairs = [(t, t.detach().requires_grad_(True)) for t in [f[:B] for f in feats] + list(fused)]
-                    self._deferred += pairs
-                    leaves = [leaf for _, leaf in pairs]
-                    return {"features": tuple(leaves[:len(feats)]), "emb": None,
-                            "rpn": (tuple(leaves[len(feats):]), tuple(scores))}
-                out = {"features": tuple(f[B:] for f in feats), "emb": emb, "rpn": None}
-                return out
+                    f_leaves = tuple(self._leaf(f[:B], i, 0, B) for i, f in enumerate(feats))
+                    r_leaves = tuple(self._leaf(t, n + i, None, None) for i, t in enumerate(fused))
+                    return {"features": f_leaves, "emb": None, "rpn": (r_leaves, tuple(scores))}
+                f_leaves = tuple(self._leaf(f[B:], i, B, 2 * B) for i, f in enumerate(feats))
+                e_leaves = tuple(self._leaf(t, 3 * n + i, None, None) for i, t in enumerate(emb)) if emb is not None else None
+                return {"features": f_leaves, "emb": e_leaves, "rpn": None}
         pend = self._pending.pop(site, None)
         if pend is not None and first_ptr is not None and pend[1] == first_ptr:
             g, _, shape, keep_alive = pend

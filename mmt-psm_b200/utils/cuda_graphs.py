@@ -137,6 +137,24 @@ class GraphedCallable(object):
         _l.add_launch_count(self.fwd_launches)
         return self.static_out
 
+    # ---- direct (autograd-free) use: the caller owns the boundary -------------------------------------------
+    def forward_detached(self, inputs, prefetched=False):
+        """Replay (or pick up the prefetched replay) and return the static output buffers as plain tensors: no autograd
+        node is created; the caller feeds `grad_buffer`s and calls `backward_direct` itself."""
+        self._skip_replay = bool(prefetched)
+        return self._replay_forward(inputs)
+
+    def grad_buffer(self, out_index):
+        """The static gradient buffer of output `out_index` (None if that output does not require grad)."""
+        return self.static_gout[self.grad_idx.index(out_index)] if out_index in self.grad_idx else None
+
+    def backward_direct(self):
+        """Replay the captured backward over whatever the grad buffers hold."""
+        self.g_bwd.replay()
+        _l.add_launch_count(self.bwd_launches)
+        if self.on_backward is not None:
+            self.on_backward(self.touched)
+
     def _replay_backward(self, gouts):
         for s, g in zip(self.static_gout, gouts):
             if g is None:

@@ -191,6 +191,26 @@ int mmt_roi_pool_backward_f32(const float* grad_output, const int* argmax, const
                               int channels, int height, int width, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * RPN loss (reference modeling/rpn/loss.py:138-196) over the fused head maps of all pyramid levels, in place:
+ * fused_levels[l] = [n_images, level_pixels[l], padded_channels] fp32, channels [0, A) objectness logits of the A
+ * anchors of a pixel, [A, 5A) their box deltas (host array of device pointers).  labels [n_images * sum(pixels*A)]
+ * fp32 (image-major, level-major, (pixel, anchor) order; 1 / 0 / -1), regression_targets [same, 4], pos_mask /
+ * neg_mask uint8 = the sampler's choice.  forward: sums_out[0] = sum of BCE-with-logits over the sampled anchors,
+ * sums_out[1] = sum of smooth-L1(beta) over the positive anchors' deltas (the caller divides by |sampled|).
+ * backward: writes d/d(fused) of  g_obj * sums[0] / n_sampled + g_box * sums[1] / n_sampled  into dfused_levels
+ * (every element, zeros included); n_sampled, grad_objectness_loss, grad_box_loss are DEVICE scalars. */
+int mmt_rpn_loss_forward_f32(const float* const* fused_levels, const int64_t* level_pixels, int n_levels,
+                             int num_anchors, int padded_channels, int n_images, const float* labels,
+                             const float* regression_targets, const unsigned char* pos_mask,
+                             const unsigned char* neg_mask, float beta, float* sums_out, void* stream);
+int mmt_rpn_loss_backward_f32(const float* const* fused_levels, float* const* dfused_levels,
+                              const int64_t* level_pixels, int n_levels, int num_anchors, int padded_channels,
+                              int n_images, const float* labels, const float* regression_targets,
+                              const unsigned char* pos_mask, const unsigned char* neg_mask, float beta,
+                              const float* n_sampled, const float* grad_objectness_loss, const float* grad_box_loss,
+                              void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * SigmoidFocalLoss — ABSENT from this reference tree; semantics are those of
  * upstream facebookresearch/maskrcnn-benchmark csrc/cuda/SigmoidFocalLoss_cuda.cu:
  *   p = sigmoid(x); t = targets[n] (1-based class, 0 = background, < 0 = ignore)

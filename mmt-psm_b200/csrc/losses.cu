@@ -6,6 +6,7 @@
 //   PSM   : maskrcnn_benchmark/modeling/roi_heads/box_head/loss.py:164-237,267-287,311-315
 //   MGD   : maskrcnn_benchmark/modeling/detector/generalized_rcnn.py:243-282
 #include <float.h>
+#include <algorithm>
 
 #include "common.cuh"
 
@@ -437,4 +438,179 @@ extern "C" int mmt_mgd_finalize_f32(const float* partials, const float* mask_sum
   mgd_finalize_kernel<<<1, 32, 0, (cudaStream_t)stream_>>>(partials, mask_sums, n_levels, n_views,
                                                            channels, loss_out);
   return mmt::check_launch("mgd_finalize");
+}
+
+// ------------------------------------------------------------------------------------ RPN loss
+// Reference modeling/rpn/loss.py:138-196: over the sampled anchors of the batch,
+//   objectness_loss = mean BCE-with-logits(objectness[sampled], labels[sampled])
+//   box_loss        = sum smooth_l1(deltas[pos], targets[pos], beta = 1/9) / |sampled|
+// The reference flattens the five per-level head maps (permute + reshape + cat), gathers the sampled rows with two
+// `nonzero`s and runs ~35 elementwise launches, then as many again in autograd's backward.  Here one kernel reads the
+// fused head maps [N, h*w, Cp] of all levels in place (channels [0,A) objectness, [A,5A) deltas) and reduces both sums
+// under the sampling masks; a second one writes the analytic gradient straight into maps of the same layout.
+namespace {
+
+constexpr int kRpnMaxLevels = 8;
+struct RpnLevels {
+  int n_levels;
+  const float* fused[kRpnMaxLevels];   // [N, pixels, Cp]
+  float* dfused[kRpnMaxLevels];        // same layout (backward only)
+  long long pixels[kRpnMaxLevels];
+  long long anchor_start[kRpnMaxLevels + 1];   // first anchor of the level inside one image's anchor list
+};
+
+__device__ __forceinline__ int rpn_level_of(const RpnLevels& L, long long a) {
+  int l = 0;
+  while (l + 1 < L.n_levels && a >= L.anchor_start[l + 1]) ++l;
+  return l;
+}
+
+__device__ __forceinline__ float bce_logits(float x, float y) {   // torch: max(x,0) - x*y + log1p(exp(-|x|))
+  return fmaxf(x, 0.f) - x * y + log1pf(expf(-fabsf(x)));
+}
+
+__global__ void __launch_bounds__(256) rpn_loss_fwd_kernel(RpnLevels L, int A, int Cp, int n_images,
+                                                           const float* __restrict__ labels,
+                                                           const float4* __restrict__ targets,
+                                                           const unsigned char* __restrict__ pos,
+                                                           const unsigned char* __restrict__ neg, float beta,
+                                                           float* __restrict__ sums /*[2]: bce, smooth-l1*/) {
+  __shared__ float s_red[32];
+  const long long per_image = L.anchor_start[L.n_levels];
+  const long long total = per_image * n_images;
+  float bce = 0.f, sl1 = 0.f;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const bool p = pos[t] != 0, q = neg[t] != 0;
+    if (!(p || q)) continue;
+    const long long img = t / per_image, a_img = t - img * per_image;
+    const int l = rpn_level_of(L, a_img);
+    const long long a_lvl = a_img - L.anchor_start[l];
+    const long long pix = a_lvl / A;
+    const int a = (int)(a_lvl - pix * A);
+    const float* row = L.fused[l] + (img * L.pixels[l] + pix) * Cp;
+    bce += bce_logits(row[a], fmaxf(labels[t], 0.f));
+    if (p) {
+      const float4 tg = targets[t];
+      const float d[4] = {row[A + 4 * a] - tg.x, row[A + 4 * a + 1] - tg.y, row[A + 4 * a + 2] - tg.z,
+                          row[A + 4 * a + 3] - tg.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float n = fabsf(d[e]);
+        sl1 += (n < beta) ? 0.5f * n * n / beta : n - 0.5f * beta;
+      }
+    }
+  }
+  bce = mmt::block_sum(bce, s_red);
+  sl1 = mmt::block_sum(sl1, s_red);
+  if (threadIdx.x == 0) {
+    atomicAdd(sums, bce);
+    atomicAdd(sums + 1, sl1);
+  }
+}
+
+// d(loss)/d(fused): every element of every map is written (zeros off the sampled anchors and in the padding channels)
+__global__ void __launch_bounds__(256) rpn_loss_bwd_kernel(RpnLevels L, int A, int Cp, int n_images,
+                                                           const float* __restrict__ labels,
+                                                           const float4* __restrict__ targets,
+                                                           const unsigned char* __restrict__ pos,
+                                                           const unsigned char* __restrict__ neg, float beta,
+                                                           const float* __restrict__ n_sampled,
+                                                           const float* __restrict__ g_obj,
+                                                           const float* __restrict__ g_box) {
+  const long long per_image = L.anchor_start[L.n_levels];
+  const long long total = per_image * n_images;
+  const float inv_n = 1.f / *n_sampled;
+  const float go = *g_obj * inv_n, gb = *g_box * inv_n;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const long long img = t / per_image, a_img = t - img * per_image;
+    const int l = rpn_level_of(L, a_img);
+    const long long a_lvl = a_img - L.anchor_start[l];
+    const long long pix = a_lvl / A;
+    const int a = (int)(a_lvl - pix * A);
+    const long long off = (img * L.pixels[l] + pix) * Cp;
+    const float* row = L.fused[l] + off;
+    float* drow = L.dfused[l] + off;
+    const bool p = pos[t] != 0, q = neg[t] != 0;
+    float dobj = 0.f;
+    float dd[4] = {0.f, 0.f, 0.f, 0.f};
+    if (p || q) {
+      const float x = row[a];
+      dobj = (1.f / (1.f + expf(-x)) - fmaxf(labels[t], 0.f)) * go;
+      if (p) {
+        const float4 tg = targets[t];
+        const float d[4] = {row[A + 4 * a] - tg.x, row[A + 4 * a + 1] - tg.y, row[A + 4 * a + 2] - tg.z,
+                            row[A + 4 * a + 3] - tg.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float n = fabsf(d[e]);
+          dd[e] = ((n < beta) ? d[e] / beta : (d[e] > 0.f ? 1.f : (d[e] < 0.f ? -1.f : 0.f))) * gb;
+        }
+      }
+    }
+    drow[a] = dobj;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) drow[A + 4 * a + e] = dd[e];
+    if (a == 0)
+      for (int c = 5 * A; c < Cp; ++c) drow[c] = 0.f;
+  }
+}
+
+int fill_levels(RpnLevels& L, const float* const* fused, float* const* dfused, const int64_t* pixels, int n_levels, int A) {
+  if (n_levels < 1 || n_levels > kRpnMaxLevels) return mmt::fail(MMT_ERR_INVALID_ARGUMENT, "rpn_loss: 1..%d levels", kRpnMaxLevels);
+  L.n_levels = n_levels;
+  long long acc = 0;
+  for (int l = 0; l < n_levels; ++l) {
+    if (!fused[l] || pixels[l] <= 0) return mmt::fail(MMT_ERR_INVALID_ARGUMENT, "rpn_loss: bad level %d", l);
+    L.fused[l] = fused[l];
+    L.dfused[l] = dfused ? dfused[l] : nullptr;
+    L.pixels[l] = pixels[l];
+    L.anchor_start[l] = acc;
+    acc += pixels[l] * A;
+  }
+  L.anchor_start[n_levels] = acc;
+  return MMT_OK;
+}
+
+}  // namespace
+
+extern "C" int mmt_rpn_loss_forward_f32(const float* const* fused_levels, const int64_t* level_pixels, int n_levels,
+                                        int num_anchors, int padded_channels, int n_images, const float* labels,
+                                        const float* regression_targets, const unsigned char* pos_mask,
+                                        const unsigned char* neg_mask, float beta, float* sums_out, void* stream_) {
+  MMT_REQUIRE(labels && regression_targets && pos_mask && neg_mask && sums_out && fused_levels && level_pixels,
+              "rpn_loss_forward: null pointer");
+  MMT_REQUIRE(padded_channels >= 5 * num_anchors && num_anchors > 0 && n_images > 0 && beta > 0.f, "rpn_loss_forward: bad sizes");
+  RpnLevels L;
+  if (int rc = fill_levels(L, fused_levels, nullptr, level_pixels, n_levels, num_anchors)) return rc;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  MMT_CUDA(cudaMemsetAsync(sums_out, 0, 2 * sizeof(float), stream));
+  const long long total = L.anchor_start[n_levels] * n_images;
+  const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)mmt::kNumSMs * 8);
+  rpn_loss_fwd_kernel<<<blocks, 256, 0, stream>>>(L, num_anchors, padded_channels, n_images, labels,
+                                                  reinterpret_cast<const float4*>(regression_targets), pos_mask,
+                                                  neg_mask, beta, sums_out);
+  return mmt::check_launch("rpn_loss_fwd");
+}
+
+extern "C" int mmt_rpn_loss_backward_f32(const float* const* fused_levels, float* const* dfused_levels,
+                                         const int64_t* level_pixels, int n_levels, int num_anchors,
+                                         int padded_channels, int n_images, const float* labels,
+                                         const float* regression_targets, const unsigned char* pos_mask,
+                                         const unsigned char* neg_mask, float beta, const float* n_sampled,
+                                         const float* grad_objectness_loss, const float* grad_box_loss, void* stream_) {
+  MMT_REQUIRE(labels && regression_targets && pos_mask && neg_mask && fused_levels && dfused_levels && level_pixels &&
+                  n_sampled && grad_objectness_loss && grad_box_loss,
+              "rpn_loss_backward: null pointer");
+  MMT_REQUIRE(padded_channels >= 5 * num_anchors && num_anchors > 0 && n_images > 0 && beta > 0.f, "rpn_loss_backward: bad sizes");
+  RpnLevels L;
+  if (int rc = fill_levels(L, fused_levels, dfused_levels, level_pixels, n_levels, num_anchors)) return rc;
+  for (int l = 0; l < n_levels; ++l) MMT_REQUIRE(dfused_levels[l] != nullptr, "rpn_loss_backward: null gradient map");
+  const long long total = L.anchor_start[n_levels] * n_images;
+  const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)mmt::kNumSMs * 8);
+  rpn_loss_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream_>>>(
+      L, num_anchors, padded_channels, n_images, labels, reinterpret_cast<const float4*>(regression_targets), pos_mask,
+      neg_mask, beta, n_sampled, grad_objectness_loss, grad_box_loss);
+  return mmt::check_launch("rpn_loss_bwd");
 }

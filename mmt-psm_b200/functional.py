@@ -138,6 +138,36 @@ def fpn_roi_align(feats, scales, rois, levels, pooled, sampling_ratio):
     return _FpnRoiAlign.apply(rois, levels, tuple(scales), pooled, sampling_ratio, *feats)
 
 
+class _RpnLoss(torch.autograd.Function):
+    """RPN objectness + box-regression losses (reference rpn/loss.py:138-196) over the fused head maps of all levels:
+    one launch forward, one launch backward (analytic gradient written in the maps' own layout)."""
+
+    @staticmethod
+    def forward(ctx, labels, targets, pos, neg, n_sampled, num_anchors, beta, *fused):
+        sums = K.rpn_loss_forward(fused, num_anchors, labels, targets, pos, neg, beta)
+        ctx.save_for_backward(labels, targets, pos, neg, n_sampled, *fused)
+        ctx.num_anchors, ctx.beta = num_anchors, beta
+        out = sums / n_sampled
+        return out[0], out[1]
+
+    @staticmethod
+    def backward(ctx, g_obj, g_box):
+        labels, targets, pos, neg, n_sampled = ctx.saved_tensors[:5]
+        fused = ctx.saved_tensors[5:]
+        zero = n_sampled.new_zeros(())
+        g_obj = zero if g_obj is None else g_obj.contiguous()
+        g_box = zero if g_box is None else g_box.contiguous()
+        dfused = K.rpn_loss_backward(fused, ctx.num_anchors, labels, targets, pos, neg, ctx.beta, n_sampled, g_obj, g_box)
+        return (None,) * 7 + tuple(dfused)
+
+
+def rpn_loss(fused, num_anchors, labels, targets, pos, neg, beta=1.0 / 9):
+    """Returns (objectness_loss, box_loss).  labels fp32 / targets [.,4] fp32 / pos, neg bool, all over the batch's
+    anchors in (image, level, pixel, anchor) order."""
+    n_sampled = (pos | neg).sum().to(torch.float32)
+    return _RpnLoss.apply(labels, targets, pos, neg, n_sampled, num_anchors, beta, *fused)
+
+
 class _PsmLoss(torch.autograd.Function):
     """PSM consistency loss (reference box_head/loss.py:164-237,267-287,311-315) — one launch; the analytic
     gradient w.r.t. the student logits is produced by the same kernel."""

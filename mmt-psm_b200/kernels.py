@@ -367,6 +367,43 @@ def sigmoid_focal_loss_backward(logits, targets, d_losses, num_classes, gamma, a
     return out
 
 
+# -------------------------------------------------------------------------------- RPN loss
+def _rpn_level_tables(fused):
+    n = len(fused)
+    ptrs = (c_void_p * n)(*[f.data_ptr() for f in fused])
+    pix = (ctypes.c_int64 * n)(*[f.shape[1] * f.shape[2] for f in fused])
+    return ptrs, pix
+
+
+def rpn_loss_forward(fused, num_anchors, labels, targets, pos, neg, beta):
+    """fused: per-level head maps [N,h,w,Cp]; returns sums [2] (BCE over sampled, smooth-L1 over positives)."""
+    _need_cuda(labels, targets, pos, neg, *fused)
+    L = _l.lib()
+    for f in fused:
+        assert f.is_contiguous() and f.dtype == torch.float32
+    assert labels.is_contiguous() and targets.is_contiguous() and pos.is_contiguous() and neg.is_contiguous()
+    assert labels.dtype == torch.float32 and targets.dtype == torch.float32 and pos.element_size() == 1 and neg.element_size() == 1
+    N, Cp = fused[0].shape[0], fused[0].shape[3]
+    assert labels.numel() == N * sum(f.shape[1] * f.shape[2] * num_anchors for f in fused)
+    sums = torch.empty(2, dtype=torch.float32, device=labels.device)
+    ptrs, pix = _rpn_level_tables(fused)
+    check(L.mmt_rpn_loss_forward_f32(ptrs, pix, len(fused), num_anchors, Cp, N, _p(labels), _p(targets), _p(pos),
+                                     _p(neg), float(beta), _p(sums), _stream()), "rpn_loss_forward")
+    return sums
+
+
+def rpn_loss_backward(fused, num_anchors, labels, targets, pos, neg, beta, n_sampled, g_obj, g_box):
+    L = _l.lib()
+    N, Cp = fused[0].shape[0], fused[0].shape[3]
+    dfused = [torch.empty_like(f) for f in fused]
+    ptrs, pix = _rpn_level_tables(fused)
+    dptrs = (c_void_p * len(fused))(*[d.data_ptr() for d in dfused])
+    check(L.mmt_rpn_loss_backward_f32(ptrs, dptrs, pix, len(fused), num_anchors, Cp, N, _p(labels), _p(targets), _p(pos),
+                                      _p(neg), float(beta), _p(n_sampled), _p(g_obj), _p(g_box), _stream()),
+          "rpn_loss_backward")
+    return dfused
+
+
 # ------------------------------------------------------------------------------------- PSM
 def psm_loss(student_logits, teacher_logits, labels, temperature=0.5, sharpen=True, hard_negative=True,
              neg_weight=1.5, neg_order=None):

@@ -62,6 +62,9 @@ _PROTOS = {
                                          c_int, P, P, P]),
     "mmt_roi_pool_backward_f32": (c_int, [P, P, P, c_int, c_int, c_int, P, c_int, c_int, c_int,
                                           c_int, P]),
+    "mmt_rpn_loss_forward_f32": (c_int, [POINTER(P), POINTER(c_int64), c_int, c_int, c_int, c_int, P, P, P, P, c_float, P, P]),
+    "mmt_rpn_loss_backward_f32": (c_int, [POINTER(P), POINTER(P), POINTER(c_int64), c_int, c_int, c_int, c_int, P, P, P, P, c_float,
+                                          P, P, P, P]),
     "mmt_sigmoid_focal_loss_forward_f32": (c_int, [P, P, c_int, c_int, c_float, c_float, P, P]),
     "mmt_sigmoid_focal_loss_backward_f32": (c_int, [P, P, P, c_int, c_int, c_float, c_float, P, P]),
     "mmt_psm_workspace_bytes": (c_size_t, [c_int]),

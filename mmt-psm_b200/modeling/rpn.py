@@ -276,18 +276,24 @@ class RPNLossComputation(object):
         labels = torch.cat(labels, dim=0)
         return obj[sampled], reg[pos], (sampled, pos.shape), labels[sampled]
 
-    def __call__(self, anchors, objectness, box_regression, targets):
+    def __call__(self, anchors, objectness, box_regression, targets, fused=None):
         """Reference rpn/loss.py:138-196.  The reference gathers the sampled anchors into index lists (two
         `nonzero`s = two host syncs) and reduces over them; here the same sums run over all anchors under the
-        sampling masks: identical terms, no data-dependent shapes."""
+        sampling masks — with the fused head maps at hand, in ONE kernel (functional.rpn_loss) that reads the five
+        per-level maps in place, instead of flattening / concatenating them and ~35 elementwise launches."""
         labels, regression_targets, pos, neg = self._sample(anchors, targets)
+        labels = torch.cat(labels, dim=0)
+        regression_targets = torch.cat(regression_targets, dim=0)
+        if fused is not None and all(f.is_cuda and f.is_contiguous() for f in fused):
+            from .. import functional as Fk
+            objectness_loss, box_loss = Fk.rpn_loss(list(fused), objectness[0].shape[-1], labels, regression_targets,
+                                                    pos, neg, 1.0 / 9)
+            return objectness_loss, box_loss
         sampled = pos | neg
         n_sampled = sampled.sum().to(torch.float32)
         # NHWC maps flatten directly to the (h, w, anchor) order of the labels
         obj = cat([o.reshape(o.shape[0], -1) for o in objectness], dim=1).reshape(-1)
         reg = cat([b.reshape(b.shape[0], -1, 4) for b in box_regression], dim=1).reshape(-1, 4)
-        labels = torch.cat(labels, dim=0)
-        regression_targets = torch.cat(regression_targets, dim=0)
         beta = 1.0 / 9
         n = torch.abs(reg - regression_targets)
         l1 = torch.where(n < beta, 0.5 * n ** 2 / beta, n - 0.5 * beta)
@@ -356,7 +362,7 @@ class RPNModule(nn.Module):
         else:
             with torch.no_grad():
                 boxes = self.box_selector_train(anchors, objectness, reg, targets, head_out=self._head_out)
-        loss_objectness, loss_rpn_box_reg = self.loss_evaluator(anchors, objectness, reg, targets)
+        loss_objectness, loss_rpn_box_reg = self.loss_evaluator(anchors, objectness, reg, targets, fused=self._head_out[0])
         return boxes, {"loss_objectness": loss_objectness, "loss_rpn_box_reg": loss_rpn_box_reg}
 
     def _forward_test(self, anchors, objectness, reg):

@@ -277,6 +277,41 @@ def test_elementwise_vs_torch(cuda):
     assert torch.equal(K().nhwc_to_nchw(K().nchw_to_nhwc(a)), a)
 
 
+# --------------------------------------------------------------------------------- RPN loss
+def test_rpn_loss_fused_matches_reference_formula(cuda):
+    """functional.rpn_loss over fused per-level head maps == the reference's formula (rpn/loss.py:138-196: BCE with
+    logits over the sampled anchors, smooth-L1(beta = 1/9) over the positives, both / |sampled|) evaluated with torch
+    ops on the flattened maps — values to 1e-6 relative, gradients w.r.t. the head maps to 1e-6 absolute."""
+    import torch.nn.functional as Fn
+    from mmt_psm_b200 import functional as Fk
+    gen = torch.Generator().manual_seed(21)
+    N, A, Cp = 2, 3, 32
+    sizes = [(12, 10), (6, 5), (3, 3)]
+    fused = [torch.randn(N, h, w, Cp, generator=gen).to(cuda).requires_grad_(True) for h, w in sizes]
+    total = N * sum(h * w * A for h, w in sizes)
+    labels = torch.randint(-1, 2, (total,), generator=gen).float().to(cuda)
+    targets = (torch.randn(total, 4, generator=gen) * 0.3).to(cuda)
+    r = torch.rand(total, generator=gen).to(cuda)
+    pos = (labels == 1) & (r < 0.5)
+    neg = (labels == 0) & (r < 0.4)
+    lo, lb = Fk.rpn_loss(fused, A, labels, targets, pos, neg, 1.0 / 9)
+    (2.0 * lo + 3.0 * lb).backward()
+    got = [f.grad.clone() for f in fused]
+    ref_in = [f.detach().clone().requires_grad_(True) for f in fused]
+    obj = torch.cat([f[..., :A].reshape(N, -1) for f in ref_in], 1).reshape(-1)
+    reg = torch.cat([f[..., A:5 * A].reshape(N, -1, 4) for f in ref_in], 1).reshape(-1, 4)
+    sampled = pos | neg
+    n = torch.abs(reg[pos] - targets[pos])
+    ref_b = torch.where(n < 1.0 / 9, 0.5 * n ** 2 * 9, n - 0.5 / 9).sum() / sampled.sum()
+    ref_o = Fn.binary_cross_entropy_with_logits(obj[sampled], labels[sampled])
+    (2.0 * ref_o + 3.0 * ref_b).backward()
+    assert abs(float(lo) - float(ref_o)) <= 1e-6 * abs(float(ref_o)) + 1e-7
+    assert abs(float(lb) - float(ref_b)) <= 1e-6 * abs(float(ref_b)) + 1e-7
+    for g, f in zip(got, ref_in):
+        assert float((g - f.grad).abs().max()) <= 1e-6
+        assert float(g[..., 5 * A:].abs().max()) == 0.0
+
+
 # ------------------------------------------------------------------------- balanced sampler
 def test_balanced_sample_counts_and_uniformity(cuda):
     """mmt_balanced_sample_f32: exact class sizes per image (min(#pos, quota), min(#neg, batch - taken)), only

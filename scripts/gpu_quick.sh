@@ -1,4 +1,5 @@
 #!/bin/bash
+# Quick GPU visit while iterating: parity suite, free-running step time, 30-iteration loss trace.
 mkdir -p gpurun_out
 timeout 1200 python -m pytest tests -m gpu -q --timeout 600 2>&1 | grep -v "^E   *\[" > gpurun_out/pytest_gpu.log
 grep -n "Error\|^E \|passed\|failed" gpurun_out/pytest_gpu.log | head -30

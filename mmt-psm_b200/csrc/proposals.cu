@@ -335,12 +335,14 @@ constexpr int kSampleCap = 8192;   // candidate keys held in shared memory durin
 __device__ unsigned int select_threshold(const float* __restrict__ labels, int n, int cls_pos, unsigned long long seed,
                                          unsigned int img, int want, int cls_size, int* s_part, int* s_bcast,
                                          unsigned int* s_keys) {
+  // a class that fits in the list is collected whole (T0 = max key); a larger one is prefiltered to ~4 x want keys
   const unsigned long long target = (unsigned long long)want * 4ull + 64ull;
-  const bool prefilter = target < (unsigned long long)cls_size;
+  const bool whole = cls_size <= kSampleCap;
+  const bool prefilter = whole || target < (unsigned long long)cls_size;
   unsigned int T0 = 0xffffffffu;
   int m = 0;
   if (prefilter) {
-    T0 = (unsigned int)((target << 32) / (unsigned long long)cls_size);
+    if (!whole) T0 = (unsigned int)((target << 32) / (unsigned long long)cls_size);
     if (threadIdx.x == 0) *s_bcast = 0;
     __syncthreads();
     for (int i = threadIdx.x; i < n; i += blockDim.x) {

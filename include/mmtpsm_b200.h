@@ -352,6 +352,7 @@ typedef struct {
 #define MMT_CONV_SIMT 2
 
 #define MMT_EPI_RELU 1
+#define MMT_STEM_INPUT_NCHW 2 /* mmt_conv_stem_fprop_f32 only: x is the reference's NCHW image batch [B,3,H,W] */
 
 /* Persistent-grid size of the tcgen05 conv kernels launched (or captured into a CUDA graph) from now on: n CTAs,
  * one per SM, leaving 148 - n SMs free for kernels of other streams.  Default 148. */
@@ -364,7 +365,8 @@ int mmt_conv_fprop_f32(const float* x_nhwc, const float* w_ohwi, const float* sc
 /* dx = conv_transpose(dy, w): data gradient.  dx is fully overwritten. */
 /* ResNet stem (reference modeling/backbone/resnet.py:288-293: Conv2d(3, 64, 7, stride 2, pad 3) + FrozenBN + ReLU):
  * the 7x7 / stride-2 convolution over 3 channels runs on the tensor cores as a 4x4 implicit GEMM over the 2x2
- * space-to-depth image (12 channels padded to one 32-wide K block).  x NHWC [B,H,W,3], w OHWI [out_c,7,7,3];
+ * space-to-depth image (12 channels padded to one 32-wide K block).  x NHWC [B,H,W,3] (or, with flag
+ * MMT_STEM_INPUT_NCHW, the reference's NCHW [B,3,H,W] batch as is), w OHWI [out_c,7,7,3];
  * workspace (256-byte aligned) >= mmt_conv_stem_workspace_bytes() holds the space-to-depth image and filter. */
 size_t mmt_conv_stem_workspace_bytes(const mmt_conv_shape* shape);
 int mmt_conv_stem_fprop_f32(const float* x_nhwc, const float* w_ohwi, const float* scale /*nullable*/,

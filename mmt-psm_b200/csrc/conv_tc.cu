@@ -550,7 +550,7 @@ __global__ void __launch_bounds__(256) filter_dgrad_kernel(const float* __restri
 // -> s2d[y + a][dy] — which is a shape the implicit-GEMM kernel above runs as is (taps -2..+1 = "pad 2", TMA
 // zero-fills the border).  x NHWC [B,H,W,3] -> s [B,ceil(H/2),ceil(W/2),32], channel = (dy*2 + dx)*3 + c.
 __global__ void __launch_bounds__(256) stem_s2d_kernel(const float* __restrict__ x, float4* __restrict__ s, int B,
-                                                       int H, int W, int H2, int W2) {
+                                                       int H, int W, int H2, int W2, int x_is_nchw) {
   const long long total = (long long)B * H2 * W2 * 8;  // float4 slots: 8 per pixel
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -564,7 +564,9 @@ __global__ void __launch_bounds__(256) stem_s2d_kernel(const float* __restrict__
         const int ch = q * 4 + e;  // < 12
         const int c = ch % 3, dx = (ch / 3) & 1, dy = ch / 6;
         const int yy = 2 * y2 + dy, xx = 2 * x2 + dx;
-        if (yy < H && xx < W) v[e] = __ldg(x + (((long long)b * H + yy) * W + xx) * 3 + c);
+        if (yy < H && xx < W)
+          v[e] = x_is_nchw ? __ldg(x + (((long long)b * 3 + c) * H + yy) * W + xx)
+                           : __ldg(x + (((long long)b * H + yy) * W + xx) * 3 + c);
       }
     }
     s[i] = make_float4(v[0], v[1], v[2], v[3]);
@@ -848,7 +850,8 @@ int conv_stem_tc(const float* x, const float* w, const float* scale, const float
   {
     const long long slots = (long long)s.batch * h2 * w2 * 8;
     const int grid = (int)std::min<long long>((slots + 255) / 256, (long long)kNumSMs * 16);
-    stem_s2d_kernel<<<grid, 256, 0, stream>>>(x, reinterpret_cast<float4*>(s2d), s.batch, s.in_h, s.in_w, h2, w2);
+    stem_s2d_kernel<<<grid, 256, 0, stream>>>(x, reinterpret_cast<float4*>(s2d), s.batch, s.in_h, s.in_w, h2, w2,
+                                              (flags & MMT_STEM_INPUT_NCHW) ? 1 : 0);
     if (int rc = check_launch("stem_s2d")) return rc;
     stem_filter_kernel<<<(s.out_c * 512 + 255) / 256, 256, 0, stream>>>(w, w4, s.out_c);
     if (int rc = check_launch("stem_filter")) return rc;

@@ -188,17 +188,21 @@ struct LevelTable {
   long long off[9];
 };
 
+// One WARP per output pixel: the lanes sweep the pooling window (up to 62 x 62 inputs at the coarsest level — a
+// thread per output serialised 3844 strided loads there).  The map holds small integers (a sum of binary masks), so
+// the fp32 window sum is exact in any order.
 __global__ void __launch_bounds__(256) mgd_masks_kernel(const float* __restrict__ M, int batch,
                                                         int H, int W, LevelTable tab,
                                                         unsigned char* __restrict__ masks,
                                                         float* __restrict__ sums) {
   const long long total = tab.off[tab.n_levels];
-  __shared__ float red[32];
   __shared__ float s_level[8];
   if (threadIdx.x < 8) s_level[threadIdx.x] = 0.f;
   __syncthreads();
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long idx = warp0; idx < total; idx += n_warps) {
     int l = 0;
     while (idx >= tab.off[l + 1]) ++l;
     const int h = tab.h[l], w = tab.w[l];
@@ -209,17 +213,19 @@ __global__ void __launch_bounds__(256) mgd_masks_kernel(const float* __restrict_
     // adaptive_avg_pool2d window: [floor(o*I/O), ceil((o+1)*I/O))
     const int y0 = (int)(((long long)oy * H) / h), y1 = (int)((((long long)oy + 1) * H + h - 1) / h);
     const int x0 = (int)(((long long)ox * W) / w), x1 = (int)((((long long)ox + 1) * W + w - 1) / w);
-    float s = 0.f;
+    const int ww = x1 - x0, area = (y1 - y0) * ww;
     const float* src = M + (long long)b * H * W;
-    for (int y = y0; y < y1; ++y)
-      for (int x = x0; x < x1; ++x) s += src[(long long)y * W + x];
-    const float mean = s / (float)((y1 - y0) * (x1 - x0));
-    const unsigned char bit = mean > 0.5f ? 1 : 0;
-    masks[idx] = bit;
-    if (bit) atomicAdd(&s_level[l], 1.f);
+    float s = 0.f;
+    for (int a = lane; a < area; a += 32) s += src[(long long)(y0 + a / ww) * W + x0 + a % ww];
+    s = mmt::warp_sum(s);
+    if (lane == 0) {
+      const float mean = s / (float)area;
+      const unsigned char bit = mean > 0.5f ? 1 : 0;
+      masks[idx] = bit;
+      if (bit) atomicAdd(&s_level[l], 1.f);
+    }
   }
   __syncthreads();
-  (void)red;
   if (threadIdx.x < tab.n_levels && s_level[threadIdx.x] != 0.f)
     atomicAdd(&sums[threadIdx.x], s_level[threadIdx.x]);
 }
@@ -397,7 +403,7 @@ extern "C" int mmt_mgd_masks_f32(const float* integral_mask, int batch, int heig
     tab.off[l + 1] = tab.off[l] + (long long)batch * level_h[l] * level_w[l];
   }
   MMT_CUDA(cudaMemsetAsync(mask_sums_out, 0, sizeof(float) * n_levels, stream));
-  mgd_masks_kernel<<<grid_for(tab.off[n_levels], 256, 8), 256, 0, stream>>>(
+  mgd_masks_kernel<<<grid_for(tab.off[n_levels] * 32, 256, 8), 256, 0, stream>>>(
       integral_mask, batch, height, width, tab, masks_out, mask_sums_out);
   return mmt::check_launch("mgd_masks");
 }

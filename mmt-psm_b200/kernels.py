@@ -553,9 +553,12 @@ def conv_fprop(x, w, shape, scale=None, bias=None, residual=None, relu=False, im
     return y
 
 
-def conv_stem_fprop(x, w, shape, scale=None, bias=None, relu=False):
+STEM_INPUT_NCHW = 2
+
+
+def conv_stem_fprop(x, w, shape, scale=None, bias=None, relu=False, nchw=False):
     """7x7 / stride-2 / pad-3 stem over 3 channels on the tensor cores (space-to-depth implicit GEMM).
-    x NHWC [B,H,W,3], w OHWI [Co,7,7,3] -> y NHWC [B,ceil(H/2),ceil(W/2),Co]."""
+    x NHWC [B,H,W,3] (or NCHW [B,3,H,W] with nchw=True), w OHWI [Co,7,7,3] -> y NHWC [B,ceil(H/2),ceil(W/2),Co]."""
     _need_cuda(x, w, scale, bias)
     L = _l.lib()
     assert x.is_contiguous() and w.is_contiguous() and x.dtype == torch.float32 and w.dtype == torch.float32
@@ -565,7 +568,8 @@ def conv_stem_fprop(x, w, shape, scale=None, bias=None, relu=False):
     ws = torch.empty(wsb, dtype=torch.uint8, device=x.device)
     y = torch.empty((shape.batch, shape.out_h, shape.out_w, shape.out_c), dtype=torch.float32, device=x.device)
     check(L.mmt_conv_stem_fprop_f32(_p(x), _p(w), _p(scale), _p(bias), _p(y), ctypes.byref(shape),
-                                    EPI_RELU if relu else 0, _p(ws), wsb, _stream()), "conv_stem_fprop")
+                                    (EPI_RELU if relu else 0) | (STEM_INPUT_NCHW if nchw else 0), _p(ws), wsb, _stream()),
+          "conv_stem_fprop")
     return y
 
 

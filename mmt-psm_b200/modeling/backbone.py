@@ -55,15 +55,23 @@ class StemWithFixedBatchNorm(nn.Module):
         self.conv1 = Conv2d(3, out_channels, 7, 2, 3, bias=False)
         self.bn1 = FrozenBatchNorm2d(out_channels)
 
-    def forward(self, x):
+    def takes_nchw(self, x_nchw):
+        """True when the tensor-core stem applies: it then reads the reference's NCHW image batch directly."""
         c = self.conv1
-        if (K.get_conv_math() == "tf32" and not c.weight.requires_grad and not x.requires_grad
-                and (c.in_channels, c.kernel_size, c.stride, c.padding) == (3, 7, 2, 3)):
+        return (K.get_conv_math() == "tf32" and not c.weight.requires_grad and not x_nchw.requires_grad and x_nchw.is_cuda
+                and (c.in_channels, c.kernel_size, c.stride, c.padding) == (3, 7, 2, 3) and x_nchw.shape[1] == 3)
+
+    def forward(self, x, nchw=False):
+        c = self.conv1
+        if nchw or (self.takes_nchw(x.permute(0, 3, 1, 2)) if x.dim() == 4 else False):
             # frozen stem: forward only, on the tensor cores (space-to-depth implicit GEMM, csrc/conv_tc.cu)
-            B, H, W, _ = x.shape
+            if nchw:
+                B, _, H, W = x.shape
+            else:
+                B, H, W, _ = x.shape
             scale, shift = self.bn1.affine()
             shape = K.conv_shape(B, H, W, 3, c.out_channels, 7, 2, 3)
-            x = K.conv_stem_fprop(x, c.weight.detach(), shape, scale, shift, relu=True)
+            x = K.conv_stem_fprop(x.contiguous(), c.weight.detach(), shape, scale, shift, relu=True, nchw=nchw)
         else:
             x = self.conv1(x, bn=self.bn1, relu=True)
         if x.requires_grad:
@@ -100,9 +108,9 @@ class ResNet(nn.Module):
             for p in m.parameters():
                 p.requires_grad = False
 
-    def forward(self, x):
+    def forward(self, x, nchw=False):
         outs = []
-        x = self.stem(x)
+        x = self.stem(x, nchw=nchw)
         for name in self.stages:
             x = getattr(self, name)(x)
             if self.return_features[name]:
@@ -145,8 +153,13 @@ class _Backbone(nn.Sequential):
     """body (+ fpn).  Accepts the reference's NCHW image batch and converts once to NHWC."""
 
     def forward(self, images_nchw):
-        x = K.nchw_to_nhwc(images_nchw)
-        for m in self:
+        mods = list(self)
+        stem = getattr(mods[0], "stem", None)
+        if stem is not None and hasattr(stem, "takes_nchw") and stem.takes_nchw(images_nchw):
+            x = mods[0](images_nchw.float(), nchw=True)     # the tensor-core stem reads the NCHW batch as is
+        else:
+            x = mods[0](K.nchw_to_nhwc(images_nchw))
+        for m in mods[1:]:
             x = m(x)
         return x
 

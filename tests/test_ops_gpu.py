@@ -560,6 +560,10 @@ def test_conv_stem_7x7_tensor_core(cuda):
         ref = torch.relu(Fn.conv2d(x.double(), w.double(), None, 2, 3) * sc.double().view(1, -1, 1, 1) + sh.double().view(1, -1, 1, 1))
         assert y.shape == ref.shape, (y.shape, ref.shape)
         assert _rel(y.double(), ref) < 3e-3, _rel(y.double(), ref)
+        # the same stem reading the reference's NCHW batch directly: bit-identical to the NHWC entry
+        y2 = kn.conv_stem_fprop(x.contiguous().to(cuda), w.permute(0, 2, 3, 1).contiguous().to(cuda), shape, sc.to(cuda),
+                                sh.to(cuda), relu=True, nchw=True).permute(0, 3, 1, 2).cpu()
+        assert torch.equal(y, y2)
 
 
 def test_conv_full_size_tc_vs_simt(cuda):

@@ -8,6 +8,7 @@ student gradient arena] -> ONE fused SGD + teacher-EMA launch.  Data parallelism
 summed with a single `all_reduce` over the flat fp32 arena and scaled by 1/world inside the optimizer kernel;
 teachers stay bit-identical across ranks without any traffic because EMA is a function of the synced student."""
 import datetime
+import gc
 import logging
 import time
 
@@ -72,6 +73,10 @@ class MTtrainer(object):
         self.n_step_unlabel = cfg.MT.N_STEP_UNLABEL
         self.world = get_world_size()
         self.last_losses = None
+        # Python's generational GC pauses (100+ ms when a full collection walks the autograd / BoxList object graphs)
+        # land at random inside iterations that are ~30 ms long: pace it instead — automatic collection off, a young-
+        # generation collection every `gc_every` iterations (0 = leave the interpreter's GC alone)
+        self.gc_every, self._gc_steps = 50, 0
         self.set_cuda_graphs(cuda_graphs)
 
     def set_cuda_graphs(self, on):
@@ -130,6 +135,13 @@ class MTtrainer(object):
 
     # ---- one iteration ------------------------------------------------------------------------
     def train_step(self, iteration, data_s, target_s, data_u_list=None):
+        if self.gc_every > 0:
+            if self._gc_steps == 0:
+                gc.collect()
+                gc.disable()
+            elif self._gc_steps % self.gc_every == 0:
+                gc.collect(1)
+            self._gc_steps += 1
         mt_on = iteration > self.start_mt and self.lambda_value > 0 and bool(self.cfg.DATASETS.NO_LABEL)
         stacked = False
         if self.cuda_graphs:
@@ -137,16 +149,23 @@ class MTtrainer(object):
             # host-side glue of each pass overlaps the conv work of the next (detector.prefetch_trunk / prefetch_student)
             data_s = data_s.to(self.device, non_blocking=True)   # pinned host batches: the copy overlaps the host's next work
             img_s = data_s.tensors if hasattr(data_s, "tensors") else data_s
-            if mt_on and data_u_list is not None and self.n_step_unlabel == 1:
-                data_u_list = [d.to(self.device, non_blocking=True) for d in data_u_list]
-                if all(isinstance(d, torch.Tensor) for d in data_u_list):
-                    stacked = self.student.prefetch_student(img_s, data_u_list[-self.student_bs:])
-                    if not stacked:
-                        self.student.prefetch_trunk("sup", img_s)
-                    with torch.no_grad():
-                        self.teacher.prefetch_trunk("aug", data_u_list[:self.teacher_bs])
-                    if not stacked:
-                        self.student.prefetch_trunk("unl", data_u_list[-self.student_bs:])
+            if mt_on and data_u_list is not None and self.n_step_unlabel == 1 and all(
+                    isinstance(d, torch.Tensor) for d in data_u_list):
+                # upload order = use order: the student's view first, so its (stacked) trunk starts while the copy
+                # engine is still bringing in the teacher's views
+                data_u_list = list(data_u_list)
+                n_u = len(data_u_list)
+                for i in range(n_u - self.student_bs, n_u):
+                    data_u_list[i] = data_u_list[i].to(self.device, non_blocking=True)
+                stacked = self.student.prefetch_student(img_s, data_u_list[-self.student_bs:])
+                if not stacked:
+                    self.student.prefetch_trunk("sup", img_s)
+                for i in range(n_u - self.student_bs):
+                    data_u_list[i] = data_u_list[i].to(self.device, non_blocking=True)
+                with torch.no_grad():
+                    self.teacher.prefetch_trunk("aug", data_u_list[:self.teacher_bs])
+                if not stacked:
+                    self.student.prefetch_trunk("unl", data_u_list[-self.student_bs:])
             else:
                 self.student.prefetch_trunk("sup", img_s)
         self.scheduler.step()

@@ -270,8 +270,15 @@ def run_ours(args):
         t0 = time.perf_counter()
         e0.record()
         last = None
+        trace = os.environ.get("MMT_BENCH_TRACE") == "1"
         for j in range(k):
+            if trace:
+                torch.cuda.synchronize()
+                ts = time.perf_counter()
             last = step(j, e2e)
+            if trace:
+                torch.cuda.synchronize()
+                print("step %s %d: %.2f ms" % ("e2e" if e2e else "dev", j, (time.perf_counter() - ts) * 1e3), file=sys.stderr, flush=True)
         e1.record()
         barrier()
         wall = time.perf_counter() - t0
@@ -286,7 +293,7 @@ def run_ours(args):
     for j in range(args.warmup):
         step(j, False)
     barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
+    sampler = ClockSampler(local) if (rank == 0 and os.environ.get("MMT_NO_CLOCKS") != "1") else None
     lib.reset_launch_count()
     ms_dev, last = timed(args.steps, False)
     launches = lib.launch_count()

@@ -1,4 +1,5 @@
 #!/bin/bash
-mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_model_gpu.py -m gpu -q --timeout 600 2>&1 | tail -2
-timeout 600 python bench.py --no-cpu-baseline --no-roofline 2>/dev/null | python -c "import json,sys; b=json.loads(sys.stdin.read()); print('mt', b['ms_per_step'], b['e2e']['ms_per_step'])"
+echo "== EAGER module loading"
+time (CUDA_MODULE_LOADING=EAGER MMT_BENCH_TRACE=1 timeout 600 python bench.py --steps 40 --no-cpu-baseline --no-roofline 2>&1 >/dev/null | grep "^step" | awk '{printf "%s ", $4} END {print ""}')
+echo "== no clock sampler (lazy loading)"
+MMT_NO_CLOCKS=1 MMT_BENCH_TRACE=1 timeout 600 python bench.py --steps 40 --no-cpu-baseline --no-roofline 2>&1 >/dev/null | grep "^step" | awk '{printf "%s ", $4} END {print ""}'

@@ -1,6 +1,9 @@
 """Fixed-size positive/negative sampling (reference modeling/balanced_positive_negative_sampler.py:16-71).
-`rng_device`: where `torch.randperm` draws (the reference draws on the tensors' device; parity tests set "cpu" so
-that the CPU reference and the CUDA path consume the same random stream)."""
+
+`rng_device = None` (default): CUDA inputs are sampled by ONE kernel launch for the whole batch
+(`mmt_balanced_sample_f32`: counter-based random keys, no count read-back) — the reference's distribution, a
+different random stream.  `rng_device = "cpu"` (parity tests): the reference's own `torch.randperm(count)[:n]`
+sequence is reproduced on the host, so that the CPU reference and the CUDA path consume the same random stream."""
 import torch
 
 

@@ -6,7 +6,9 @@ selection rules, same loss formulae.  B200 differences:
   * the head's 3x3 conv (+bias+ReLU) and the fused cls(3)+bbox(12) 1x1 conv are tcgen05 launches on NHWC maps,
     so the reference's permute(0,2,3,1).reshape flattening is a free view;
   * the 5 levels x B images NMS problems of one pass (10 `_C.nms` calls with 10 blocking D2H copies in the
-    reference, csrc/cuda/nms.cu:100) are ONE segmented on-device NMS and one 40-byte count read-back.
+    reference, csrc/cuda/nms.cu:100) are ONE segmented on-device NMS returning per-row keep flags; candidate gather,
+    box decoding, target matching / encoding, sampling and the loss itself are single kernels of libmmtpsm_b200
+    (csrc/proposals.cu, csrc/losses.cu) instead of chains of elementwise torch launches.
 """
 import torch
 import torch.nn.functional as F
@@ -83,34 +85,21 @@ class RPNPostProcessor(nn.Module):
             out.append(cat_boxlist((p, gt)))
         return out
 
-    def _c_offsets(self, offs):
-        import ctypes
-        cache = self.__dict__.setdefault("_c_off_cache", {})
-        if offs not in cache:
-            if len(cache) > 16:
-                cache.clear()
-            cache[offs] = (ctypes.c_int * len(offs))(*offs)
-        return cache[offs]
-
     def _segments(self, N, sizes, image_shapes, device):
-        """Static description of the (image, level) NMS problems of a pass, cached per shape: host offsets plus, per
-        candidate row, its segment id / segment start / position inside the segment (device int64)."""
+        """Static description of the (image, level) NMS problems of a pass, cached per shape: segment offsets (a
+        ctypes int array, image-major) and the per-image (width, height) table on the device."""
+        import ctypes
         key = (N, sizes, image_shapes, str(device))
         cache = self.__dict__.setdefault("_seg_cache", {})
         if key not in cache:
             if len(cache) > 16:
                 cache.clear()
-            offs, seg_id, seg_start = [0], [], []
+            offs = [0]
             for j in range(N):
                 for k in sizes:
-                    seg_id += [len(offs) - 1] * k
-                    seg_start += [offs[-1]] * k
                     offs.append(offs[-1] + k)
-            seg_id = torch.tensor(seg_id, dtype=torch.int64, device=device)
-            seg_start = torch.tensor(seg_start, dtype=torch.int64, device=device)
-            pos = torch.arange(offs[-1], dtype=torch.int64, device=device) - seg_start
             wh = torch.tensor([[float(w), float(h)] for (w, h) in image_shapes], dtype=torch.float32, device=device)
-            cache[key] = (offs, seg_id, seg_start, pos, wh)
+            cache[key] = ((ctypes.c_int * len(offs))(*offs), wh)
         return cache[key]
 
     @torch.no_grad()
@@ -133,8 +122,7 @@ class RPNPostProcessor(nn.Module):
             A_ = objectness[0].shape[-1]
         sizes = [min(self.pre_nms_top_n, s.shape[1]) for s in scores_l]
         K_ = sum(sizes)
-        T = N * K_
-        offs, seg_id, seg_start, pos, image_wh = self._segments(N, tuple(sizes), image_shapes, device)
+        offs, image_wh = self._segments(N, tuple(sizes), image_shapes, device)
         deltas = torch.empty((N, K_, 4), dtype=torch.float32, device=device)
         anch = torch.empty((N, K_, 4), dtype=torch.float32, device=device)
         cand_scores = torch.empty((N, K_), dtype=torch.float32, device=device)
@@ -148,7 +136,7 @@ class RPNPostProcessor(nn.Module):
                                                        self.box_coder.bbox_xform_clip, image_wh, K_, flat_scores,
                                                        self.min_size)
         # filtered (too small) boxes carry score -1: they sort behind, and so can never suppress, a valid box
-        flags = K.nms_segmented_flags(boxes, scores_nms, self._c_offsets(tuple(offs)), self.nms_thresh)
+        flags = K.nms_segmented_flags(boxes, scores_nms, offs, self.nms_thresh)
         if valid is not None:
             flags &= valid
         if self.post_nms_top_n > 0 and max(sizes) > self.post_nms_top_n:   # keep[:post_nms_top_n] per (image, level)

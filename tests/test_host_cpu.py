@@ -1,0 +1,142 @@
+"""CPU suite: host-side logic of the operator surface the reference's launcher drives — cfg semantics (yacs quirks
+of SURVEY App. D), BoxList container contract, loss weighting / ramps, LR schedule, registry, synthetic data contract.
+No CUDA, no oracle."""
+import math
+
+import pytest
+import torch
+
+from conftest import ROOT  # noqa: F401  (puts the repo on sys.path)
+
+
+def test_cfg_yacs_semantics():
+    import mmt_psm_b200  # noqa: F401
+    from mmt_psm_b200.config import TRAIN_MT_OVERRIDES, get_cfg_defaults
+    c = get_cfg_defaults()
+    # (ii) flat KEY VAL list from the command line, literal-eval'd strings; (iii) list<->tuple, int->float coercion
+    c.merge_from_list(["MT.CLS_LOSS_TYPE", "'bce'", "MT.SHARPEN", "True", "SOLVER.BASE_LR", "0.005", "MT.LAMBDA", 5,
+                       "MODEL.RPN.ANCHOR_STRIDE", "(4, 8, 16, 32, 64)"])
+    assert c.MT.CLS_LOSS_TYPE == "bce" and c.MT.SHARPEN is True and c.SOLVER.BASE_LR == 0.005
+    assert isinstance(c.MT.LAMBDA, float) and c.MT.LAMBDA == 5.0
+    assert c.MODEL.RPN.ANCHOR_STRIDE == (4, 8, 16, 32, 64)
+    c.merge_from_list(TRAIN_MT_OVERRIDES)
+    assert c.MT.START_MT == 1000 and c.MT.T_ADAPT is True and c.MODEL.ROI_BOX_HEAD.DO == 0.5
+    # (iv) unknown keys are errors
+    with pytest.raises(KeyError):
+        c.merge_from_list(["MT.NO_SUCH_KEY", 1])
+    with pytest.raises(ValueError):
+        c.merge_from_list(["MT.START_MT", "'soon'"])
+    # (v) freeze makes assignment raise; clone deep-copies and keeps the frozen flag
+    c.freeze()
+    with pytest.raises(AttributeError):
+        c.MT.LAMBDA = 1.0
+    d = c.clone()
+    d.defrost()
+    d.MT.LAMBDA = 1.0
+    assert c.MT.LAMBDA == 5.0 and d.MT.LAMBDA == 1.0
+    # (vi) `if cfg.MODEL.RELATION_MASK:` on a node is always truthy (reference mask_head.py:48)
+    assert bool(c.MODEL.RELATION_MASK)
+
+
+def test_boxlist_contract():
+    from mmt_psm_b200.structures.bounding_box import BoxList
+    from mmt_psm_b200.structures.boxlist_ops import boxlist_iou, cat_boxlist
+    b = BoxList(torch.tensor([[10., 20., 29., 59.], [0., 0., 99., 49.]]), (100, 60), "xyxy")
+    b.add_field("labels", torch.tensor([1, 2]))
+    assert b.area().tolist() == [20. * 40., 100. * 50.]                     # legacy +1 extents
+    w = b.convert("xywh")
+    assert w.bbox.tolist() == [[10., 20., 20., 40.], [0., 0., 100., 50.]]
+    assert torch.equal(w.convert("xyxy").bbox, b.bbox)
+    f = b.transpose(0)                                                       # horizontal flip: x' = W - x - 1
+    assert f.bbox.tolist() == [[70., 20., 89., 59.], [0., 0., 99., 49.]]
+    assert torch.equal(f.transpose(0).bbox, b.bbox)
+    s = b[torch.tensor([1])]
+    assert len(s) == 1 and s.get_field("labels").tolist() == [2] and s.size == (100, 60)
+    c = cat_boxlist([b, s])
+    assert len(c) == 3 and c.get_field("labels").tolist() == [1, 2, 2]
+    iou = boxlist_iou(b, s)
+    assert abs(float(iou[1, 0]) - 1.0) < 1e-7 and 0 < float(iou[0, 0]) < 1
+    with pytest.raises(ValueError):
+        BoxList(torch.zeros(3, 5), (10, 10))
+    clipped = BoxList(torch.tensor([[-5., -5., 120., 70.]]), (100, 60)).clip_to_image(remove_empty=False)
+    assert clipped.bbox.tolist() == [[0., 0., 99., 59.]]
+
+
+def test_loss_weighting_and_ramps():
+    from mmt_psm_b200.engine.MTtrainer import weight_sum_losses
+    from mmt_psm_b200.utils.miscellaneous import sigmoid_rampdown, sigmoid_rampup
+    losses = {"loss_classifier": torch.tensor(2.0), "mt_classifier": torch.tensor(3.0), "mt_fg_loss": torch.tensor(4.0)}
+    bal = {"mt_classifier": 0.2, "nms_loss": 1.0, "mt_fg_loss": 1.0}
+    # plateau: keys containing 'mt' x lambda, then the per-term balance (reference MTtrainer.py:67-109)
+    out = weight_sum_losses(losses, 5000, 250, 250, 10 ** 6, l=5.0, balanced=bal, start_mt=1000)
+    assert float(out["loss_classifier"]) == 2.0
+    assert abs(float(out["mt_classifier"]) - 3.0 * 5.0 * 0.2) < 1e-6 and abs(float(out["mt_fg_loss"]) - 20.0) < 1e-6
+    # ramp-up right after START_MT
+    out = weight_sum_losses(losses, 1100, 250, 250, 10 ** 6, l=5.0, balanced=bal, start_mt=1000)
+    w = 5.0 * sigmoid_rampup(100, 250)
+    assert abs(float(out["mt_fg_loss"]) - 4.0 * w) < 1e-5 and w < 5.0
+    # ramp-down near the end uses the ramp-UP length (reference quirk, MTtrainer.py:92)
+    out = weight_sum_losses(losses, 999900, 250, 400, 10 ** 6, l=5.0, balanced=bal, start_mt=1000)
+    assert abs(float(out["mt_fg_loss"]) - 4.0 * 5.0 * sigmoid_rampdown(100, 250)) < 1e-5
+    assert sigmoid_rampup(0, 250) == pytest.approx(math.exp(-5.0)) and sigmoid_rampup(250, 250) == 1.0
+
+
+def test_warmup_multistep_lr():
+    from mmt_psm_b200.solver import WarmupMultiStepLR
+
+    class Opt(object):
+        base_lr = 0.02
+
+        def set_lr(self, lr):
+            self.lr = lr
+    o = Opt()
+    s = WarmupMultiStepLR(o, (30, 40), gamma=0.1, warmup_factor=1.0 / 3, warmup_iters=10, warmup_method="linear")
+    assert o.lr == pytest.approx(0.02 / 3)                       # last_epoch 0
+    for _ in range(5):
+        s.step()
+    assert o.lr == pytest.approx(0.02 * (1 / 3 * 0.5 + 0.5))     # half-way through the linear warm-up
+    for _ in range(10):
+        s.step()
+    assert o.lr == pytest.approx(0.02)
+    for _ in range(20):
+        s.step()
+    assert o.lr == pytest.approx(0.002)                          # epoch 35: one milestone passed
+    with pytest.raises(ValueError):
+        WarmupMultiStepLR(o, (40, 30))
+
+
+def test_registry_and_model_surface():
+    from mmt_psm_b200.config.presets import mt_psm_cfg
+    from mmt_psm_b200.modeling import registry
+    from mmt_psm_b200.modeling.detector import build_detection_model, reference_state_dict
+    assert "R-50-FPN" in registry.BACKBONES and "SingleConvRPNHead" in registry.RPN_HEADS
+    assert "FPN2MLPFeatureExtractor" in registry.ROI_BOX_FEATURE_EXTRACTORS
+    cfg = mt_psm_cfg(start_mt=0)
+    m = build_detection_model(cfg, is_student=True)
+    sd = reference_state_dict(m)
+    # the reference's state-dict names and layouts at the boundary (OIHW convs, [out, in] linears, IOHW deconv)
+    assert tuple(sd["backbone.body.stem.conv1.weight"].shape) == (64, 3, 7, 7)
+    assert tuple(sd["backbone.body.layer1.0.conv1.weight"].shape) == (64, 64, 1, 1)
+    assert tuple(sd["backbone.fpn.fpn_layer1.weight"].shape) == (256, 256, 3, 3)
+    assert tuple(sd["rpn.head.cls_logits.weight"].shape) == (3, 256, 1, 1)
+    assert tuple(sd["box_heads.box.feature_extractor.fc6.weight"].shape) == (1024, 256 * 7 * 7)
+    assert tuple(sd["mask_heads.mask.predictor.conv5_mask.weight"].shape) == (256, 256, 2, 2)
+    assert tuple(sd["hint_adaptor.adapter_1.weight"].shape) == (128, 256, 1, 1)
+    frozen = [n for n, p in m.named_parameters() if not p.requires_grad]
+    assert any(n.startswith("backbone.body.stem") for n in frozen) and any(n.startswith("backbone.body.layer1") for n in frozen)
+    assert not any(n.startswith("backbone.body.layer2") for n in frozen)          # FREEZE_CONV_BODY_AT = 2
+
+
+def test_synthetic_batch_contract():
+    from mmt_psm_b200.data.synthetic import make_batch
+    images, targets, views = make_batch(7, batch=2, size=128, n_views=3, n_cyto=3, n_nuc=2)
+    assert tuple(images.shape) == (2, 3, 128, 128) and images.dtype == torch.float32
+    assert len(views) == 3 and all(tuple(v.shape) == (2, 3, 128, 128) for v in views)
+    for t in targets:
+        assert len(t) == 5 and t.mode == "xyxy" and t.size == (128, 128)
+        assert sorted(t.get_field("labels").tolist()) == [1, 1, 1, 2, 2]
+        assert len(t.get_field("masks").polygons) == 5
+        b = t.bbox
+        assert (b[:, 2] > b[:, 0]).all() and (b[:, 3] > b[:, 1]).all() and b.min() >= 0 and b.max() <= 127
+    again = make_batch(7, batch=2, size=128, n_views=3, n_cyto=3, n_nuc=2)
+    assert torch.equal(images, again[0]) and torch.equal(views[2], again[2][2])   # seeded: identical on every machine

@@ -191,6 +191,23 @@ int mmt_roi_pool_backward_f32(const float* grad_output, const int* argmax, const
                               int channels, int height, int width, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Colour views of unlabeled crops (reference data/transforms/build.py:27-35 `transpart2`,
+ * transforms.py:84-206, data/datasets/Pap.py:818-831): AdjustBrightness -> AdjustContrast -> AdjustHue -> RandomErasing ->
+ * ToTensor -> Normalize(BGR255 - mean), bit-exact with the Pillow / torchvision arithmetic of the host pipeline.
+ * images_hwc [batch, H, W, 3] uint8 RGB (device); per (view, image) row-major [n_views * batch]: brightness / contrast
+ * factors (fp32), hue_shift (int: uint8 wrap-around amount, trunc(hue_factor * 255) mod 256).
+ * mmt_color_luma_sums_u8: luma_sums_out[v*batch+b] = sum over pixels of L of the brightness-adjusted image (the contrast
+ * pivot is int(sum / pixels + 0.5)).  mmt_color_views_u8: views_out [n_views, batch, 3, H, W] fp32 (channels B, G, R);
+ * erase_rects = device array of n_rects records {int view*batch+image, top, left, h, w; int64 fill_offset} applied in
+ * order, fill_pool = uint8 [h*w*3] blocks (the host draws rectangles and noise: the reference's random stream). */
+int mmt_color_luma_sums_u8(const unsigned char* images_hwc, const float* brightness, int n_views, int batch, int height,
+                           int width, unsigned long long* luma_sums_out, void* stream);
+int mmt_color_views_u8(const unsigned char* images_hwc, const float* brightness, const float* contrast,
+                       const int* hue_shift, const unsigned long long* luma_sums, int n_views, int batch, int height,
+                       int width, const void* erase_rects, int n_rects, const unsigned char* fill_pool, float mean_b,
+                       float mean_g, float mean_r, float* views_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * RPN loss (reference modeling/rpn/loss.py:138-196) over the fused head maps of all pyramid levels, in place:
  * fused_levels[l] = [n_images, level_pixels[l], padded_channels] fp32, channels [0, A) objectness logits of the A
  * anchors of a pixel, [A, 5A) their box deltas (host array of device pointers).  labels [n_images * sum(pixels*A)]

@@ -367,6 +367,49 @@ def sigmoid_focal_loss_backward(logits, targets, d_losses, num_classes, gamma, a
     return out
 
 
+# ---------------------------------------------------------------------------- colour views
+def color_views(images_u8, params, pixel_mean):
+    """images_u8 CUDA uint8 [B,H,W,3]; params[v][b] = dict(brightness, contrast, hue, rects=[(top, left, fill[h,w,3])]).
+    Returns a list over views of fp32 [B,3,H,W] (BGR * 255 - mean), bit-exact with the reference's PIL pipeline."""
+    import numpy as np
+    _need_cuda(images_u8)
+    L = _l.lib()
+    assert images_u8.dtype == torch.uint8 and images_u8.is_contiguous() and images_u8.shape[-1] == 3
+    B, H, W, _ = images_u8.shape
+    V = len(params)
+    dev = images_u8.device
+    flat = [p for view in params for p in view]
+    assert len(flat) == V * B
+    br = torch.tensor([p["brightness"] for p in flat], dtype=torch.float32).to(dev)
+    ct = torch.tensor([p["contrast"] for p in flat], dtype=torch.float32).to(dev)
+    hs = torch.tensor([int(np.trunc(p["hue"] * 255.0)) % 256 for p in flat], dtype=torch.int32).to(dev)
+    rec, pool, off = [], [], 0
+    for vb, p in enumerate(flat):
+        for top, left, fill in p["rects"]:
+            h, w = fill.shape[:2]
+            if h == 0 or w == 0:
+                continue
+            rec.append((vb, int(top), int(left), int(h), int(w), off))
+            blk = np.ascontiguousarray(fill).astype(np.uint8).reshape(-1)   # numpy's float -> uint8 assignment: truncation
+            pool.append(blk)
+            off += blk.size
+    rects_dev = pool_dev = None
+    if rec:
+        arr = np.zeros(len(rec), dtype=np.dtype([("vb", "<i4"), ("top", "<i4"), ("left", "<i4"), ("h", "<i4"), ("w", "<i4"),
+                                                  ("pad", "<i4"), ("fill", "<i8")]))
+        for i, r in enumerate(rec):
+            arr[i] = (r[0], r[1], r[2], r[3], r[4], 0, r[5])
+        rects_dev = torch.from_numpy(arr.view(np.uint8).copy()).to(dev)
+        pool_dev = torch.from_numpy(np.concatenate(pool)).to(dev)
+    sums = torch.empty(V * B, dtype=torch.int64, device=dev)
+    out = torch.empty((V, B, 3, H, W), dtype=torch.float32, device=dev)
+    check(L.mmt_color_luma_sums_u8(_p(images_u8), _p(br), V, B, H, W, _p(sums), _stream()), "color_luma_sums")
+    mb, mg, mr = (float(m) for m in pixel_mean)
+    check(L.mmt_color_views_u8(_p(images_u8), _p(br), _p(ct), _p(hs), _p(sums), V, B, H, W, _p(rects_dev), len(rec),
+                               _p(pool_dev), mb, mg, mr, _p(out), _stream()), "color_views")
+    return [out[v] for v in range(V)]
+
+
 # -------------------------------------------------------------------------------- RPN loss
 def _rpn_level_tables(fused):
     n = len(fused)

@@ -62,6 +62,8 @@ _PROTOS = {
                                          c_int, P, P, P]),
     "mmt_roi_pool_backward_f32": (c_int, [P, P, P, c_int, c_int, c_int, P, c_int, c_int, c_int,
                                           c_int, P]),
+    "mmt_color_luma_sums_u8": (c_int, [P, P, c_int, c_int, c_int, c_int, P, P]),
+    "mmt_color_views_u8": (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, P, c_int, P, c_float, c_float, c_float, P, P]),
     "mmt_rpn_loss_forward_f32": (c_int, [POINTER(P), POINTER(c_int64), c_int, c_int, c_int, c_int, P, P, P, P, c_float, P, P]),
     "mmt_rpn_loss_backward_f32": (c_int, [POINTER(P), POINTER(P), POINTER(c_int64), c_int, c_int, c_int, c_int, P, P, P, P, c_float,
                                           P, P, P, P]),

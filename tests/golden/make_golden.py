@@ -303,9 +303,33 @@ def gen_step():
     print({k: float(v) for k, v in out.items() if v.ndim == 0})
 
 
+def gen_color_views():
+    """K + S colour views of one unlabeled crop through the REFERENCE's own transform classes
+    (data/transforms/transforms.py, `transpart2` of data/transforms/build.py:27-35), seeded python / numpy streams."""
+    import importlib.util
+    import random
+    from PIL import Image
+    spec = importlib.util.spec_from_file_location("ref_transforms", os.path.join(TREE, "maskrcnn_benchmark/data/transforms/transforms.py"))
+    T = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(T)          # by path: the package __init__ pulls openslide / slidingwindow
+    g = np.random.default_rng(42)
+    img = g.integers(0, 256, (72, 96, 3), dtype=np.uint8)
+    img[10:30, 20:60] = (img[10:30, 20:60] // 8) + 200          # a bright, low-saturation patch
+    img[40:60, 5:40, 1] = 0                                      # a saturated patch
+    part2 = T.Compose([T.AdjustBrightness(0.15), T.AdjustContrast(0.15), T.AdjustHue(0.05), T.RandomErasing(0.9),
+                       T.ToTensor(), T.Normalize(mean=[102.9801, 115.9465, 122.7717], std=[1., 1., 1.], to_bgr255=True)])
+    random.seed(5)
+    np.random.seed(5)
+    views = []
+    for _ in range(3):
+        out, _ = part2(Image.fromarray(img.copy(), "RGB"), None)
+        views.append(out.numpy())
+    save("color_views", image=img, views=np.stack(views), seed=5)
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
-    which = sys.argv[1:] or ["nms", "roi_align", "psm", "mgd", "ema", "glue", "mask_targets", "step"]
+    which = sys.argv[1:] or ["nms", "roi_align", "psm", "mgd", "ema", "glue", "mask_targets", "step", "color_views"]
     if "nms" in which: gen_nms()
     if "roi_align" in which: gen_roi_align()
     if "psm" in which: gen_psm()
@@ -314,3 +338,4 @@ if __name__ == "__main__":
     if "glue" in which: gen_glue()
     if "mask_targets" in which: gen_mask_targets()
     if "step" in which: gen_step()
+    if "color_views" in which: gen_color_views()

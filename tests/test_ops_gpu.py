@@ -277,6 +277,40 @@ def test_elementwise_vs_torch(cuda):
     assert torch.equal(K().nhwc_to_nchw(K().nchw_to_nhwc(a)), a)
 
 
+# ----------------------------------------------------------------------------- colour views
+def test_color_views_bit_exact(cuda):
+    """mmt_color_views_u8 == the reference's host pipeline: (1) the golden views produced by the reference's own
+    transform classes, with the parameters re-drawn from the same seeds; (2) the oracle on a batch of two larger
+    random crops x 3 views with erase rectangles, including saturated / grey / black pixels.  Bit-exact."""
+    import random
+    from mmt_psm_b200.data.unlabeled_views import colour_views, draw_view_params
+    from oracle import color_ref as C
+    g = golden("color_views")
+    img = g["image"]
+    random.seed(int(g["seed"]))
+    np.random.seed(int(g["seed"]))
+    params = [[draw_view_params(img.shape[0], img.shape[1])] for _ in range(g["views"].shape[0])]
+    views = colour_views(torch.from_numpy(img)[None].to(cuda), params)
+    for v, out in enumerate(views):
+        assert np.array_equal(out[0].cpu().numpy(), g["views"][v]), v
+    rng = np.random.default_rng(3)
+    batch = rng.integers(0, 256, (2, 150, 210, 3), dtype=np.uint8)
+    batch[0, :20] = 0
+    batch[0, 20:40] = 255
+    batch[1, :30, :, :] = batch[1, :30, :, :1]                # grey rows (s == 0)
+    batch[1, 60:90, :, 2] = 0
+    random.seed(11)
+    np.random.seed(11)
+    params = [[draw_view_params(150, 210) for _ in range(2)] for _ in range(3)]
+    params[1][0]["brightness"], params[2][1]["hue"] = 1.15, -0.05
+    views = colour_views(torch.from_numpy(batch).to(cuda), params)
+    for v in range(3):
+        for b in range(2):
+            p = params[v][b]
+            ref = C.colour_view(batch[b], p["brightness"], p["contrast"], p["hue"], p["rects"])
+            assert np.array_equal(views[v][b].cpu().numpy(), ref), (v, b)
+
+
 # --------------------------------------------------------------------------------- RPN loss
 def test_rpn_loss_fused_matches_reference_formula(cuda):
     """functional.rpn_loss over fused per-level head maps == the reference's formula (rpn/loss.py:138-196: BCE with

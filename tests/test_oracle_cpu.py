@@ -139,3 +139,39 @@ def test_focal_oracle_vs_torchvision():
             onehot[i, c - 1] = 1
     ref = tvo.sigmoid_focal_loss(x.double(), onehot.double(), alpha=0.25, gamma=2.0, reduction="none")
     np.testing.assert_allclose(mine.numpy(), ref.numpy(), rtol=1e-9, atol=1e-12)
+
+
+def test_color_oracle_matches_pillow_and_reference_views():
+    """oracle/color_ref.py: (1) its RGB <-> HSV restatement equals Pillow's on a quarter of all 2^24 colours (offsets
+    cover every residue) and on every (h, s, v) the hue shift can produce; (2) brightness / contrast / hue equal
+    torchvision's PIL ops (the reference's `tf.adjust_*` call path); (3) the whole view pipeline, with parameters
+    drawn in the reference's order from seeded python / numpy streams, equals the reference's own transform classes
+    (tests/golden/color_views.npz), bit for bit."""
+    import importlib.util
+    import random
+    from PIL import Image
+    import torchvision.transforms.functional as tf
+    from conftest import ROOT
+    from oracle import color_ref as C
+    idx = np.arange(1, 1 << 24, 4, dtype=np.int64) + (np.arange((1 << 24) // 4) % 4) - 1
+    cube = np.stack([(idx >> 16) & 255, (idx >> 8) & 255, idx & 255], -1).astype(np.uint8).reshape(2048, 2048, 3)
+    assert np.array_equal(C.rgb_to_hsv(cube), np.array(Image.fromarray(cube, "RGB").convert("HSV")))
+    assert np.array_equal(C.hsv_to_rgb(cube), np.array(Image.fromarray(cube, "HSV").convert("RGB")))
+    g = golden("color_views")
+    img = g["image"]
+    pil = Image.fromarray(img, "RGB")
+    for f in (0.85, 0.97, 1.0, 1.15):
+        assert np.array_equal(C.adjust_brightness(img, f), np.array(tf.adjust_brightness(pil, f)))
+        assert np.array_equal(C.adjust_contrast(img, f), np.array(tf.adjust_contrast(pil, f)))
+    for h in (-0.05, -0.017, 0.0, 0.033, 0.05):
+        assert np.array_equal(C.adjust_hue(img, h), np.array(tf.adjust_hue(pil, h)))
+    spec = importlib.util.spec_from_file_location("uv_params", os.path.join(ROOT, "mmt-psm_b200", "data", "unlabeled_views.py"))
+    src = open(spec.origin).read().replace("from .. import kernels as K", "K = None")
+    ns = {}
+    exec(compile(src, spec.origin, "exec"), ns)          # the parameter drawing only: no CUDA needed
+    random.seed(int(g["seed"]))
+    np.random.seed(int(g["seed"]))
+    for v in range(g["views"].shape[0]):
+        p = ns["draw_view_params"](img.shape[0], img.shape[1])
+        out = C.colour_view(img, p["brightness"], p["contrast"], p["hue"], p["rects"])
+        assert np.array_equal(out, g["views"][v]), v

@@ -311,6 +311,45 @@ def test_color_views_bit_exact(cuda):
             assert np.array_equal(views[v][b].cpu().numpy(), ref), (v, b)
 
 
+def test_unlabeled_dataset_and_device_collator(cuda):
+    """UnlabeledCrops + DeviceViewCollator == the reference's unlabeled item pipeline (transpart1 on the host, aug_k x
+    transpart2, zero-padded collation) restated with PIL + the oracle, for a same-size and a ragged batch."""
+    import random
+    from PIL import Image
+    import torchvision.transforms.functional as tf
+    from mmt_psm_b200.data.unlabeled import DeviceViewCollator, UnlabeledCrops, reference_resize_size
+    from mmt_psm_b200.data.unlabeled_views import draw_view_params
+    from oracle import color_ref as C
+    assert reference_resize_size(1000, 1000, 800, 1333) == (800, 800)
+    assert reference_resize_size(2000, 1000, 800, 1333) == (666, 1332)      # the long side caps the scale
+    rng = np.random.default_rng(8)
+    for shapes in ([(100, 120)] * 2, [(100, 120), (90, 150)]):
+        crops = [rng.integers(0, 256, (h, w, 3), dtype=np.uint8) for h, w in shapes]
+        ds = UnlabeledCrops(crops, min_size=64, max_size=120, aug_k=3)
+        random.seed(3)
+        np.random.seed(3)
+        views, idx = DeviceViewCollator(cuda, size_divisible=32)([ds[i] for i in range(len(crops))])
+        random.seed(3)
+        np.random.seed(3)
+        ref_items = []
+        for c in crops:   # the reference's order of draws: flip, then per view the colour parameters and rectangles
+            img = Image.fromarray(c, "RGB")
+            img = tf.resize(img, reference_resize_size(img.size[0], img.size[1], 64, 120))
+            if random.random() < 0.5:
+                img = tf.hflip(img)
+            a = np.array(img)
+            ref_items.append([C.colour_view(a, **{k: v for k, v in p.items()}) for p in
+                              [draw_view_params(a.shape[0], a.shape[1]) for _ in range(3)]])
+        assert idx == tuple(range(len(crops))) and len(views) == 3
+        for k in range(3):
+            v = views[k].cpu().numpy()
+            assert v.shape[2] % 32 == 0 and v.shape[3] % 32 == 0
+            for b, item in enumerate(ref_items):
+                r = item[k]
+                assert np.array_equal(v[b, :, :r.shape[1], :r.shape[2]], r), (k, b)
+                assert not v[b, :, r.shape[1]:, :].any() and not v[b, :, :, r.shape[2]:].any()   # zero padding
+
+
 # --------------------------------------------------------------------------------- RPN loss
 def test_rpn_loss_fused_matches_reference_formula(cuda):
     """functional.rpn_loss over fused per-level head maps == the reference's formula (rpn/loss.py:138-196: BCE with

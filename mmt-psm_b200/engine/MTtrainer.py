@@ -209,8 +209,13 @@ class MTtrainer(object):
         self.student.train()
         self.teacher.eval()
         t0 = end = time.time()
+        iteration = self.start_iter
         for iteration, (data_s, target_s, _) in enumerate(self.dataloader_s, self.start_iter):
-            losses_dict, losses = self.train_step(iteration, data_s, target_s)
+            data_u = None
+            if (self.dataloader_u is not None and iteration > self.start_mt and self.lambda_value > 0
+                    and self.n_step_unlabel == 1):
+                data_u, _ = self._next_unlabeled()   # fetched up front so that its trunks can be prefetched
+            losses_dict, losses = self.train_step(iteration, data_s, target_s, data_u)
             if iteration % 20 == 0 or iteration == self.max_iter:  # the only host syncs of the loop
                 red = reduce_loss_dict(losses_dict)
                 meters.update(loss=sum(v for v in red.values()), **red)
@@ -222,8 +227,7 @@ class MTtrainer(object):
                     torch.cuda.max_memory_allocated() / 1024.0 / 1024.0))
             if iteration % self.checkpoint_period == 0:
                 self.save_model(iteration)
-            if iteration == self.max_iter:
-                self.save_model(final=True)
+        self.save_model(iteration + 1, final=True)
         total = time.time() - t0
         self.logger.info("Total training time: %s (%.4f s / it)" % (datetime.timedelta(seconds=total), total / max(self.max_iter, 1)))
 
@@ -231,10 +235,10 @@ class MTtrainer(object):
         if self.ckpt_s is None:
             return
         if iteration > 0 and not final:
-            self.ckpt_s.save("model_{:07d}".format(iteration))
+            self.ckpt_s.save("model_{:07d}".format(iteration), iteration=iteration)
             if iteration > self.start_mt:
-                self.ckpt_t.save("t_model_{:07d}".format(iteration))
+                self.ckpt_t.save("t_model_{:07d}".format(iteration), iteration=iteration)
         if final:
-            self.ckpt_s.save("model_final")
+            self.ckpt_s.save("model_final", iteration=iteration)
             if iteration > self.start_mt:
-                self.ckpt_t.save("t_model_final")
+                self.ckpt_t.save("t_model_final", iteration=iteration)

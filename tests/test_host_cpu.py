@@ -140,3 +140,37 @@ def test_synthetic_batch_contract():
         assert (b[:, 2] > b[:, 0]).all() and (b[:, 3] > b[:, 1]).all() and b.min() >= 0 and b.max() <= 127
     again = make_batch(7, batch=2, size=128, n_views=3, n_cyto=3, n_nuc=2)
     assert torch.equal(images, again[0]) and torch.equal(views[2], again[2][2])   # seeded: identical on every machine
+
+
+def test_checkpoint_roundtrip_reference_layout(tmp_path):
+    """save -> load restores weights bit for bit through the reference-layout boundary; the file holds the reference's
+    key names / layouts; `last_checkpoint` resumes; scheduler state travels."""
+    from mmt_psm_b200.config.presets import mt_psm_cfg
+    from mmt_psm_b200.modeling.detector import build_detection_model
+    from mmt_psm_b200.solver import WarmupMultiStepLR
+    from mmt_psm_b200.utils.checkpoint import DetectronCheckpointer
+    from mmt_psm_b200.utils.synthetic_init import init_model
+    cfg = mt_psm_cfg(start_mt=0)
+    a = build_detection_model(cfg, is_student=True)
+    init_model(a, 3)
+
+    class Opt(object):
+        base_lr = 0.01
+
+        def set_lr(self, lr):
+            self.lr = lr
+    sched = WarmupMultiStepLR(Opt(), (30, 40))
+    for _ in range(7):
+        sched.step()
+    ck = DetectronCheckpointer(cfg, a, None, sched, str(tmp_path), True)
+    path = ck.save("model_0000007", iteration=7)
+    raw = torch.load(path, map_location="cpu", weights_only=False)
+    assert tuple(raw["model"]["backbone.body.stem.conv1.weight"].shape) == (64, 3, 7, 7)       # OIHW in the file
+    assert raw["iteration"] == 7 and raw["scheduler"]["last_epoch"] == 7
+    b = build_detection_model(cfg, is_student=True)
+    sched_b = WarmupMultiStepLR(Opt(), (30, 40))
+    extra = DetectronCheckpointer(cfg, b, None, sched_b, str(tmp_path), True).load()            # via last_checkpoint
+    assert extra["iteration"] == 7 and sched_b.last_epoch == 7
+    sa, sb = a.state_dict(), b.state_dict()
+    assert all(torch.equal(sa[k], sb[k]) for k in sa if "cell_anchors" not in k)
+    assert DetectronCheckpointer(cfg, b, save_dir=str(tmp_path / "empty"), save_to_disk=True).load() == {}

@@ -31,6 +31,8 @@ def main():
     ap.add_argument("--synthetic", action="store_true", help="train on the seeded synthetic crop stream")
     ap.add_argument("--init-weights", default="", help="reference-layout .pth to start both networks from")
     ap.add_argument("--no-graphs", action="store_true")
+    ap.add_argument("--preset", default="", choices=["", "train_mt"],
+                    help="train_mt: apply the option list of the reference's scripts/train_mt.sh (IR-Net off) before KEY VAL")
     ap.add_argument("opts", nargs=argparse.REMAINDER, default=None)
     args = ap.parse_args()
 
@@ -53,6 +55,9 @@ def main():
     rank = dist.get_rank() if world > 1 else 0
     if args.config_file:
         cfg.merge_from_file(args.config_file)
+    if args.preset == "train_mt":
+        from mmt_psm_b200.config import TRAIN_MT_OVERRIDES
+        cfg.merge_from_list(TRAIN_MT_OVERRIDES + ["MODEL.RELATION_NMS.USE_RELATION_NMS", False])
     cfg.merge_from_list(args.opts or [])
     cfg.freeze()
     logging.basicConfig(level=logging.INFO if rank == 0 else logging.WARNING, format="%(asctime)s %(name)s: %(message)s")

@@ -1,50 +1,55 @@
-"""Smoothed meters (reference utils/metric_logger.py:8-66)."""
-from collections import defaultdict, deque
-
-import torch
+"""Windowed training meters behind the trainer's log line (`loss: 1.8430 (1.9021)  time: 0.0301 (0.0304)`):
+`MetricLogger.update(name=value, ...)`, attribute access to a meter, `str()` = name: window median (run average).
+Same surface as the reference's utils/metric_logger.py; values stay Python floats (no tensor round trips)."""
+import collections
+import statistics
 
 
 class SmoothedValue(object):
+    """Last `window_size` values plus the running sum / count of everything seen."""
+
     def __init__(self, window_size=20):
-        self.deque = deque(maxlen=window_size)
-        self.total, self.count = 0.0, 0
+        self.window = collections.deque(maxlen=window_size)
+        self.total = 0.0
+        self.count = 0
 
     def update(self, value):
-        self.deque.append(value)
-        self.count += 1
+        value = float(value)
+        self.window.append(value)
         self.total += value
+        self.count += 1
 
     @property
     def median(self):
-        return torch.tensor(list(self.deque)).median().item()
+        return statistics.median(self.window) if self.window else 0.0
 
     @property
     def avg(self):
-        return torch.tensor(list(self.deque)).mean().item()
+        return sum(self.window) / len(self.window) if self.window else 0.0
 
     @property
     def global_avg(self):
-        return self.total / max(self.count, 1)
+        return self.total / self.count if self.count else 0.0
 
 
 class MetricLogger(object):
     def __init__(self, delimiter="\t"):
-        self.meters = defaultdict(SmoothedValue)
         self.delimiter = delimiter
+        self.meters = collections.defaultdict(SmoothedValue)
 
-    def update(self, **kwargs):
-        for k, v in kwargs.items():
-            if isinstance(v, torch.Tensor):
-                v = v.item()
-            assert isinstance(v, (float, int))
-            self.meters[k].update(v)
+    def update(self, **named_values):
+        for name, value in named_values.items():
+            if hasattr(value, "item"):      # 0-dim tensor
+                value = value.item()
+            if not isinstance(value, (int, float)):
+                raise TypeError("meter %s: expected a number, got %s" % (name, type(value).__name__))
+            self.meters[name].update(value)
 
-    def __getattr__(self, attr):
-        if attr in self.meters:
-            return self.meters[attr]
-        if attr in self.__dict__:
-            return self.__dict__[attr]
-        raise AttributeError("'%s' object has no attribute '%s'" % (type(self).__name__, attr))
+    def __getattr__(self, name):
+        meters = self.__dict__.get("meters", {})
+        if name in meters:
+            return meters[name]
+        raise AttributeError("%s has no meter or attribute %r" % (type(self).__name__, name))
 
     def __str__(self):
-        return self.delimiter.join("%s: %.4f (%.4f)" % (n, m.median, m.global_avg) for n, m in self.meters.items())
+        return self.delimiter.join("%s: %.4f (%.4f)" % (k, m.median, m.global_avg) for k, m in self.meters.items())

@@ -41,8 +41,10 @@ def synthetic_state_dict(shapes, seed=0, adaptor_scale=None):
             t = base * (torch.rand(shape, generator=g) * 0.2 + 0.9)
         elif leaf == "bias":
             t = torch.randn(shape, generator=g) * 0.01
+            if name.endswith("relation_nms.classifier.bias"):
+                t = t + 0.5                              # a trained IoU regressor answers ~0.5 on real objects (FG_THREAD 0.1)
         elif leaf == "weight" and len(shape) == 4:
-            if "conv5_mask" in name:                     # ConvTranspose IOHW: fan_in = in channels
+            if ("conv5_mask" in name and "appearance_feature_extractor" not in name) or "deconv_1" in name:  # ConvTranspose IOHW
                 fan_in = shape[0]
             else:
                 fan_in = shape[1] * shape[2] * shape[3]

@@ -327,6 +327,116 @@ def gen_color_views():
     save("color_views", image=img, views=np.stack(views), seed=5)
 
 
+def relation_cfg():
+    """cfg of configs/pap/e2e_mask_rcnn_R_50_FPN_1x.yaml + scripts/train_mt.sh with both IR-Net modules on (BASELINE config 4)."""
+    c = cfg.clone()
+    c.merge_from_file(os.path.join(TREE, "configs/pap/e2e_mask_rcnn_R_50_FPN_1x.yaml"))
+    c.merge_from_list(MT_OPTS + ["MODEL.RELATION_NMS.USE_RELATION_NMS", True, "MODEL.RELATION_MASK.USE_RELATION", True,
+                                 "MODEL.RELATION_NMS.REG_IOU", True, "MODEL.RELATION_NMS.REG_IOU_MSK", False,
+                                 "MODEL.RELATION_NMS.LOSS", 1., "MODEL.ROI_BOX_HEAD.DO", 0.0])
+    return c
+
+
+def _relation_inputs(g, n, n_gt, size):
+    """ROIs scattered around n_gt ground-truth boxes (several near-duplicates per object), head outputs and RPN objectness."""
+    from maskrcnn_benchmark.structures.bounding_box import BoxList
+    ctr = torch.rand(n_gt, 2, generator=g) * (size - 80) + 40
+    wh = torch.rand(n_gt, 2, generator=g) * 50 + 14
+    gt = torch.cat([ctr - wh / 2, ctr + wh / 2], 1).clamp(0, size - 1)
+    gl = torch.randint(1, 3, (n_gt,), generator=g)
+    own = torch.randint(0, n_gt, (n,), generator=g)
+    rois = (gt[own] + torch.randn(n, 4, generator=g) * 5).clamp(0, size - 1)
+    rois[:, 2:] = torch.max(rois[:, 2:], rois[:, :2] + 4)
+    far = torch.rand(n, generator=g) < 0.25                       # a quarter of the ROIs are background
+    rois[far] = clustered_boxes(g, int(far.sum()), float(size))
+    logits = torch.randn(n, 3, generator=g)
+    logits[~far, 0] -= 1.5
+    logits[torch.arange(n)[~far], gl[own][~far]] += 2.0
+    reg = torch.randn(n, 12, generator=g) * 0.4
+    x = torch.relu(torch.randn(n, 1024, generator=g)).half().float()   # stored as fp16
+    obj = torch.rand(n, generator=g)
+    props = BoxList(rois, (size, size))
+    props.add_field("objectness", obj)
+    target = BoxList(gt, (size, size))
+    target.add_field("labels", gl)
+    return x, props, torch.softmax(logits, 1), reg, target
+
+
+def gen_relation():
+    """The reference's IR-Net modules on their own (modeling/relation/relation_module.py DuplicationRemovalNetwork,
+    mask_relation_module.py MaskRelationRefineNet), train and eval mode, synthetic weights keyed like the detector's."""
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    import mmt_psm_b200  # noqa: F401
+    from mmt_psm_b200.utils.synthetic_init import synthetic_state_dict
+    from maskrcnn_benchmark.modeling.relation.relation_module import DuplicationRemovalNetwork
+    from maskrcnn_benchmark.modeling.relation.mask_relation_module import MaskRelationRefineNet
+    from maskrcnn_benchmark.structures.bounding_box import BoxList
+    c = relation_cfg()
+    out = {}
+    g = torch.Generator().manual_seed(77)
+
+    net = DuplicationRemovalNetwork(c)
+    pre = "relation_nms."
+    sd = synthetic_state_dict({pre + k: tuple(v.shape) for k, v in net.state_dict().items()}, 0)
+    net.load_state_dict({k[len(pre):]: v for k, v in sd.items()})
+    for tag, n, n_gt in (("a", 120, 14), ("b", 50, 9)):          # more / fewer ROIs than FIRST_N = 90
+        x, props, prob, reg, target = _relation_inputs(g, n, n_gt, 256)
+        if tag == "b":
+            target = target[target.get_field("labels") == 1]     # one class without any ground truth
+        for k, v in (("x", x.half()), ("rois", props.bbox), ("obj", props.get_field("objectness")), ("prob", prob), ("reg", reg),
+                     ("gt", target.bbox), ("gt_labels", target.get_field("labels"))):
+            out["nms_%s_%s" % (tag, k)] = v.numpy()
+        net.train()
+        xr = x.clone().requires_grad_(True)
+        _, loss = net((xr, [props], prob, reg, [target]))
+        loss["nms_loss"].backward()
+        out["nms_%s_loss" % tag] = loss["nms_loss"].detach().numpy()
+        out["nms_%s_dx" % tag] = xr.grad.numpy()
+        out["nms_%s_dclassifier" % tag] = net.classifier.weight.grad.clone().numpy()
+        out["nms_%s_dWG" % tag] = net.relation_module.WG.weight.grad.clone().numpy()
+        net.zero_grad()
+        with torch.no_grad():
+            ranked = net.prepare_ranking(prob, reg, [props], [target], reg_iou=True)[0]
+        out["nms_%s_sorted_idx" % tag] = ranked.get_field("sorted_idx").numpy()
+        out["nms_%s_reg_label" % tag] = ranked.get_field("labels_iou_reg").numpy()
+        net.eval()
+        with torch.no_grad():
+            res, _ = net((x, [props], prob, reg, [None]))
+        r = res[0]
+        for f in ("scores", "objectness", "all_scores", "labels"):
+            out["nms_%s_det_%s" % (tag, f)] = r.get_field(f).numpy()
+        out["nms_%s_det_bbox" % tag] = r.bbox.numpy()
+        print("relation nms", tag, float(loss["nms_loss"]), "detections", len(r))
+
+    mnet = MaskRelationRefineNet(c, None)
+    pre = "mask_heads.mask.mask_relation_module."
+    sd = synthetic_state_dict({pre + k: tuple(v.shape) for k, v in mnet.state_dict().items()}, 0)
+    mnet.load_state_dict({k[len(pre):]: v for k, v in sd.items()})
+    mnet.train()
+    for tag, P in (("a", 14), ("b", 4)):
+        f = torch.relu(torch.randn(P, 256, 14, 14, generator=g)).half().float()   # stored as fp16
+        m = torch.randn(P, 3, 28, 28, generator=g) * 2
+        boxes = clustered_boxes(g, P, 256.0)
+        labels = torch.randint(1, 3, (P,), generator=g) if tag == "a" else torch.full((P,), 2, dtype=torch.int64)
+        obj = torch.rand(P, generator=g)
+        obj[::4] = 1.0                                            # ground-truth boxes join the proposals with objectness 1
+        p = BoxList(boxes, (256, 256))
+        p.add_field("labels", labels)
+        p.add_field("objectness", obj)
+        fr = f.clone().requires_grad_(True)
+        mr = m.clone().requires_grad_(True)
+        logits2, sp, _, _ = mnet((fr, mr, p, None))
+        wsum = torch.randn(logits2.shape, generator=g)
+        (logits2 * wsum).sum().backward()
+        for k, v in (("f", f.half()), ("m", m), ("boxes", boxes), ("labels", labels), ("obj", obj), ("logits2", logits2.detach()),
+                     ("sorted_boxes", sp[0].bbox), ("sorted_labels", sp[0].get_field("labels")), ("w", wsum),
+                     ("df_sum", fr.grad.sum((2, 3))), ("dm", mr.grad), ("dgamma", mnet.relation_module.gamma.grad.clone())):
+            out["msk_%s_%s" % (tag, k)] = v.numpy()
+        mnet.zero_grad()
+        print("relation mask", tag, tuple(logits2.shape), float(logits2.abs().mean()))
+    save("relation", **out)
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
     which = sys.argv[1:] or ["nms", "roi_align", "psm", "mgd", "ema", "glue", "mask_targets", "step", "color_views"]
@@ -339,3 +449,4 @@ if __name__ == "__main__":
     if "mask_targets" in which: gen_mask_targets()
     if "step" in which: gen_step()
     if "color_views" in which: gen_color_views()
+    if "relation" in which: gen_relation()

@@ -175,3 +175,61 @@ def test_color_oracle_matches_pillow_and_reference_views():
         p = ns["draw_view_params"](img.shape[0], img.shape[1])
         out = C.colour_view(img, p["brightness"], p["contrast"], p["hue"], p["rects"])
         assert np.array_equal(out, g["views"][v]), v
+
+
+def _gold_t(g, k):
+    a = g[k]
+    return torch.from_numpy(a.astype(np.float32) if a.dtype == np.float16 else a)
+
+
+def test_relation_nms_oracle_matches_reference():
+    """IR-Net duplicate removal (reference relation_module.py): ranking, IoU-regression labels, loss + gradients and the
+    eval-mode detections, bit-exact against the patched reference's module on seeded inputs (golden relation.npz)."""
+    from oracle import relation_ref as RR
+    from mmt_psm_b200.utils.synthetic_init import synthetic_state_dict
+    g = golden("relation")
+    cfg = RR.RelationCfg()
+    sd = synthetic_state_dict(RR.nms_weight_shapes(), 0)
+    for tag in "ab":
+        a = {k: _gold_t(g, "nms_%s_%s" % (tag, k)) for k in ("x", "prob", "reg", "rois", "obj", "gt", "gt_labels")}
+        x = a["x"].requires_grad_(True)
+        for v in sd.values():
+            v.requires_grad_(True)
+            v.grad = None
+        loss, ranked = RR.relation_nms_loss(sd, RR.NMS_PREFIX, cfg, x, a["prob"], a["reg"], a["rois"], a["obj"], (256, 256),
+                                            a["gt"], a["gt_labels"])
+        loss.backward()
+        assert np.array_equal(ranked["idx"].numpy(), g["nms_%s_sorted_idx" % tag])
+        assert np.array_equal(ranked["labels_reg"].numpy(), g["nms_%s_reg_label" % tag])
+        assert (g["nms_%s_reg_label" % tag] > 0).sum() >= 2
+        np.testing.assert_allclose(loss.item(), g["nms_%s_loss" % tag], rtol=1e-6)
+        np.testing.assert_allclose(x.grad.numpy(), g["nms_%s_dx" % tag], rtol=1e-5, atol=1e-9)
+        np.testing.assert_allclose(sd[RR.NMS_PREFIX + "relation_module.WG.weight"].grad.numpy(), g["nms_%s_dWG" % tag],
+                                   rtol=1e-5, atol=1e-8)
+        det = RR.relation_nms_detect({k: v.detach() for k, v in sd.items()}, RR.NMS_PREFIX, cfg, x.detach(), a["prob"],
+                                     a["reg"], a["rois"], a["obj"], (256, 256))
+        assert len(det["labels"]) > 10
+        for f in ("bbox", "scores", "labels", "objectness", "all_scores"):
+            assert np.array_equal(det[f].numpy(), g["nms_%s_det_%s" % (tag, f)]), f
+
+
+def test_relation_mask_oracle_matches_reference():
+    """IR-Net mask refinement (reference mask_relation_module.py, CIAM): refined logits, row order and gradients."""
+    from oracle import relation_ref as RR
+    from mmt_psm_b200.utils.synthetic_init import synthetic_state_dict
+    g = golden("relation")
+    sd = synthetic_state_dict(RR.mask_weight_shapes(), 0)
+    for tag in "ab":
+        f = _gold_t(g, "msk_%s_f" % tag).requires_grad_(True)
+        m = _gold_t(g, "msk_%s_m" % tag).requires_grad_(True)
+        for v in sd.values():
+            v.requires_grad_(True)
+            v.grad = None
+        out, order = RR.mask_relation(sd, RR.MASK_PREFIX, f, m, _gold_t(g, "msk_%s_labels" % tag), _gold_t(g, "msk_%s_obj" % tag))
+        (out * _gold_t(g, "msk_%s_w" % tag)).sum().backward()
+        np.testing.assert_allclose(out.detach().numpy(), g["msk_%s_logits2" % tag], rtol=1e-5, atol=1e-6)
+        assert np.array_equal(g["msk_%s_boxes" % tag][order.numpy()], g["msk_%s_sorted_boxes" % tag])
+        assert np.array_equal(g["msk_%s_labels" % tag][order.numpy()], g["msk_%s_sorted_labels" % tag])
+        np.testing.assert_allclose(m.grad.numpy(), g["msk_%s_dm" % tag], rtol=1e-4, atol=1e-6)
+        np.testing.assert_allclose(f.grad.sum((2, 3)).numpy(), g["msk_%s_df_sum" % tag], rtol=1e-4, atol=1e-4)
+        np.testing.assert_allclose(sd[RR.MASK_PREFIX + "relation_module.gamma"].grad.numpy(), g["msk_%s_dgamma" % tag], rtol=1e-4)

@@ -130,6 +130,9 @@ def get_cfg_defaults():
 # `scripts/train_mt.sh` overrides (reference scripts/train_mt.sh:4-20) — the configuration the headline
 # metric is quoted on, as a KEY VAL list for merge_from_list.
 TRAIN_MT_OVERRIDES = [
+    "MODEL.RELATION_NMS.WEIGHT", 1., "MODEL.RELATION_NMS.ALPHA", 0., "MODEL.RELATION_NMS.LOSS", 1.,
+    "MODEL.RELATION_NMS.D_LOSS", 0., "MODEL.RELATION_NMS.GAMMA", 1., "MODEL.RELATION_NMS.REG_IOU", True,
+    "MODEL.RELATION_NMS.REG_IOU_MSK", False,
     "MT.ALPHA", 0.99, "MT.ALPHA_RAMPUP", 0.99, "MT.LAMBDA", 5., "MT.RAMPUP_STEP", 250, "MT.RAMPDOWN_STEP", 250,
     "MT.TEMP", 0.5, "MT.SHARPEN", True, "MT.START_MT", 1000, "MT.AUG_S", 1, "MT.CLS_LOSS_TYPE", "bce",
     "SOLVER.IMS_PER_BATCH", 4, "MT.CLS_LOSS", 0.2, "MT.MEAN_TARGET", True, "MT.FLIP", True, "MT.CONF_PAIR", True,

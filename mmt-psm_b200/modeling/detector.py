@@ -10,6 +10,7 @@ Internally every feature map is NHWC.  Two result-preserving restructurings of t
     same tensor twice: generalized_rcnn.py:127 and :204; frozen BN makes both passes identical).
 """
 import torch
+import torch.nn.functional as F
 from torch import nn
 
 from .. import functional as Fk
@@ -17,6 +18,7 @@ from ..structures.image_list import ImageList, to_image_list
 from .backbone import build_backbone
 from .box_head import MaskRCNNFPNAdaptor, build_roi_box_head
 from .mask_head import build_roi_mask_head
+from .relation import DuplicationRemovalNetwork
 from .rpn import build_rpn
 
 
@@ -65,10 +67,7 @@ class GeneralizedRCNN(nn.Module):
         self.rpn = build_rpn(cfg, is_teacher)
         self.box_heads = box_roi_heads(cfg)
         self.mask_heads = mask_roi_heads(cfg, is_student)
-        if cfg.MODEL.RELATION_NMS.USE_RELATION_NMS:
-            raise NotImplementedError("IR-Net duplicate removal (MODEL.RELATION_NMS.USE_RELATION_NMS) is a 'next' row "
-                                      "(SURVEY §8f-4); run with MODEL.RELATION_NMS.USE_RELATION_NMS False")
-        self.relation_nms = None
+        self.relation_nms = DuplicationRemovalNetwork(cfg, is_teacher) if cfg.MODEL.RELATION_NMS.USE_RELATION_NMS else None
         self.mt_fg_hint = cfg.MT.FG_HINT
         self.mt_cls = cfg.MT.CLS_LOSS
         self.hint_adaptor = MaskRCNNFPNAdaptor(cfg)
@@ -279,6 +278,8 @@ class GeneralizedRCNN(nn.Module):
     def set_module_mode(self, mode):
         self.rpn.set_teacher_mode(mode)
         self.box_heads.box.set_teacher_mode(mode)
+        if self.relation_nms is not None:
+            self.relation_nms.set_teacher_mode(mode)
         self.mask_heads.mask.set_teacher_mode(mode)
 
     # ------------------------------------------------------------------------------ supervised
@@ -292,11 +293,22 @@ class GeneralizedRCNN(nn.Module):
         features = _features
         proposals, proposal_losses = self.rpn(images, features, targets, head_out=_rpn_head)
         x, result, losses, class_logits, box_regression = self.box_heads(features, proposals, targets)
+        nms_loss = None
+        if self.relation_nms is not None:
+            # IR-Net duplicate removal on the box head's ROIs (reference generalized_rcnn.py:63-95, one image per call
+            # there; every image is its own attention problem, so the whole batch goes through in one call here):
+            # training adds `nms_loss`, eval replaces the greedy-NMS detections the mask head and the teacher consume
+            nms_result, nms_loss = self.relation_nms((x, result, F.softmax(class_logits, dim=1), box_regression,
+                                                      targets if targets is not None else [None] * len(result)))
+            if not self.training:
+                result = nms_result
         result, detector_losses = self.mask_heads(losses, features, result, targets, images)
         if self.training:
             out = {}
             out.update(detector_losses)
             out.update(proposal_losses)
+            if nms_loss is not None:
+                out.update(nms_loss)
             return out
         return result
 

@@ -1,7 +1,8 @@
 """Mask head: FPN feature extractor (4x conv3x3), C4 predictor (deconv 2x2 + 1x1), loss, post-processing.
 
 Mirrors reference modeling/roi_heads/mask_head/{mask_head.py:16-156, roi_mask_feature_extractors.py:91-146,
-roi_mask_predictors.py:9-36, loss.py:37-180, inference.py:14-266} with IR-Net (RELATION_MASK) off.  B200
+roi_mask_predictors.py:9-36, loss.py:37-180, inference.py:14-266}; with MODEL.RELATION_MASK.USE_RELATION the IR-Net
+refinement branch (modeling/relation.py) adds its deeply-supervised second set of logits.  B200
 differences: all convs are tcgen05 launches on NHWC ROI tiles; mask TARGETS are rasterised on the device
 (`mmt_rasterize_polygons_f32`) instead of the per-ROI pycocotools loop on the host; the teacher's
 Masker paste loop (one 800x800 CPU canvas per detection) is one paste-and-sum kernel producing the integral
@@ -202,10 +203,14 @@ class ROIMaskHead(nn.Module):
     def __init__(self, cfg, is_student=False):
         super().__init__()
         self.cfg = cfg.clone()
-        if cfg.MODEL.RELATION_MASK.USE_RELATION:
-            raise NotImplementedError("IR-Net (MODEL.RELATION_MASK.USE_RELATION) is a 'next' row (SURVEY §8f-4)")
         self.feature_extractor = make_roi_mask_feature_extractor(cfg)
         self.predictor = make_roi_mask_predictor(cfg)
+        # the reference builds the refinement net whenever the RELATION_MASK node exists (mask_head.py:48, always);
+        # its parameters only matter with USE_RELATION, so it is only built (and held in HBM / the optimizer) then
+        self.mask_relation_module = None
+        if cfg.MODEL.RELATION_MASK.USE_RELATION:
+            from .relation import MaskRelationRefineNet
+            self.mask_relation_module = MaskRelationRefineNet(cfg, self.predictor)
         self.post_processor = make_roi_mask_post_processor(cfg)
         self.mask_generator = make_roi_mask_generator(cfg)
         self.loss_evaluator = make_roi_mask_loss_evaluator(cfg)
@@ -220,13 +225,20 @@ class ROIMaskHead(nn.Module):
             proposals, positive_inds = keep_only_positive_boxes(proposals)
         x, _ = self.feature_extractor(features, proposals)
         mask_logits = self.predictor(x)
+        loss_seg = self.loss_evaluator(proposals, mask_logits, targets) if self.training else None
+        if self.mask_relation_module is not None:
+            # IR-Net: second set of logits from instance-to-instance attention, rows re-ordered per image by
+            # (class, objectness) — all images in one pass (reference mask_head.py:96-124 loops over images)
+            mask_logits, proposals = self.mask_relation_module.refine(x, mask_logits, proposals)
         if not self.training:
             if self.mode is None or self.mode == "train":
                 result = self.post_processor(mask_logits, proposals)
             else:
                 result = self.mask_generator(mask_logits, proposals)
             return x, result, {}
-        loss_seg = self.loss_evaluator(proposals, mask_logits, targets)
+        if self.mask_relation_module is not None:
+            loss_2 = self.loss_evaluator(proposals, mask_logits, targets)
+            loss_seg = 0.5 * (loss_seg + loss_2) if self.cfg.MODEL.RELATION_MASK.DEEP_SUPER else loss_2
         return x, all_proposals, dict(loss_seg=loss_seg)
 
 

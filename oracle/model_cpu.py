@@ -17,7 +17,7 @@ import torch
 import torch.nn.functional as F
 import torchvision.ops as tvops
 
-from . import ops_ref, polygon_ref
+from . import ops_ref, polygon_ref, relation_ref
 
 BELOW, BETWEEN = -1, -2
 
@@ -150,6 +150,9 @@ class Cfg(object):
     warmup_factor, warmup_iters, steps, gamma = 1.0 / 3, 500, (5000,), 0.1
     freeze_at = 2
     aug_k, aug_s = 2, 1
+    relation = False          # IR-Net modules (BASELINE config 4): MODEL.RELATION_NMS.USE_RELATION_NMS + RELATION_MASK.USE_RELATION
+    relation_cfg = relation_ref.RelationCfg
+    nms_loss_w = 1.0          # MODEL.RELATION_NMS.LOSS (train_mt.sh)
 
 
 class Net(object):
@@ -232,13 +235,41 @@ class Net(object):
         return (F.linear(x, self.sd[p + "cls_score.weight"], self.sd[p + "cls_score.bias"]),
                 F.linear(x, self.sd[p + "bbox_pred.weight"], self.sd[p + "bbox_pred.bias"]))
 
-    def mask_logits(self, feats, boxes_per_img):  # roi_mask_feature_extractors.py:131-146, roi_mask_predictors.py:34-36
+    def mask_logits(self, feats, boxes_per_img, with_features=False):  # roi_mask_feature_extractors.py:131-146, roi_mask_predictors.py:34-36
         x = self.pool(feats, boxes_per_img, 14)
         for i in range(1, 5):
             x = F.relu(self.conv(x, "mask_heads.mask.feature_extractor.mask_fcn%d" % i, 1, 1))
         p = "mask_heads.mask.predictor."
-        x = F.relu(F.conv_transpose2d(x, self.sd[p + "conv5_mask.weight"], self.sd[p + "conv5_mask.bias"], 2))
-        return self.conv(x, p + "mask_fcn_logits")
+        y = F.relu(F.conv_transpose2d(x, self.sd[p + "conv5_mask.weight"], self.sd[p + "conv5_mask.bias"], 2))
+        y = self.conv(y, p + "mask_fcn_logits")
+        return (x, y) if with_features else y
+
+    def refine_masks(self, x, ml, boxes, labels, obj):  # mask_head.py:96-124 (IR-Net branch, per image)
+        """Per-image CIAM refinement; returns (refined logits, boxes, labels) with every image's rows re-ordered by
+        (class, objectness) as the reference's sorted proposals are."""
+        n = [len(b) for b in boxes]
+        out, nb, nl = [], [], []
+        for xi, mi, b, l, o in zip(x.split(n), ml.split(n), boxes, labels, obj):
+            if len(b) == 0:
+                out.append(mi); nb.append(b); nl.append(l)
+                continue
+            lg, order = relation_ref.mask_relation(self.sd, relation_ref.MASK_PREFIX, xi, mi, l, o, self.cfg.num_classes - 1)
+            out.append(lg); nb.append(b[order]); nl.append(l[order])
+        return torch.cat(out), nb, nl
+
+    def seg_loss(self, ml, posb, targets):  # mask_head/loss.py:118-180
+        tl, tm = [], []
+        for pb, t in zip(posb, targets):
+            m = match(box_iou(t["bbox"], pb), self.cfg.roi_fg, self.cfg.roi_bg, False)
+            lab = t["labels"][m.clamp(min=0)].to(torch.int64)
+            lab[m == BELOW] = 0
+            pi = torch.nonzero(lab > 0).squeeze(1)
+            inst = [t["polygons"][int(i)] for i in m[pi]]
+            tm.append(torch.from_numpy(polygon_ref.project_masks_on_boxes_ref(inst, pb[pi].numpy(), self.cfg.mask_res)))
+            tl.append(lab)
+        tl, tm = torch.cat(tl), torch.cat(tm)
+        pi = torch.nonzero(tl > 0).squeeze(1)
+        return F.binary_cross_entropy_with_logits(ml[pi, tl[pi]], tm) if tm.numel() else ml.sum() * 0
 
     def adaptors(self, feats):
         return [self.conv(feats[i], "hint_adaptor.adapter_%d" % (i + 1)) for i in range(5)]
@@ -330,9 +361,9 @@ class Net(object):
             regt.append(encode(g[m.clamp(min=0)], b, self.cfg.box_w))
         pos, neg = sample(labels, self.cfg.roi_batch, self.cfg.roi_pos)
         out = []
-        for (b, _), lab, rt, p, n in zip(props, labels, regt, pos, neg):
+        for (b, _), lab, rt, p, n in zip(props, labels, regt, pos, neg):   # `_` = RPN objectness (1 for appended GT boxes)
             idx = torch.nonzero(p | n).squeeze(1)
-            out.append(dict(bbox=b[idx], labels=lab[idx], regt=rt[idx]))
+            out.append(dict(bbox=b[idx], labels=lab[idx], regt=rt[idx], obj=_[idx]))
         return out
 
     def detections(self, cls, reg, props, image_sizes):  # box_head/inference.py:36-145
@@ -382,22 +413,24 @@ class Net(object):
         pos = torch.nonzero(labels > 0).squeeze(1)
         mi = 4 * labels[pos][:, None] + torch.tensor([0, 1, 2, 3])
         l_box = smooth_l1(br[pos[:, None], mi], regt[pos], 1.0) / labels.numel()
+        out = {}
+        if self.cfg.relation:  # generalized_rcnn.py:63-95: IR-Net duplicate removal, one image per call
+            n = [len(s["bbox"]) for s in samp]
+            prob = F.softmax(cls, 1)
+            per = [relation_ref.relation_nms_loss(self.sd, relation_ref.NMS_PREFIX, self.cfg.relation_cfg, xi, pi_, ri, s["bbox"],
+                                                  s["obj"], (isz[1], isz[0]), t["bbox"], t["labels"])[0]
+                   for xi, pi_, ri, s, isz, t in zip(x.split(n), prob.split(n), br.split(n), samp, image_sizes, targets)]
+            out["nms_loss"] = torch.mean(torch.stack(per))
         # mask head on positives (mask_head.py:74-150, loss.py:118-180)
         posb = [s["bbox"][s["labels"] > 0] for s in samp]
-        ml = self.mask_logits(feats, posb)
-        tl, tm = [], []
-        for pb, t in zip(posb, targets):
-            m = match(box_iou(t["bbox"], pb), self.cfg.roi_fg, self.cfg.roi_bg, False)
-            lab = t["labels"][m.clamp(min=0)].to(torch.int64)
-            lab[m == BELOW] = 0
-            pi = torch.nonzero(lab > 0).squeeze(1)
-            inst = [t["polygons"][int(i)] for i in m[pi]]
-            tm.append(torch.from_numpy(polygon_ref.project_masks_on_boxes_ref(inst, pb[pi].numpy(), self.cfg.mask_res)))
-            tl.append(lab)
-        tl, tm = torch.cat(tl), torch.cat(tm)
-        pi = torch.nonzero(tl > 0).squeeze(1)
-        l_seg = F.binary_cross_entropy_with_logits(ml[pi, tl[pi]], tm) if tm.numel() else ml.sum() * 0
-        return dict(loss_classifier=l_cls, loss_box_reg=l_box, loss_seg=l_seg, loss_objectness=l_obj, loss_rpn_box_reg=l_rpn)
+        mx, ml = self.mask_logits(feats, posb, with_features=True)
+        l_seg = self.seg_loss(ml, posb, targets)
+        if self.cfg.relation:  # mask_head.py:96-150, DEEP_SUPER
+            ml2, sb, _ = self.refine_masks(mx, ml, posb, [s["labels"][s["labels"] > 0] for s in samp],
+                                           [s["obj"][s["labels"] > 0] for s in samp])
+            l_seg = 0.5 * (l_seg + self.seg_loss(ml2, sb, targets))
+        out.update(loss_classifier=l_cls, loss_box_reg=l_box, loss_seg=l_seg, loss_objectness=l_obj, loss_rpn_box_reg=l_rpn)
+        return out
 
     # ---- teacher (generalized_rcnn.py:117-167) --------------------------------------------------------
     @torch.no_grad()
@@ -411,8 +444,19 @@ class Net(object):
         props = self.proposals(pla, obj, reg, image_sizes, c.pre_test, c.post_test, c.fpn_post_test, False)
         x = self.box_feat(f0, [b for b, _ in props], False)
         cls, br = self.box_pred(x)
-        dets = self.detections(cls, br, props, image_sizes)
-        ml = self.mask_logits(f0, [d["bbox"] for d in dets]).sigmoid()
+        if c.relation:  # the box head hands its raw ROIs to the duplicate-removal network (box_head.py:55-58)
+            n = [len(b) for b, _ in props]
+            prob = F.softmax(cls, 1)
+            dets = [relation_ref.relation_nms_detect(self.sd, relation_ref.NMS_PREFIX, c.relation_cfg, xi, pi_, ri, b, o, (sz[1], sz[0]))
+                    for xi, pi_, ri, (b, o), sz in zip(x.split(n), prob.split(n), br.split(n), props, image_sizes)]
+            mx, ml = self.mask_logits(f0, [d["bbox"] for d in dets], with_features=True)
+            ml, sb, sl = self.refine_masks(mx, ml, [d["bbox"] for d in dets], [d["labels"] for d in dets],
+                                           [d["objectness"] for d in dets])
+            dets = [dict(bbox=b, labels=l) for b, l in zip(sb, sl)]
+            ml = ml.sigmoid()
+        else:
+            dets = self.detections(cls, br, props, image_sizes)
+            ml = self.mask_logits(f0, [d["bbox"] for d in dets]).sigmoid()
         labels = torch.cat([d["labels"] for d in dets])
         prob = ml[torch.arange(len(labels)), labels].split([len(d["bbox"]) for d in dets])
         integral = torch.stack([paste_sum(p, d["bbox"], H, W) for p, d in zip(prob, dets)])
@@ -433,7 +477,7 @@ class Net(object):
             fb[:, 0], fb[:, 2] = W - b[:, 2] - 1, W - b[:, 0] - 1
             flipped.append(fb)
         logits = [self.box_pred(self.box_feat(f, boxes if i % 2 == 0 else flipped, False))[0] for i, f in enumerate(aug)]
-        return dict(samples=samp, class_logit_t=logits, embedding=emb, seg_mask=integral)
+        return dict(samples=samp, class_logit_t=logits, embedding=emb, seg_mask=integral, dets=dets)
 
     # ---- student on the unlabeled view (generalized_rcnn.py:170-199) -----------------------------------
     def forward_student(self, image, t):
@@ -504,7 +548,7 @@ class Trainer(object):
             losses.update(self.student.forward_student(views[-1], t))
         self.last_epoch += 1
         w = self.mt_weight(iteration)
-        bal = {"mt_classifier": c.cls_w, "mt_fg_loss": c.fg_w}
+        bal = {"mt_classifier": c.cls_w, "mt_fg_loss": c.fg_w, "nms_loss": c.nms_loss_w}
         weighted = {k: (v * w if "mt" in k else v) * bal.get(k, 1.0) for k, v in losses.items()}
         total = sum(weighted.values())
         for k in self.student.trainable:

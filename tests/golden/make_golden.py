@@ -437,6 +437,57 @@ def gen_relation():
     save("relation", **out)
 
 
+def gen_step_relation():
+    """As gen_step with both IR-Net modules on (BASELINE config 4 = what the reference's yaml + train_mt.sh select):
+    supervised step with nms_loss and the deeply-supervised refined mask loss, teacher whose coarse inference goes through
+    the duplicate-removal network and the mask refinement, student-unlabeled losses."""
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    import mmt_psm_b200  # noqa: F401
+    from mmt_psm_b200.data.synthetic import make_batch
+    from mmt_psm_b200.utils.synthetic_init import synthetic_state_dict
+    from maskrcnn_benchmark.modeling.detector import build_detection_model
+    from maskrcnn_benchmark.structures.bounding_box import BoxList
+    from maskrcnn_benchmark.structures.segmentation_mask import SegmentationMask
+    c = relation_cfg()
+    student = build_detection_model(c, is_student=True)
+    teacher = build_detection_model(c, is_teacher=True)
+    sd = synthetic_state_dict({k: tuple(v.shape) for k, v in student.state_dict().items()}, 0)
+    for m in (student, teacher):
+        missing, unexpected = m.load_state_dict(sd, strict=False)
+        assert not unexpected and all("cell_anchors" in k for k in missing), missing
+    size = 256
+    images, targets, views = make_batch(1234, 2, size, 3, 6, 6)
+    rt = []
+    for t in targets:
+        b = BoxList(t.bbox, t.size, "xyxy")
+        b.add_field("labels", t.get_field("labels"))
+        b.add_field("masks", SegmentationMask([[p.tolist() for p in inst.polygons] for inst in t.get_field("masks").polygons], t.size))
+        rt.append(b)
+    student.train()
+    teacher.eval()
+    torch.manual_seed(7)
+    sup = student(images, rt)
+    out = {"sup_" + k: v.detach().numpy() for k, v in sup.items()}
+    with torch.no_grad():
+        infer = teacher(views[0].clone())
+        out["infer_n"] = np.array([len(b) for b in infer])
+        out["infer_labels"] = torch.cat([b.get_field("labels") for b in infer]).numpy()
+        out["infer_boxes"] = torch.cat([b.bbox for b in infer]).numpy()
+        out["infer_scores"] = torch.cat([b.get_field("scores") for b in infer]).numpy()
+        torch.manual_seed(11)
+        tr = teacher.forward_teacher([views[0].clone(), views[1].clone()])
+    mt = student.forward_student([views[2].clone()], tr)
+    out.update({"mt_" + k: v.detach().numpy() for k, v in mt.items()})
+    out["t_n_rois"] = np.array([len(b) for b in tr["result_t"]])
+    out["t_labels"] = torch.cat([b.get_field("labels") for b in tr["result_t"]]).numpy()
+    out["t_boxes"] = torch.cat([b.bbox for b in tr["result_t"]]).numpy()
+    out["t_logits"] = torch.stack(tr["class_logit_t"]).numpy()
+    out["t_seg_mask_sum"] = np.array([float(m.sum()) for m in tr["seg_mask"]])
+    out["t_seg_mask"] = np.packbits(torch.stack(tr["seg_mask"]).numpy() > 0)
+    save("step_relation", size=size, **out)
+    print({k: float(v) for k, v in out.items() if v.ndim == 0}, out["infer_n"], out["t_n_rois"])
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
     which = sys.argv[1:] or ["nms", "roi_align", "psm", "mgd", "ema", "glue", "mask_targets", "step", "color_views"]
@@ -450,3 +501,4 @@ if __name__ == "__main__":
     if "step" in which: gen_step()
     if "color_views" in which: gen_color_views()
     if "relation" in which: gen_relation()
+    if "step_relation" in which: gen_step_relation()

@@ -4,7 +4,7 @@
 unlabeled fwd+bwd with PSM + MGD, [NCCL all-reduce of the student gradient arena], fused SGD + teacher EMA)
 on synthetic 1000x1000 two-class crops (-> 800x800 after the reference's Resize), per-GPU batch 2 labeled + 2 unlabeled.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload mt|sup]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload mt|sup|mt_relation]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
 
@@ -38,7 +38,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="mt", choices=["mt", "sup"])
+    ap.add_argument("--workload", default="mt", choices=["mt", "sup", "mt_relation"],
+                    help="mt = BASELINE config 3 (the headline), sup = config 2, mt_relation = config 4 (IR-Net modules on)")
     ap.add_argument("--size", type=int, default=SIZE, help="network input size (800 = reference Resize of a 1000 crop)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
@@ -67,6 +68,9 @@ def ncu_traffic():
 
 
 def workload_name(args):
+    if args.workload == "mt_relation":
+        return ("MMT-PSM mean-teacher + IR-Net (RELATION_NMS + RELATION_MASK on; MT.AUG_K=2, AUG_S=1, LAMBDA=5), R50-FPN, "
+                "per-GPU 2 labeled + 2 unlabeled crops x 3 views, %dx%d" % (args.size, args.size))
     if args.workload == "mt":
         return ("MMT-PSM mean-teacher (MT.AUG_K=2, AUG_S=1, LAMBDA=5, CLS_LOSS=0.2, FG_HINT=1, relation off), R50-FPN, "
                 "per-GPU 2 labeled + 2 unlabeled crops x 3 views, %dx%d" % (args.size, args.size))
@@ -119,7 +123,7 @@ class ClockSampler(object):
 
 
 # ------------------------------------------------------------------------------------- CPU reference
-def build_oracle_trainer(size):
+def build_oracle_trainer(size, relation=False):
     """The oracle's restatement of the reference trainer (TEST INFRASTRUCTURE; the CPU arm only)."""
     import torch
     import mmt_psm_b200  # noqa: F401
@@ -128,13 +132,14 @@ def build_oracle_trainer(size):
     from mmt_psm_b200.modeling.detector import build_detection_model, reference_state_dict
     from mmt_psm_b200.utils.synthetic_init import synthetic_state_dict
     from oracle import model_cpu
-    c = mt_psm_cfg(start_mt=0)
+    c = mt_psm_cfg(start_mt=0, relation=relation)
     m = build_detection_model(c, is_student=True)
     shapes = {k: tuple(v.shape) for k, v in reference_state_dict(m).items()}
     del m
     sd = synthetic_state_dict(shapes, 0)
     oc = model_cpu.Cfg()
     oc.start_mt = 0
+    oc.relation = relation
     trainer = model_cpu.Trainer(sd, oc)
     trainer.last_epoch = 2000
     images, targets, views = make_batch(1234, BATCH, size, 3, 20, 20)
@@ -149,8 +154,8 @@ def time_cpu_reference(args, steps, warmup):
     import torch
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    trainer, images, tg, views = build_oracle_trainer(args.size)
-    use_views = views if args.workload == "mt" else None
+    trainer, images, tg, views = build_oracle_trainer(args.size, relation=args.workload == "mt_relation")
+    use_views = views if args.workload in ("mt", "mt_relation") else None
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
@@ -208,8 +213,8 @@ def run_ours(args):
     from mmt_psm_b200.utils.synthetic_init import init_model
     lib.lib()
 
-    mt = args.workload == "mt"
-    cfg = mt_psm_cfg(start_mt=0) if mt else supervised_cfg()
+    mt = args.workload in ("mt", "mt_relation")
+    cfg = mt_psm_cfg(start_mt=0, relation=args.workload == "mt_relation") if mt else supervised_cfg()
     torch.manual_seed(0)
     student = build_detection_model(cfg, is_student=True).to(dev)
     teacher = build_detection_model(cfg, is_teacher=True).to(dev)

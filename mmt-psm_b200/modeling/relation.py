@@ -18,9 +18,11 @@ Same constructor arguments, parameter names and state-dict keys as the reference
   numpy's argmax and intersect1d's first occurrence;
 * eval mode selects survivors with the segmented on-device NMS (keep flags) and ONE read-back (the final row list) instead
   of nonzero + NMS (+ D2H) per class and image;
-* the 3x3 convs of the appearance extractor (257 -> 256 -> 256 -> 256 -> 16 @14x14) run on the tcgen05 conv engine over NHWC
-  ROI tiles (the 257-channel input and the 16-channel output are zero-padded to the engine's 32-channel granularity at
-  call time; the parameters keep the reference's shapes).
+* the 3x3 convs of the appearance extractor (257 -> 256 -> 256 -> 256 -> 16 @14x14) and the 1024 / 128-wide linears run on
+  the tcgen05 conv engine over NHWC ROI tiles (the 257-channel input and the 16-channel output are zero-padded to the
+  engine's 32-channel granularity at call time; the parameters keep the reference's shapes).  The layers narrower than
+  that granularity (WG 64 -> 16, the 128 -> 1 IoU classifier, the 16-channel deconv / 1x1 classifier of the mask branch,
+  < 0.1 GFLOP together) and the [N, N] attention products are plain fp32 matmuls.
 Only the configuration the repo's yaml + scripts/train_mt.sh select is built: USE_IOU False, CLASS_AGNOSTIC False,
 CLS_WISE_RELATION False, MERGE_METHOD >= 0; RELATION_MASK TYPE CIAM, FEATURE_EXTRACTOR RoiAlignMaskFeatureExtractor,
 EXTRACTOR_CHANNEL != 1, SAME_PREDICTOR False, NORM -1, PRE_NORM False.  Anything else raises at construction."""
@@ -108,7 +110,7 @@ class RelationModule(nn.Module):
         f = f_a.reshape(-1, N, C, D).transpose(1, 2).contiguous()                   # [B,C,N,D]
         B = f.shape[0]
         flat = f.view(B * C * N, D)
-        w_g = self.WG(position_embedding.reshape(-1, position_embedding.shape[-1]), relu=True)
+        w_g = F.relu(F.linear(position_embedding.reshape(-1, position_embedding.shape[-1]), self.WG.weight, self.WG.bias))
         w_g = w_g.view(B, C, N, N, G).permute(0, 1, 4, 2, 3)                        # [B,C,G,N,N]
         k = self.WK(flat).view(B, C, N, G, dk).permute(0, 1, 3, 4, 2)               # [B,C,G,dk,N]
         q = self.WQ(flat).view(B, C, N, G, dq).permute(0, 1, 3, 2, 4)               # [B,C,G,N,dq]
@@ -232,7 +234,8 @@ class DuplicationRemovalNetwork(nn.Module):
         feat = feat + rank[None, :, None, :]
         pos = extract_multi_position_matrix(torch.stack([q["boxes"] for q in ranked]), None, self.geo_feature_dim, 1000)
         feat = F.relu(feat + self.relation_module(feat, pos, None))
-        out = self.classifier(feat.reshape(-1, r.APPEARANCE_FEAT_DIM)).view(B, N, self.fg_class, len(self.target_thresh))
+        out = F.linear(feat.reshape(-1, r.APPEARANCE_FEAT_DIM), self.classifier.weight, self.classifier.bias)
+        out = out.view(B, N, self.fg_class, len(self.target_thresh))
         return out if self.reg_iou else torch.sigmoid(out)
 
     def forward(self, x):
@@ -432,8 +435,11 @@ class MaskRelationRefineNet(nn.Module):
         own = torch.sigmoid(mask_logits[order][rows, :, :, labels])                 # [P,28,28] own-class probability
         x = self.appearance_feature_extractor((features_roi[order], own[:, None]))
         x = self.relation_module(x, gid)
-        x = self.deconv_1(x, relu=True)
-        logits = self.classifier(x)
+        # ConvTranspose2d(ch, ch, 2, 2) + ReLU + 1x1 classifier on 16 channels: two small matmuls and a pixel shuffle
+        P, H, W, ch = x.shape
+        y = F.relu(torch.matmul(x, self.deconv_1.weight.view(4 * ch, ch).t()) + self.deconv_1.bias.repeat(4))
+        y = y.view(P, H, W, 2, 2, ch).permute(0, 1, 3, 2, 4, 5).reshape(P, 2 * H, 2 * W, ch)
+        logits = torch.matmul(y, self.classifier.weight.view(-1, ch).t()) + self.classifier.bias
         out, off = [], 0
         for p, n in zip(proposals, counts):
             out.append(p[order[off:off + n] - off])

@@ -7,7 +7,10 @@ the REFERENCE's layout, the same tensors on every machine (torch CPU generator s
 activations stay O(1): He-normal convs, frozen-BN scale 1 on the bottleneck's inner convs and the downsample (skip) branch, 0.25 on the
 residual-closing conv3, 1/64 on the stem (pixel range -> O(1)), and MGD adaptors at 0.1 x He (a trained student / teacher
 pair maps the views to nearby embeddings; with unit-scale random adaptors the un-normalised L2 hint loss starts at O(1) and
-SGD at the cfg learning rate diverges within 5 iterations — measured, profiles/r01_loss_trace_*.log).  Used by bench.py, smoke() and the step-level parity fixtures (the
+SGD at the cfg learning rate diverges within 5 iterations — measured, profiles/r01_loss_trace_*.log), and the IR-Net
+duplicate-removal head's ROI-feature embedding at 0.1 x (its IoU regressor is linear in the fc7 features, whose norm swings 2-8 x
+during the first iterations of a randomly initialised box head: at full scale nms_loss goes 0.1 -> 35 -> NaN in four
+iterations, at 0.1 x it decreases monotonically — profiles/r01_loss_trace_relation_cpu_v6.log).  Used by bench.py, smoke() and the step-level parity fixtures (the
 reference model is loaded with exactly the same dict)."""
 import math
 import os
@@ -62,6 +65,8 @@ def synthetic_state_dict(shapes, seed=0, adaptor_scale=None):
                 std = 0.01
             if "bbox_pred" in name:
                 std = 0.001
+            if "roi_feat_embedding_fc" in name:
+                std *= float(os.environ.get("MMT_SYNTH_RELATION_SCALE", "0.1"))   # see the module docstring (IR-Net head)
             t = torch.randn(shape, generator=g) * std
         else:
             t = torch.randn(shape, generator=g) * 0.01

@@ -229,11 +229,30 @@ def test_step_with_relation_matches_reference_golden(cuda, restore, math, tol_su
     kernels.set_conv_math(math)
     cfg, student, teacher, images, targets, views, g = _build(cuda)
     assert len(student.state_dict()) == 349          # every reference state-dict entry is built
+    seen = {}
+    hook = student.relation_nms.register_forward_pre_hook(lambda mod, inp: seen.update(x=inp[0]))
     torch.manual_seed(7)
     sup = student(images.to(cuda), [t.to(cuda) for t in targets])
-    for k in ("loss_classifier", "loss_box_reg", "loss_seg", "loss_objectness", "loss_rpn_box_reg", "nms_loss"):
+    hook.remove()
+    for k in ("loss_classifier", "loss_box_reg", "loss_seg", "loss_objectness", "loss_rpn_box_reg"):
         ref, got = float(g["sup_" + k]), float(sup[k])
         assert abs(got - ref) <= tol_sup * max(abs(ref), 1e-2), (math, k, got, ref)
+    # nms_loss hangs on DISCRETE choices made from near-tied numbers: the 90 best of 512 ROIs per class by a softmax score
+    # whose neighbours are an fp32 ulp apart (random-init classifier), and per ground truth the best-scored overlapping box
+    # — one flipped pair moves the loss by ~0.5 %.  So: (a) against the reference's number at a tolerance that allows a few
+    # flips, and (b) tightly against the oracle evaluated on the very tensors the module was handed in this run.
+    ref, got = float(g["sup_nms_loss"]), float(sup["nms_loss"])
+    assert abs(got - ref) <= (3e-2 if math == "fp32" else 1.5e-1) * ref, (math, "nms_loss", got, ref)
+    from mmt_psm_b200.modeling.detector import reference_state_dict
+    from oracle import relation_ref as RR
+    x, props, prob, reg, tg = seen["x"]
+    sd = {k: v.cpu() for k, v in reference_state_dict(student).items() if k.startswith(RR.NMS_PREFIX)}
+    n = [len(p) for p in props]
+    per = [RR.relation_nms_loss(sd, RR.NMS_PREFIX, RR.RelationCfg(), xi.detach().cpu(), pi.detach().cpu(), ri.detach().cpu(),
+                                p.bbox.cpu(), p.get_field("objectness").cpu(), p.size, t.bbox.cpu(), t.get_field("labels").cpu())[0]
+           for xi, pi, ri, p, t in zip(x.split(n), prob.split(n), reg.split(n), props, tg)]
+    same_inputs = float(torch.mean(torch.stack(per)))
+    assert abs(got - same_inputs) <= (2e-3 if math == "fp32" else 5e-2) * same_inputs, (math, got, same_inputs)
     sum(sup.values()).backward()                     # the relation branches are differentiable end to end
     for name in ("relation_nms.relation_module.WK.weight", "relation_nms.nms_rank_fc.weight",
                  "mask_heads.mask.mask_relation_module.appearance_feature_extractor.mask_fcn1.weight",
@@ -307,7 +326,9 @@ def test_full_training_step_with_relation_matches_oracle(cuda, restore):
         assert terr <= 2e-3 * upd + 1e-6, ("teacher", name, terr, upd)
         if "relation" in name:
             n_rel += 1
-            assert upd > 0, name                      # every relation parameter receives a gradient in this step
+            # every relation parameter receives a gradient in this step — except WK's bias: a shift common to all keys
+            # leaves every softmax row unchanged, its gradient is zero up to rounding
+            assert upd > 0 or name.endswith("WK.bias"), name
     assert n_rel == 27
     trainer.set_cuda_graphs(True)
     for it in range(6, 10):

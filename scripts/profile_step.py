@@ -25,7 +25,7 @@ if os.environ.get("MMT_CONV_MAX_CTAS"):
     from mmt_psm_b200 import lib as _lib
     _lib.check(_lib.lib().mmt_conv_set_max_ctas(int(os.environ["MMT_CONV_MAX_CTAS"])))
 QUICK = os.environ.get("MMT_PROFILE_QUICK") == "1"
-cfg = mt_psm_cfg(start_mt=0)
+cfg = mt_psm_cfg(start_mt=0, relation=os.environ.get("MMT_RELATION") == "1")   # MMT_RELATION=1: BASELINE config 4
 torch.manual_seed(0)
 student = build_detection_model(cfg, is_student=True).to(dev)
 teacher = build_detection_model(cfg, is_teacher=True).to(dev)

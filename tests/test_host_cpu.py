@@ -174,3 +174,4 @@ def test_checkpoint_roundtrip_reference_layout(tmp_path):
     sa, sb = a.state_dict(), b.state_dict()
     assert all(torch.equal(sa[k], sb[k]) for k in sa if "cell_anchors" not in k)
     assert DetectronCheckpointer(cfg, b, save_dir=str(tmp_path / "empty"), save_to_disk=True).load() == {}
+

@@ -78,7 +78,7 @@ def test_relation_embeddings_and_row_order_match_oracle():
     for g in gid.unique():
         rows = (gid == g).nonzero()[:, 0]
         ref = RR.ciam(x[rows].permute(0, 3, 1, 2).contiguous(), ciam.gamma.detach()).permute(0, 2, 3, 1)
-        assert torch.allclose(got[rows], ref, rtol=1e-5, atol=1e-5)
+        assert torch.allclose(got[rows], ref, rtol=1e-4, atol=1e-4)
 
 
 def test_relation_cfg_of_the_reference_yaml():

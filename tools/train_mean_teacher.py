@@ -4,12 +4,13 @@
 the B200 path: this package's cfg / models / FusedSGDEMA / MTtrainer, `torchrun` for multi-GPU.
 
     python tools/train_mean_teacher.py --config-file configs/pap/e2e_mask_rcnn_R_50_FPN_1x.yaml --synthetic \
-        SOLVER.MAX_ITER 200 MT.START_MT 20 MODEL.RELATION_NMS.USE_RELATION_NMS False OUTPUT_DIR runs/demo
+        SOLVER.MAX_ITER 200 MT.START_MT 20 OUTPUT_DIR runs/demo
 
 The reference's dataset classes are out of scope: `--synthetic` feeds the seeded synthetic crop stream the
-benchmark uses (labeled batches + unlabeled uint8 crops whose colour views are rendered on the device).  IR-Net
-(`MODEL.RELATION_NMS.USE_RELATION_NMS True`, which scripts/train_mt.sh sets) is a "next" row and is rejected by the model
-with a clear message.  `--init-weights FILE` loads a reference-layout checkpoint (e.g. e2e_mask_rcnn_R_50_FPN_1x.pth);
+benchmark uses (labeled batches + unlabeled uint8 crops whose colour views are rendered on the device).  The yaml and
+scripts/train_mt.sh switch the IR-Net modules on exactly as the reference's do (BASELINE config 4); append
+`MODEL.RELATION_NMS.USE_RELATION_NMS False MODEL.RELATION_MASK.USE_RELATION False` for the plain mean-teacher iteration the
+headline metric is quoted on (config 3).  `--init-weights FILE` loads a reference-layout checkpoint (e.g. e2e_mask_rcnn_R_50_FPN_1x.pth);
 without it the deterministic synthetic initialisation is used.  Resumes from OUTPUT_DIR/last_checkpoint."""
 import argparse
 import logging
@@ -32,7 +33,7 @@ def main():
     ap.add_argument("--init-weights", default="", help="reference-layout .pth to start both networks from")
     ap.add_argument("--no-graphs", action="store_true")
     ap.add_argument("--preset", default="", choices=["", "train_mt"],
-                    help="train_mt: apply the option list of the reference's scripts/train_mt.sh (IR-Net off) before KEY VAL")
+                    help="train_mt: apply the option list of the reference's scripts/train_mt.sh before KEY VAL")
     ap.add_argument("opts", nargs=argparse.REMAINDER, default=None)
     args = ap.parse_args()
 
@@ -57,7 +58,7 @@ def main():
         cfg.merge_from_file(args.config_file)
     if args.preset == "train_mt":
         from mmt_psm_b200.config import TRAIN_MT_OVERRIDES
-        cfg.merge_from_list(TRAIN_MT_OVERRIDES + ["MODEL.RELATION_NMS.USE_RELATION_NMS", False])
+        cfg.merge_from_list(TRAIN_MT_OVERRIDES + ["MODEL.RELATION_NMS.USE_RELATION_NMS", True])   # train_mt.sh:7
     cfg.merge_from_list(args.opts or [])
     cfg.freeze()
     logging.basicConfig(level=logging.INFO if rank == 0 else logging.WARNING, format="%(asctime)s %(name)s: %(message)s")

@@ -1,0 +1,117 @@
+"""Offline (no GPU): which convs of the iteration are starved for CTAs, and what split-K would buy.
+
+Reads the measured per-layer table (profiles/r01_conv_layers_v3.log: forward time at batch 2 and at the teacher's
+stacked batch 8) and applies the tile rule of csrc/conv_tc.cu (128-pixel x BN-channel tiles, BN from pick_bn, one
+persistent CTA per SM, 148 SMs).  Per layer: tiles, share of the SMs that have a tile, serial k-blocks per tile, the time
+the measured per-SM operand rate predicts (85 GB/s L2->SM per SM, 44 GB/s HBM share for the epilogue — the two numbers
+DESIGN §4 derives from ncu), and the same model with the K loop split across idle SMs (partial tiles reduced by TMA
+reduce-add, as the wgrad kernel already does).  A MODEL, printed next to the measurement it is calibrated on; the
+split-K column is the estimate that ranks round-2 work, not a result.
+
+    python scripts/conv_tile_model.py > profiles/r01_conv_tile_model_v6.md
+"""
+import math
+import os
+import re
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SMS, TILE_M, BK_BYTES = 148, 128, 128
+L2_SM, HBM_SM = 85e9, 44e9
+
+
+def pick_bn(m_tiles, n_out):
+    bn = 256
+    while bn > 32 and bn // 2 >= n_out:
+        bn //= 2
+    while bn > 64 and m_tiles * math.ceil(n_out / bn) * 2 <= SMS:
+        bn //= 2
+    return bn
+
+
+def model(B, H, Ci, Co, k, split=1):
+    pixels = B * H * H
+    m_tiles = math.ceil(pixels / TILE_M)
+    bn = pick_bn(m_tiles, Co)
+    tiles = m_tiles * math.ceil(Co / bn)
+    kblocks = k * k * Ci * 4 // BK_BYTES
+    split = max(1, min(split, kblocks))
+    per_k = (TILE_M * BK_BYTES + bn * BK_BYTES) / L2_SM
+    epi = TILE_M * bn * 4 / HBM_SM * (2 if split > 1 else 1)      # partial tiles: reduce-add traffic on top of the store
+    rounds = math.ceil(tiles * split / SMS)
+    return tiles, bn, kblocks, rounds * (math.ceil(kblocks / split) * per_k + epi) * 1e6
+
+
+def shape_of(name):
+    m = re.match(r"(l\d|fpn_inner\d|fpn_layer\d|rpn conv|rpn heads|adaptor)", name)
+    size = {"l1": 200, "l2": 100, "l3": 50, "l4": 25}
+    k = 3 if "3x3" in name else 1
+    ch = re.search(r"(\d+)->(\d+)", name)
+    at = re.search(r"@(\d+)", name)
+    if name.startswith("rpn conv"):
+        ci, co = 256, 256
+    else:
+        ci, co = int(ch.group(1)), int(ch.group(2))
+    if at:
+        h = int(at.group(1))
+    elif name.startswith("fpn"):
+        h = (200, 100, 50, 25)[int(re.search(r"(\d) ", name).group(1)) - 1]
+    else:
+        h = size[name[:2]]
+        if "s2" in name:
+            h //= 2                                           # output size of the stride-2 layers
+        elif name.startswith(("l2", "l3", "l4")) and False:
+            pass
+    return h, ci, co, k
+
+
+def main():
+    rows = []
+    for line in open(os.path.join(ROOT, "profiles", "r01_conv_layers_v3.log")):
+        if "|" not in line or line.startswith("layer"):
+            continue
+        cols = [c.strip() for c in line.split("|")]
+        name, cnt = cols[0].rsplit(None, 1)
+        f2 = float(cols[1].split()[0])
+        f8 = float(cols[2].split()[0])
+        rows.append((name.strip(), int(cnt), f2, f8))
+    print("# tcgen05 conv family: tiles vs SMs, and a split-K estimate (model; see scripts/conv_tile_model.py)\n")
+    print("| layer | n | tiles B2 (BN) | SMs with a tile | k-blocks | measured B2 us | model B2 us | model, K split to fill | est. saving / iteration us |")
+    print("|---|---|---|---|---|---|---|---|---|")
+    total_meas = total_save = total_model = 0.0
+    launches = 0
+    floors = []
+    for name, cnt, f2, f8 in rows:
+        h, ci, co, k = shape_of(name)
+        tiles, bn, kb, t1 = model(2, h, ci, co, k)
+        s = max(1, SMS // tiles)
+        _, _, _, ts = model(2, h, ci, co, k, split=s)
+        passes = 2 if not name.startswith(("rpn", "adaptor")) else 1
+        # the saving is taken relative to the MEASURED time, scaled by the model's ratio, forward passes at batch 2 only
+        save = max(0.0, f2 * (1 - ts / t1)) * cnt * passes if (s > 1 and ts < t1) else 0.0
+        total_meas += f2 * cnt * passes
+        total_save += save
+        total_model += t1 * cnt * passes
+        launches += cnt * passes
+        if t1 < 0.5 * f2:
+            floors.append(f2 - t1)
+        print("| %s | %d | %d (%d) | %d %% | %d | %.1f | %.1f | %s | %.0f |" % (
+            name, cnt, tiles, bn, min(100, round(100 * tiles / SMS)), kb, f2, t1,
+            ("%.1f (x%d)" % (ts, s)) if s > 1 else "-", save))
+    floors.sort()
+    med = floors[len(floors) // 2] if floors else 0.0
+    print("\nFixed cost per launch: the bandwidth model explains %.2f of the %.2f ms; the layers it under-predicts by more than "
+          "2x (%d of %d rows) exceed it by a median of %.1f us (min %.1f, max %.1f) — prologue (tensor-map fetch, barrier "
+          "init, TMEM allocation, first TMA round trip), the un-overlapped last epilogue and the launch gap.  With ~%d "
+          "forward launches per student pass and ~485 tcgen05 launches per iteration that floor is ~%.1f ms of the "
+          "conv family's ~19 ms: programmatic dependent launch (prologue of layer n+1 under the tail of layer n) and "
+          "fusing the bottleneck's 1x1 chains attack it; split-K does not." % (
+              total_model / 1e3, total_meas / 1e3, len(floors), len(rows), med, floors[0] if floors else 0,
+              floors[-1] if floors else 0, launches // 2, 485 * med / 1e3))
+    print("\nForward launches at batch 2 (student passes): measured %.2f ms / iteration; modelled split-K saving %.2f ms "
+          "(%.0f %%).  The dgrad launches have the same tile geometry (and the same starvation); the teacher's batch-8 "
+          "pass has 4x the pixel tiles and is starved only from layer4 down." % (total_meas / 1e3, total_save / 1e3,
+                                                                                 100 * total_save / total_meas))
+
+
+if __name__ == "__main__":
+    main()

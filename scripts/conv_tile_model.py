@@ -104,7 +104,7 @@ def main():
           "init, TMEM allocation, first TMA round trip), the un-overlapped last epilogue and the launch gap.  With ~%d "
           "forward launches per student pass and ~485 tcgen05 launches per iteration that floor is ~%.1f ms of the "
           "conv family's ~19 ms: programmatic dependent launch (prologue of layer n+1 under the tail of layer n) and "
-          "fusing the bottleneck's 1x1 chains attack it; split-K does not." % (
+          "fusing the small-map bottleneck chains removes launches outright (programmatic dependent launch can only hide the launch gap: a CTA of this kernel owns ~200 KB of shared memory and all TMEM columns); split-K does not address it." % (
               total_model / 1e3, total_meas / 1e3, len(floors), len(rows), med, floors[0] if floors else 0,
               floors[-1] if floors else 0, launches // 2, 485 * med / 1e3))
     print("\nForward launches at batch 2 (student passes): measured %.2f ms / iteration; modelled split-K saving %.2f ms "

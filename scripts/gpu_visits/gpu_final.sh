@@ -1,5 +1,5 @@
 #!/bin/bash
-# Round-end style visit: GPU parity suite, smoke, bench (ours + reference arm), secondary workloads.
+# Round-end style visit: GPU parity suites (ops, step, IR-Net), smoke, bench (ours + reference arm), secondary workloads incl. config 4.
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv > gpurun_out/smi.txt 2>&1
 nproc > gpurun_out/nproc.txt
@@ -15,3 +15,5 @@ timeout 600 python bench.py --workload sup --no-cpu-baseline > gpurun_out/bench_
 echo "sup rc=$?"; cut -c1-330 gpurun_out/bench_sup.json
 timeout 600 python bench.py --size 1024 --no-cpu-baseline > gpurun_out/bench_1024.json 2> gpurun_out/bench_1024.err
 echo "1024 rc=$?"; cut -c1-330 gpurun_out/bench_1024.json
+timeout 600 python bench.py --workload mt_relation --no-cpu-baseline --warmup 20 --steps 40 > gpurun_out/bench_relation.json 2> gpurun_out/bench_relation.err
+echo "relation rc=$?"; cut -c1-330 gpurun_out/bench_relation.json

@@ -429,8 +429,8 @@ def reference_state_dict(model):
 
 
 def load_reference_state_dict(model, sd, strict=False):
-    """Load a reference-layout state dict (e.g. e2e_mask_rcnn_R_50_FPN_1x.pth contents).  Keys the hot path does
-    not build (relation modules) are ignored unless strict."""
+    """Load a reference-layout state dict (e.g. e2e_mask_rcnn_R_50_FPN_1x.pth contents).  Keys this model does
+    not build (e.g. the IR-Net modules when they are switched off in cfg) are ignored unless strict."""
     conv, deconv = _special(model)
     fe = model.box_heads.box.feature_extractor
     own = model.state_dict()

@@ -5,7 +5,7 @@ save_dir, save_to_disk)`, `.save(name, **extra)`, `.load(f)`, `.has_checkpoint()
 Weights are written in the REFERENCE's layout and key names (OIHW convs, IOHW deconv, fc6 columns in (c, h, w) order:
 modeling/detector.py `reference_state_dict`), so a file saved here loads into the reference and a reference `.pth`
 (e.g. e2e_mask_rcnn_R_50_FPN_1x.pth) loads here; `module.` prefixes of DataParallel checkpoints are stripped, keys the
-hot path does not build (relation modules) are reported, not fatal.  Optimizer state = the flat momentum arena."""
+model does not build (the IR-Net modules when switched off in cfg) are reported, not fatal.  Optimizer state = the flat momentum arena."""
 import logging
 import os
 

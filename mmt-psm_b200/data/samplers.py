@@ -61,3 +61,40 @@ class IterationBasedBatchSampler(torch.utils.data.BatchSampler):
 
     def __len__(self):
         return self.num_iterations
+
+
+class GroupedBatchSampler(torch.utils.data.BatchSampler):
+    """Mini-batches whose elements share a group id (aspect-ratio bucket), in an order as close as possible to the
+    wrapped sampler's (the batch sampler the reference's train loader builds when DATALOADER.ASPECT_RATIO_GROUPING is
+    on, data/build.py + data/samplers/grouped_batch_sampler.py; behaviour pinned by the reference's own
+    tests/test_data_samplers.py).  Every group's ids are taken in sampled order and cut into chunks of `batch_size`; the
+    chunks of all groups are emitted ordered by where their first element sits in the sampled order; with
+    `drop_uneven` the short chunks are dropped."""
+
+    def __init__(self, sampler, group_ids, batch_size, drop_uneven=False):
+        if not isinstance(sampler, torch.utils.data.Sampler):
+            raise ValueError("sampler should be an instance of torch.utils.data.Sampler, but got sampler=%r" % (sampler,))
+        self.sampler, self.group_ids = sampler, list(group_ids)
+        self.batch_size, self.drop_uneven = batch_size, drop_uneven
+        self._cached = None
+
+    def _batches(self):
+        order = list(self.sampler)
+        position = {idx: p for p, idx in enumerate(order)}
+        per_group = {}
+        for idx in order:
+            per_group.setdefault(self.group_ids[idx], []).append(idx)
+        chunks = [ids[i:i + self.batch_size] for ids in per_group.values() for i in range(0, len(ids), self.batch_size)]
+        chunks.sort(key=lambda c: position[c[0]])
+        if self.drop_uneven:
+            chunks = [c for c in chunks if len(c) == self.batch_size]
+        return chunks
+
+    def __iter__(self):
+        batches, self._cached = (self._cached if self._cached is not None else self._batches()), None
+        return iter(batches)
+
+    def __len__(self):
+        if self._cached is None:
+            self._cached = self._batches()      # the next __iter__ hands out exactly these
+        return len(self._cached)

@@ -11,7 +11,7 @@ import os
 
 import torch
 
-from ..modeling.detector import load_reference_state_dict, reference_state_dict
+from .model_serialization import _unwrap, load_state_dict
 
 
 class Checkpointer(object):
@@ -23,7 +23,7 @@ class Checkpointer(object):
     def save(self, name, **kwargs):
         if not self.save_dir or not self.save_to_disk:
             return None
-        data = {"model": {k: v.cpu() for k, v in reference_state_dict(self.model).items()}}
+        data = {"model": {k: v.cpu() for k, v in self._model_state().items()}}
         if self.optimizer is not None:
             data["optimizer"] = {k: (v.cpu() if isinstance(v, torch.Tensor) else v)
                                  for k, v in self.optimizer.state_dict().items()}
@@ -37,6 +37,14 @@ class Checkpointer(object):
         self.tag_last_checkpoint(save_file)
         return save_file
 
+    def _model_state(self):
+        """The detector in the reference's layout and key names; any other module as its own state dict (wrapper
+        prefixes included, like the reference — the loader ignores them)."""
+        if hasattr(_unwrap(self.model), "box_heads"):
+            from ..modeling.detector import reference_state_dict
+            return reference_state_dict(_unwrap(self.model))
+        return self.model.state_dict()
+
     def load(self, f=None, test=False):
         """Resumes from `last_checkpoint` if the run directory has one (like the reference), else from `f`; with
         neither, the model keeps its initialisation.  Returns the extra data stored next to the weights."""
@@ -48,8 +56,7 @@ class Checkpointer(object):
         self.logger.info("Loading checkpoint from %s", f)
         checkpoint = torch.load(f, map_location="cpu", weights_only=False)
         sd = checkpoint.pop("model", checkpoint)
-        sd = {(k[len("module."):] if k.startswith("module.") else k): v for k, v in sd.items()}
-        missing, unexpected = load_reference_state_dict(self.model, sd)
+        missing, unexpected = load_state_dict(self.model, sd)     # longest-suffix key matching, `module.` ignored
         if missing:
             self.logger.warning("keys not in the checkpoint (kept at their initialisation): %s", missing[:8])
         if unexpected:

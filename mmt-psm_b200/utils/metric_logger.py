@@ -21,7 +21,8 @@ class SmoothedValue(object):
 
     @property
     def median(self):
-        return statistics.median(self.window) if self.window else 0.0
+        # lower middle value for an even count, like the torch.median the reference's meter uses
+        return statistics.median_low(self.window) if self.window else 0.0
 
     @property
     def avg(self):

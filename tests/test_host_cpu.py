@@ -175,3 +175,105 @@ def test_checkpoint_roundtrip_reference_layout(tmp_path):
     assert all(torch.equal(sa[k], sb[k]) for k in sa if "cell_anchors" not in k)
     assert DetectronCheckpointer(cfg, b, save_dir=str(tmp_path / "empty"), save_to_disk=True).load() == {}
 
+
+
+def test_metric_logger_contract_of_the_reference_test():
+    """The assertions of the reference's own tests/test_metric_logger.py, on this package's meters."""
+    from mmt_psm_b200.utils.metric_logger import MetricLogger
+    meter = MetricLogger()
+    for i in range(10):
+        meter.update(metric=float(i))
+    m = meter.meters["metric"]
+    assert (m.count, m.total, m.median, m.avg) == (10, 45, 4, 4.5)
+    assert meter.metric is m and meter.delimiter == "\t"
+    with pytest.raises(AttributeError):
+        _ = meter.not_existent
+    meter.update(loss=torch.tensor(2.0), time=0.5)
+    assert "loss: 2.0000 (2.0000)" in str(meter) and abs(meter.time.global_avg - 0.5) < 1e-12
+
+
+def test_batch_samplers_known_answers_of_the_reference_tests():
+    """Known answers of the reference's tests/test_data_samplers.py for the batch samplers its train loader stacks."""
+    import itertools
+    from torch.utils.data.sampler import BatchSampler, RandomSampler, Sampler, SequentialSampler
+    from mmt_psm_b200.data.samplers import GroupedBatchSampler, IterationBasedBatchSampler
+
+    class Subset(Sampler):
+        def __init__(self, ids):
+            self.ids = ids
+
+        def __iter__(self):
+            return iter(self.ids)
+
+        def __len__(self):
+            return len(self.ids)
+
+    data = list(range(40))
+    for bs in (1, 3, 5, 6):   # groups of 10 consecutive ids: order is preserved
+        out = list(GroupedBatchSampler(SequentialSampler(data), [i // 10 for i in data], bs, False))
+        assert list(itertools.chain.from_iterable(out)) == data
+    gid = [0, 0, 1, 0, 1, 1, 0, 1, 1, 0]
+    seq = SequentialSampler(list(range(10)))
+    assert list(GroupedBatchSampler(seq, gid, 1, False)) == [[i] for i in range(10)]
+    assert list(GroupedBatchSampler(seq, gid, 3, False)) == [[0, 1, 3], [2, 4, 5], [6, 9], [7, 8]]
+    assert list(GroupedBatchSampler(seq, gid, 4, False)) == [[0, 1, 3, 6], [2, 4, 5, 7], [8], [9]]
+    assert list(GroupedBatchSampler(seq, gid, 3, True)) == [[0, 1, 3], [2, 4, 5]]
+    assert list(GroupedBatchSampler(Subset([0, 3, 5, 6, 7, 8]), gid, 3, False)) == [[0, 3, 6], [5, 7, 8]]
+    assert list(GroupedBatchSampler(Subset([5, 0, 6, 1, 3, 8]), gid, 3, False)) == [[5, 8], [0, 6, 1], [3]]
+    assert list(GroupedBatchSampler(Subset([5, 0, 6, 1, 3, 8]), gid, 3, True)) == [[0, 6, 1]]
+    g = GroupedBatchSampler(RandomSampler(list(range(10))), gid, 3, True)
+    n = len(g)
+    assert len(list(g)) == n == len(g)
+    for bs in (2, 3, 4):
+        for iters in (4, 10, 20):
+            for drop_last in (False, True):
+                inner = BatchSampler(SequentialSampler(list(range(10))), bs, drop_last=drop_last)
+                it = IterationBasedBatchSampler(inner, iters)
+                assert len(it) == iters
+                for i, batch in enumerate(it):
+                    start = (i % len(inner)) * bs
+                    assert batch == list(range(start, min(start + bs, 10)))
+
+
+def test_checkpointer_contract_of_the_reference_test(tmp_path):
+    """The cases of the reference's own tests/checkpoint.py: save / resume via `last_checkpoint` or by file name across
+    DataParallel prefixes, and longest-suffix key matching into a nested model."""
+    import os
+    from collections import OrderedDict
+    from torch import nn
+    from mmt_psm_b200.utils.checkpoint import Checkpointer
+    from mmt_psm_b200.utils.model_serialization import load_state_dict
+    make = lambda: nn.Sequential(nn.Linear(2, 3), nn.Linear(3, 1))
+    pairs = [(make(), make()), (nn.DataParallel(make()), make()), (make(), nn.DataParallel(make())),
+             (nn.DataParallel(make()), nn.DataParallel(make()))]
+    for i, (trained, fresh) in enumerate(pairs):
+        d = str(tmp_path / ("same%d" % i))
+        Checkpointer(trained, save_dir=d, save_to_disk=True).save("checkpoint_file")
+        ck = Checkpointer(fresh, save_dir=d)
+        assert ck.has_checkpoint() and ck.get_checkpoint_file() == os.path.join(d, "checkpoint_file.pth")
+        ck.load()
+        for a, b in zip(trained.parameters(), fresh.parameters()):
+            assert a is not b and a.equal(b)
+    for i, (trained, fresh) in enumerate([(make(), make()), (nn.DataParallel(make()), make()), (make(), nn.DataParallel(make()))]):
+        d, other = str(tmp_path / ("src%d" % i)), str(tmp_path / ("dst%d" % i))
+        os.makedirs(other)
+        Checkpointer(trained, save_dir=d, save_to_disk=True).save("checkpoint_file")
+        ck = Checkpointer(fresh, save_dir=other)
+        assert not ck.has_checkpoint() and ck.get_checkpoint_file() == ""
+        ck.load(os.path.join(d, "checkpoint_file.pth"))
+        for a, b in zip(trained.parameters(), fresh.parameters()):
+            assert a is not b and a.equal(b)
+    for wrap in (False, True):
+        m = nn.Module()
+        m.block1 = nn.Module()
+        m.block1.layer1 = nn.Linear(2, 3)
+        m.layer2 = nn.Linear(3, 2)
+        m.res = nn.Module()
+        m.res.layer2 = nn.Linear(3, 2)
+        sd = OrderedDict([("layer1.weight", torch.rand(3, 2)), ("layer1.bias", torch.rand(3)), ("layer2.weight", torch.rand(2, 3)),
+                          ("layer2.bias", torch.rand(2)), ("res.layer2.weight", torch.rand(2, 3)), ("res.layer2.bias", torch.rand(2))])
+        model = nn.DataParallel(m) if wrap else m
+        missing, unused = load_state_dict(model, sd)
+        assert not missing and not unused
+        for loaded, stored in zip(model.state_dict().values(), sd.values()):
+            assert loaded is not stored and loaded.equal(stored)

@@ -45,10 +45,17 @@ class Checkpointer(object):
             return reference_state_dict(_unwrap(self.model))
         return self.model.state_dict()
 
+    # the COCO Mask R-CNN file the reference starts from: loaded as TRANSFER LEARNING (reference utils/checkpoint.py:79-117,
+    # 148-160) — the class-count-dependent predictors are dropped, optimizer / scheduler state is not taken, the
+    # iteration counter restarts, and an existing `last_checkpoint` does not override it
+    TRANSFER_FILE = "e2e_mask_rcnn_R_50_FPN_1x.pth"
+    TRANSFER_DROPPED = ("cls_score", "bbox_pred", "mask_fcn_logits")
+
     def load(self, f=None, test=False):
         """Resumes from `last_checkpoint` if the run directory has one (like the reference), else from `f`; with
         neither, the model keeps its initialisation.  Returns the extra data stored next to the weights."""
-        if self.has_checkpoint():
+        transfer = bool(f) and not test and self.TRANSFER_FILE in f
+        if self.has_checkpoint() and not transfer:
             f = self.get_checkpoint_file()
         if not f:
             self.logger.info("No checkpoint found. Initializing model from scratch")
@@ -56,6 +63,11 @@ class Checkpointer(object):
         self.logger.info("Loading checkpoint from %s", f)
         checkpoint = torch.load(f, map_location="cpu", weights_only=False)
         sd = checkpoint.pop("model", checkpoint)
+        if transfer:
+            sd = {k: v for k, v in sd.items() if not any(name in k for name in self.TRANSFER_DROPPED)}
+            checkpoint.pop("optimizer", None)
+            checkpoint.pop("scheduler", None)
+            checkpoint["iteration"] = -1
         missing, unexpected = load_state_dict(self.model, sd)     # longest-suffix key matching, `module.` ignored
         if missing:
             self.logger.warning("keys not in the checkpoint (kept at their initialisation): %s", missing[:8])

@@ -277,3 +277,41 @@ def test_checkpointer_contract_of_the_reference_test(tmp_path):
         assert not missing and not unused
         for loaded, stored in zip(model.state_dict().values(), sd.values()):
             assert loaded is not stored and loaded.equal(stored)
+
+
+def test_checkpointer_transfer_learning_file(tmp_path):
+    """The COCO start file is loaded the reference's way (utils/checkpoint.py:79-117,148-160): predictors dropped, no
+    optimizer / scheduler state, iteration -1, and it wins over an existing last_checkpoint."""
+    from mmt_psm_b200.config.presets import mt_psm_cfg
+    from mmt_psm_b200.modeling.detector import build_detection_model, reference_state_dict
+    from mmt_psm_b200.solver import WarmupMultiStepLR
+    from mmt_psm_b200.utils.checkpoint import DetectronCheckpointer
+    from mmt_psm_b200.utils.synthetic_init import init_model
+    cfg = mt_psm_cfg(start_mt=0)
+    src = build_detection_model(cfg, is_student=True)
+    init_model(src, 5)
+    f = str(tmp_path / "e2e_mask_rcnn_R_50_FPN_1x.pth")
+    torch.save({"model": {"module." + k: v for k, v in reference_state_dict(src).items()}, "iteration": 89999,
+                "scheduler": {"last_epoch": 89999}}, f)
+
+    class Opt(object):
+        base_lr = 0.01
+
+        def set_lr(self, lr):
+            self.lr = lr
+    dst = build_detection_model(cfg, is_student=True)
+    init_model(dst, 1)
+    before = {k: v.clone() for k, v in dst.state_dict().items()}
+    sched = WarmupMultiStepLR(Opt(), (30, 40))
+    run = str(tmp_path / "run")
+    DetectronCheckpointer(cfg, dst, None, sched, run, True).save("model_0000003", iteration=3)     # a last_checkpoint exists
+    extra = DetectronCheckpointer(cfg, dst, None, sched, run, True).load(f)
+    assert extra["iteration"] == -1 and sched.last_epoch != 89999
+    a, b = src.state_dict(), dst.state_dict()
+    for k in b:
+        if "cell_anchors" in k:
+            continue
+        if any(n in k for n in ("cls_score", "bbox_pred", "mask_fcn_logits")):
+            assert torch.equal(b[k], before[k]), k          # kept at its own initialisation
+        else:
+            assert torch.equal(b[k], a[k]), k

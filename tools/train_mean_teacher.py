@@ -71,7 +71,7 @@ def main():
     out_dir = cfg.OUTPUT_DIR or "."
     pre = DetectronCheckpointer(cfg, model_s, save_dir="", save_to_disk=False)
     if args.init_weights:
-        pre.load(args.init_weights, test=True)
+        pre.load(args.init_weights)     # the COCO start file goes through the transfer-learning rules (utils/checkpoint.py)
     model_t.load_state_dict(model_s.state_dict())
     optimizer = make_optimizer(cfg, model_s, model_t)
     scheduler = make_lr_scheduler(cfg, optimizer)

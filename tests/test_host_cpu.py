@@ -315,3 +315,18 @@ def test_checkpointer_transfer_learning_file(tmp_path):
             assert torch.equal(b[k], before[k]), k          # kept at its own initialisation
         else:
             assert torch.equal(b[k], a[k]), k
+
+
+def test_run_logger_contract(tmp_path, capsys):
+    from mmt_psm_b200.utils.logger import setup_logger
+    log = setup_logger("mmt_test_run", str(tmp_path), 0)
+    setup_logger("mmt_test_run", str(tmp_path), 0)                      # idempotent: one line per message
+    log.getChild("trainer").info("iter: 20  loss: 1.5")
+    for h in log.handlers:
+        h.flush()
+    text = open(str(tmp_path / "log.txt")).read()
+    assert text.count("iter: 20  loss: 1.5") == 1 and "mmt_test_run.trainer INFO" in text
+    assert "iter: 20  loss: 1.5" in capsys.readouterr().out
+    quiet = setup_logger("mmt_test_rank1", str(tmp_path / "r1"), 1)
+    quiet.info("nothing")
+    assert not (tmp_path / "r1").exists()

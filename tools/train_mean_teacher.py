@@ -62,7 +62,8 @@ def main():
     cfg.merge_from_list(args.opts or [])
     cfg.freeze()
     logging.basicConfig(level=logging.INFO if rank == 0 else logging.WARNING, format="%(asctime)s %(name)s: %(message)s")
-    log = logging.getLogger("maskrcnn_benchmark.trainer")
+    from mmt_psm_b200.utils.logger import setup_logger
+    log = setup_logger("maskrcnn_benchmark", cfg.OUTPUT_DIR, rank).getChild("trainer")   # stdout + OUTPUT_DIR/log.txt on rank 0
 
     torch.manual_seed(0)
     model_s = build_detection_model(cfg, is_student=True).to(device)

@@ -57,3 +57,57 @@ class UnlabeledViewLoader(object):
             order = torch.randperm(len(self.ds), generator=self.gen).tolist()
             for i in range(0, len(order) - self.batch + 1, self.batch):
                 yield self.collate([self.ds[j] for j in order[i:i + self.batch]])
+
+
+def aspect_groups(sizes_wh, bins=(1,)):
+    """Group id per image from its height / width ratio (reference data/build.py:80-93, `_quantize` over
+    DATALOADER.ASPECT_RATIO_GROUPING's single bin edge 1: portrait-or-square = 1, landscape = 0)."""
+    import bisect
+    edges = sorted(bins)
+    return [bisect.bisect_right(edges, float(h) / float(w)) for w, h in sizes_wh]
+
+
+class LabeledCropLoader(object):
+    """The labeled ('source') loader over real crops: the reference's sampler chain (data/build.py:71-116 —
+    Random / Sequential / Distributed sampler -> GroupedBatchSampler by aspect ratio -> IterationBasedBatchSampler for
+    exactly `max_iter` batches, resumable at `start_iter`) around `LabeledCrops`, with the collation on the device
+    (`DeviceSourceCollator`).  Yields `(ImageList, targets, indices)`; host-side item work can run in `num_workers`
+    DataLoader workers (the device collator runs in the consuming process)."""
+
+    def __init__(self, dataset, device, images_per_batch=2, max_iter=1, start_iter=0, shuffle=True, aspect_grouping=True,
+                 size_divisible=32, pixel_mean=PIXEL_MEAN, world=1, rank=0, num_workers=0, sizes_wh=None):
+        from .labeled import DeviceSourceCollator
+        from .samplers import GroupedBatchSampler, IterationBasedBatchSampler
+        if world > 1:
+            sampler = DistributedSampler(dataset, num_replicas=world, rank=rank, shuffle=shuffle)
+        elif shuffle:
+            sampler = torch.utils.data.RandomSampler(dataset)
+        else:
+            sampler = torch.utils.data.SequentialSampler(dataset)
+        if aspect_grouping:
+            if sizes_wh is None:
+                sizes_wh = [self._size_of(dataset.crops[i]) for i in range(len(dataset))]
+            batches = GroupedBatchSampler(sampler, aspect_groups(sizes_wh), images_per_batch, drop_uneven=False)
+        else:
+            batches = torch.utils.data.BatchSampler(sampler, images_per_batch, drop_last=False)
+        self.batch_sampler = IterationBasedBatchSampler(batches, max_iter, start_iter)
+        self.loader = torch.utils.data.DataLoader(dataset, batch_sampler=self.batch_sampler, num_workers=num_workers,
+                                                  collate_fn=list)
+        self.collate = DeviceSourceCollator(device, size_divisible, tuple(pixel_mean))
+
+    @staticmethod
+    def _size_of(src):
+        if isinstance(src, str):
+            from PIL import Image
+            with Image.open(src) as im:
+                return im.size
+        if hasattr(src, "size") and not hasattr(src, "shape"):
+            return src.size                                   # PIL image: (w, h)
+        return (src.shape[1], src.shape[0])
+
+    def __len__(self):
+        return len(self.batch_sampler)
+
+    def __iter__(self):
+        for items in self.loader:
+            yield self.collate(items)

@@ -488,6 +488,52 @@ def gen_step_relation():
     print({k: float(v) for k, v in out.items() if v.ndim == 0}, out["infer_n"], out["t_n_rois"])
 
 
+def gen_source_items():
+    """Labeled (`source`) items through the REFERENCE's own transform classes and containers: data/transforms/build.py:37-50
+    (Resize, RandomHorizontalFlip, AdjustBrightness / Contrast / Hue, RandomErasing(0.7), ToTensor, Normalize) applied to a
+    PIL crop and a BoxList target with polygon masks (structures/bounding_box.py, segmentation_mask.py)."""
+    import importlib.util
+    import random
+    from PIL import Image
+    from maskrcnn_benchmark.structures.bounding_box import BoxList
+    from maskrcnn_benchmark.structures.segmentation_mask import SegmentationMask
+    spec = importlib.util.spec_from_file_location("ref_transforms", os.path.join(TREE, "maskrcnn_benchmark/data/transforms/transforms.py"))
+    T = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(T)
+    tr = T.Compose([T.Resize(64, 120), T.RandomHorizontalFlip(0.5), T.AdjustBrightness(0.15), T.AdjustContrast(0.15),
+                    T.AdjustHue(0.05), T.RandomErasing(0.7), T.ToTensor(),
+                    T.Normalize(mean=[102.9801, 115.9465, 122.7717], std=[1., 1., 1.], to_bgr255=True)])
+    g = np.random.default_rng(21)
+    tg = torch.Generator().manual_seed(21)
+    out = {"seed": 9, "n": 4}
+    random.seed(9)
+    np.random.seed(9)
+    for i, (h, w) in enumerate(((100, 120), (90, 150), (128, 96), (100, 120))):
+        img = g.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        inst = synthetic_instances(tg, 5, float(min(h, w)))
+        boxes = []
+        for polys in inst:
+            xs = np.concatenate([np.asarray(p[0::2]) for p in polys])
+            ys = np.concatenate([np.asarray(p[1::2]) for p in polys])
+            boxes.append([xs.min(), ys.min(), xs.max(), ys.max()])
+        labels = torch.randint(1, 3, (5,), generator=tg)
+        t = BoxList(torch.tensor(boxes, dtype=torch.float32), (w, h), "xyxy")
+        t.add_field("labels", labels)
+        t.add_field("masks", SegmentationMask(inst, (w, h)))
+        image, t2 = tr(Image.fromarray(img, "RGB"), t)
+        out["img_%d" % i] = img
+        out["boxes_%d" % i] = np.asarray(boxes, dtype=np.float32)
+        out["labels_%d" % i] = labels.numpy()
+        out["poly_%d" % i] = np.array([len(polys) for polys in inst])
+        out["poly_flat_%d" % i] = np.concatenate([np.asarray(p, dtype=np.float64) for polys in inst for p in polys])
+        out["poly_len_%d" % i] = np.array([len(p) for polys in inst for p in polys])
+        out["out_image_%d" % i] = image.numpy()
+        out["out_boxes_%d" % i] = t2.bbox.numpy()
+        out["out_size_%d" % i] = np.array(t2.size)
+        out["out_poly_flat_%d" % i] = np.concatenate([p.numpy().astype(np.float64) for m in t2.get_field("masks").polygons for p in m.polygons])
+    save("source_items", **out)
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
     which = sys.argv[1:] or ["nms", "roi_align", "psm", "mgd", "ema", "glue", "mask_targets", "step", "color_views"]
@@ -500,5 +546,6 @@ if __name__ == "__main__":
     if "mask_targets" in which: gen_mask_targets()
     if "step" in which: gen_step()
     if "color_views" in which: gen_color_views()
+    if "source_items" in which: gen_source_items()
     if "relation" in which: gen_relation()
     if "step_relation" in which: gen_step_relation()

@@ -12,6 +12,7 @@ def setup_logger(name, save_dir, distributed_rank, test=False):
     logger.setLevel(logging.DEBUG)
     if distributed_rank > 0:
         logger.addHandler(logging.NullHandler())
+        logger.propagate = False                 # nothing from the non-master ranks reaches the root handlers either
         return logger
     sinks = [logging.StreamHandler(stream=sys.stdout)]
     if save_dir:

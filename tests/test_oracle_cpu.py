@@ -233,3 +233,70 @@ def test_relation_mask_oracle_matches_reference():
         np.testing.assert_allclose(m.grad.numpy(), g["msk_%s_dm" % tag], rtol=1e-4, atol=1e-6)
         np.testing.assert_allclose(f.grad.sum((2, 3)).numpy(), g["msk_%s_df_sum" % tag], rtol=1e-4, atol=1e-4)
         np.testing.assert_allclose(sd[RR.MASK_PREFIX + "relation_module.gamma"].grad.numpy(), g["msk_%s_dgamma" % tag], rtol=1e-4)
+
+
+# ------------------------------------------------------------------------------------------- size-independent properties
+def test_oracle_properties_hypothesis():
+    """Domain properties the path offers, on random cases: NMS is idempotent and its survivors are pairwise below the
+    threshold; BoxCoder decode(encode(gt, anchor), anchor) returns gt (legacy +1 extents); the IR-Net label preparation
+    gives every ground truth at most one winner, only boxes above the threshold win, and a winner's IoU-regression target is
+    its IoU with a ground truth of that class."""
+    from hypothesis import given, settings, strategies as st
+    from oracle import relation_ref as RR
+
+    def boxes_from(seed, n, size=300.0):
+        g = torch.Generator().manual_seed(seed)
+        c = torch.rand(n, 2, generator=g) * size
+        wh = torch.rand(n, 2, generator=g) * 60 + 4
+        return torch.cat([c - wh / 2, c + wh / 2], 1)
+
+    @settings(max_examples=25, deadline=None, derandomize=True)
+    @given(st.integers(0, 10 ** 6), st.integers(1, 120), st.sampled_from([0.3, 0.5, 0.7]))
+    def nms_props(seed, n, thr):
+        b = boxes_from(seed, n).numpy()
+        s = torch.rand(n, generator=torch.Generator().manual_seed(seed + 1)).numpy()
+        keep = np.asarray(R.nms_ref(b, s, thr))
+        assert np.all(np.diff(keep) > 0)                                   # ascending original indices
+        again = np.asarray(R.nms_ref(b[keep], s[keep], thr))
+        assert np.array_equal(again, np.arange(len(keep)))                 # idempotent
+        iou = R.boxlist_iou_ref(b[keep], b[keep]).numpy().copy()
+        np.fill_diagonal(iou, 0)
+        assert (iou <= thr + 1e-6).all()
+
+    @settings(max_examples=25, deadline=None, derandomize=True)
+    @given(st.integers(0, 10 ** 6), st.integers(1, 60))
+    def coder_roundtrip(seed, n):
+        from oracle import model_cpu as M
+        gt, an = boxes_from(seed, n), boxes_from(seed + 7, n)
+        w = (10., 10., 5., 5.)
+        back = M.decode(M.encode(gt, an, w), an, w)
+        assert torch.allclose(back, gt, rtol=1e-4, atol=2e-3)
+
+    @settings(max_examples=25, deadline=None, derandomize=True)
+    @given(st.integers(0, 10 ** 6), st.integers(1, 90), st.integers(0, 30))
+    def label_props(seed, n, m):
+        g = torch.Generator().manual_seed(seed)
+        gt = boxes_from(seed, m)
+        gl = torch.randint(1, 3, (m,), generator=g)
+        if m:
+            boxes = gt[torch.randint(0, m, (n, 2), generator=g)] + torch.randn(n, 2, 4, generator=g) * 4
+        else:
+            boxes = boxes_from(seed + 3, 2 * n).view(n, 2, 4)
+        boxes[..., 2:] = torch.max(boxes[..., 2:], boxes[..., :2] + 1)
+        scores = torch.sort(torch.rand(n, 2, generator=g), 0, descending=True)[0]
+        lab = RR.reg_labels(boxes, scores, gt, gl, (0.1,))
+        hot = RR.reg_labels(boxes, scores, gt, gl, (0.1,), binary=True)
+        assert lab.shape == (n, 2, 1) and (lab >= 0).all() and (lab <= 1 + 1e-6).all()
+        assert np.array_equal(lab > 0, (hot > 0) & (lab > 0))
+        for c in range(2):
+            k = int((gl == c + 1).sum())
+            assert (hot[:, c, 0] > 0).sum() <= max(k, 0)                    # at most one winner per ground truth
+            if k:
+                iou = RR._iou_plus1(boxes[:, c], gt[gl == c + 1]).numpy()
+                win = lab[:, c, 0] > 0
+                assert (iou.max(1)[win] > 0.1).all()
+                assert np.allclose(lab[win, c, 0], iou.max(1)[win], atol=1e-6)
+
+    nms_props()
+    coder_roundtrip()
+    label_props()

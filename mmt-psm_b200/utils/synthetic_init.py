@@ -23,7 +23,7 @@ def _gen(name, seed):
     return torch.Generator().manual_seed((zlib.crc32(name.encode()) + 1000003 * seed) % (2 ** 31))
 
 
-def synthetic_state_dict(shapes, seed=0, adaptor_scale=None):
+def synthetic_state_dict(shapes, seed=0, adaptor_scale=None, box_reg_gain=1.0):
     if adaptor_scale is None:
         adaptor_scale = float(os.environ.get("MMT_SYNTH_ADAPTOR_SCALE", "0.1"))
     out = {}
@@ -64,7 +64,7 @@ def synthetic_state_dict(shapes, seed=0, adaptor_scale=None):
             if "cls_score" in name:
                 std = 0.01
             if "bbox_pred" in name:
-                std = 0.001
+                std = 0.001 * box_reg_gain             # > 1: parity fixtures that must exercise the box-regression loss
             if "roi_feat_embedding_fc" in name:
                 std *= float(os.environ.get("MMT_SYNTH_RELATION_SCALE", "0.1"))   # see the module docstring (IR-Net head)
             t = torch.randn(shape, generator=g) * std
@@ -74,10 +74,10 @@ def synthetic_state_dict(shapes, seed=0, adaptor_scale=None):
     return out
 
 
-def init_model(model, seed=0):
+def init_model(model, seed=0, **kw):
     """Fill `model` (this package's GeneralizedRCNN) through the reference-layout boundary."""
     from ..modeling.detector import load_reference_state_dict, reference_state_dict
     shapes = {k: tuple(v.shape) for k, v in reference_state_dict(model).items()}
-    sd = synthetic_state_dict(shapes, seed)
+    sd = synthetic_state_dict(shapes, seed, **kw)
     load_reference_state_dict(model, sd)
     return sd

@@ -153,6 +153,9 @@ class Cfg(object):
     relation = False          # IR-Net modules (BASELINE config 4): MODEL.RELATION_NMS.USE_RELATION_NMS + RELATION_MASK.USE_RELATION
     relation_cfg = relation_ref.RelationCfg
     nms_loss_w = 1.0          # MODEL.RELATION_NMS.LOSS (train_mt.sh)
+    tf32_operands = False     # True: every conv / linear sees its operands with 10 mantissa bits (low 13 bits dropped), fp32
+                              # accumulate — what the reference computes under torch.backends.cudnn.allow_tf32 (its GPU default)
+                              # and what the tcgen05 kind::tf32 path computes; used to hold the SHIPPED conv math to a tight bound
 
 
 class Net(object):
@@ -169,8 +172,17 @@ class Net(object):
             self.sd[k].requires_grad_(True)
 
     # ---- layers ---------------------------------------------------------------------------------
+    def _op(self, t):
+        """Operand as the multiplier sees it (straight-through for autograd)."""
+        if not self.cfg.tf32_operands:
+            return t
+        return t + (ops_ref.tf32_round(t.detach()) - t.detach())
+
     def conv(self, x, name, stride=1, pad=0):
-        return F.conv2d(x, self.sd[name + ".weight"], self.sd.get(name + ".bias"), stride, pad)
+        return F.conv2d(self._op(x), self._op(self.sd[name + ".weight"]), self.sd.get(name + ".bias"), stride, pad)
+
+    def linear(self, x, name):
+        return F.linear(self._op(x), self._op(self.sd[name + ".weight"]), self.sd[name + ".bias"])
 
     def bn(self, x, name):  # layers/batch_norm.py:19-24
         scale = self.sd[name + ".weight"] * self.sd[name + ".running_var"].rsqrt()
@@ -224,23 +236,22 @@ class Net(object):
     def box_feat(self, feats, boxes_per_img, istrain):  # roi_box_feature_extractors.py:107-125
         p = "box_heads.box.feature_extractor."
         x = self.pool(feats, boxes_per_img, 7).flatten(1)
-        x = F.relu(F.linear(x, self.sd[p + "fc6.weight"], self.sd[p + "fc6.bias"]))
-        x = F.relu(F.linear(x, self.sd[p + "fc7.weight"], self.sd[p + "fc7.bias"]))
+        x = F.relu(self.linear(x, p + "fc6"))
+        x = F.relu(self.linear(x, p + "fc7"))
         if self.cfg.dropout > 0:
             x = F.dropout(x, p=self.cfg.dropout, training=istrain)
         return x
 
     def box_pred(self, x):
         p = "box_heads.box.predictor."
-        return (F.linear(x, self.sd[p + "cls_score.weight"], self.sd[p + "cls_score.bias"]),
-                F.linear(x, self.sd[p + "bbox_pred.weight"], self.sd[p + "bbox_pred.bias"]))
+        return self.linear(x, p + "cls_score"), self.linear(x, p + "bbox_pred")
 
     def mask_logits(self, feats, boxes_per_img, with_features=False):  # roi_mask_feature_extractors.py:131-146, roi_mask_predictors.py:34-36
         x = self.pool(feats, boxes_per_img, 14)
         for i in range(1, 5):
             x = F.relu(self.conv(x, "mask_heads.mask.feature_extractor.mask_fcn%d" % i, 1, 1))
         p = "mask_heads.mask.predictor."
-        y = F.relu(F.conv_transpose2d(x, self.sd[p + "conv5_mask.weight"], self.sd[p + "conv5_mask.bias"], 2))
+        y = F.relu(F.conv_transpose2d(self._op(x), self._op(self.sd[p + "conv5_mask.weight"]), self.sd[p + "conv5_mask.bias"], 2))
         y = self.conv(y, p + "mask_fcn_logits")
         return (x, y) if with_features else y
 

@@ -255,7 +255,7 @@ def gen_mask_targets():
          masks=masks.numpy().astype(np.uint8))
 
 
-def gen_step():
+def gen_step(size=256, n_cyto=6, n_nuc=6, name="step_small", **init_kw):
     """One supervised step + one mean-teacher forward (teacher -> student-unlabeled) of the REFERENCE model on CPU,
     from the deterministic synthetic weights / inputs of mmt_psm_b200 (DO = 0 so no dropout stream is involved)."""
     sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
@@ -272,12 +272,11 @@ def gen_step():
     student = build_detection_model(c, is_student=True)
     teacher = build_detection_model(c, is_teacher=True)
     shapes = {k: tuple(v.shape) for k, v in student.state_dict().items() if "mask_relation_module" not in k}
-    sd = synthetic_state_dict(shapes, 0)
+    sd = synthetic_state_dict(shapes, 0, **init_kw)
     for m in (student, teacher):
         missing, unexpected = m.load_state_dict(sd, strict=False)
         assert not unexpected and all("mask_relation_module" in k or "cell_anchors" in k for k in missing), missing
-    size = 256
-    images, targets, views = make_batch(1234, 2, size, 3, 6, 6)
+    images, targets, views = make_batch(1234, 2, size, 3, n_cyto, n_nuc)
     rt = []
     for t in targets:
         b = BoxList(t.bbox, t.size, "xyxy")
@@ -299,7 +298,8 @@ def gen_step():
     out["t_logits"] = torch.stack(tr["class_logit_t"]).numpy()
     out["t_seg_mask_sum"] = np.array([float(m.sum()) for m in tr["seg_mask"]])
     out["t_seg_mask"] = np.packbits(torch.stack(tr["seg_mask"]).numpy() > 0)
-    save("step_small", size=size, **out)
+    save(name, size=size, n_cyto=n_cyto, n_nuc=n_nuc, adaptor_scale=init_kw.get("adaptor_scale", 0.1),
+         box_reg_gain=init_kw.get("box_reg_gain", 1.0), **out)
     print({k: float(v) for k, v in out.items() if v.ndim == 0})
 
 
@@ -455,8 +455,7 @@ def gen_step_relation():
     for m in (student, teacher):
         missing, unexpected = m.load_state_dict(sd, strict=False)
         assert not unexpected and all("cell_anchors" in k for k in missing), missing
-    size = 256
-    images, targets, views = make_batch(1234, 2, size, 3, 6, 6)
+    images, targets, views = make_batch(1234, 2, size, 3, n_cyto, n_nuc)
     rt = []
     for t in targets:
         b = BoxList(t.bbox, t.size, "xyxy")
@@ -545,6 +544,7 @@ if __name__ == "__main__":
     if "glue" in which: gen_glue()
     if "mask_targets" in which: gen_mask_targets()
     if "step" in which: gen_step()
+    if "step_full" in which: gen_step(800, 20, 20, "step_full", adaptor_scale=0.4, box_reg_gain=40.0)   # the benchmarked size: 800x800, 40 objects / image; init gains so that loss_box_reg and mt_fg_loss are O(0.1)
     if "color_views" in which: gen_color_views()
     if "source_items" in which: gen_source_items()
     if "relation" in which: gen_relation()

@@ -532,6 +532,13 @@ CONV_CASES = [
     (3, 14, 14, 256, 256, 3, 1, 1),
     (1, 20, 20, 256, 32, 1, 1, 0),
     (2, 9, 9, 2048, 256, 1, 1, 0),
+    (1, 1, 1024, 12544, 1024, 1, 1, 0),   # FC6 as the box head runs it: 1024 ROIs x (7*7*256) -> 1024 (392 K blocks / tile)
+    (5, 14, 14, 256, 1024, 1, 1, 0),      # mask predictor's ConvTranspose2d(256, 256, 2, 2) as ONE 1x1 conv with 4*256 outputs
+]
+# heads whose channel count is padded to the TMA granularity (15 -> 16: fused RPN cls+bbox, fused box predictor)
+HEAD_CASES = [
+    (2, 50, 50, 256, 16, 1, 1, 0),
+    (1, 1, 1000, 1024, 16, 1, 1, 0),
 ]
 
 
@@ -605,6 +612,34 @@ def test_conv_dgrad_wgrad(cuda, impl):
         assert _rel(db.cpu(), dy.sum((0, 2, 3))) < 1e-5
 
 
+def test_conv_padded_heads_tc(cuda):
+    """16-channel (15 padded) heads: fprop + wgrad on the tcgen05 kernels (BN = 32 tile, TMA clips the stores); dgrad of
+    these shapes (GEMM K = 16) is routed to the FFMA kernel by CONV_AUTO and must agree as well."""
+    import torch.nn.functional as Fn
+    kn = K()
+    gen = torch.Generator().manual_seed(33)
+    for case in HEAD_CASES:
+        B, H, W, Ci, Co, k, s, p = case
+        x, w = _conv_inputs(case, gen, cuda)
+        w[15:] = 0                                     # the padding row
+        bias = torch.randn(Co, generator=gen)
+        shape = kn.conv_shape(B, H, W, Ci, Co, k, s, p)
+        dy = torch.randn(B, Co, shape.out_h, shape.out_w, generator=gen)
+        xd = x.permute(0, 2, 3, 1).contiguous().to(cuda)
+        wd = w.permute(0, 2, 3, 1).contiguous().to(cuda)
+        dyd = dy.permute(0, 2, 3, 1).contiguous().to(cuda)
+        y = kn.conv_fprop(xd, wd, shape, None, bias.to(cuda), None, False, kn.CONV_TCGEN05).permute(0, 3, 1, 2).cpu()
+        ref = R.conv_bn_act_ref(x, w, None, bias, None, False, s, p, operands="tf32")
+        assert _rel(y, ref) < 1e-4, (case, _rel(y, ref))
+        xr, wr = x.double().requires_grad_(True), w.double().requires_grad_(True)
+        Fn.conv2d(xr, wr, None, s, p).backward(dy.double())
+        dw, db = kn.conv_wgrad(xd, dyd, shape, True, kn.CONV_TCGEN05)
+        assert _rel(dw.permute(0, 3, 1, 2).cpu(), wr.grad.float()) < 3e-3, case
+        assert _rel(db.cpu(), dy.sum((0, 2, 3))) < 1e-5
+        dx = kn.conv_dgrad(dyd, wd, shape, kn.CONV_AUTO).permute(0, 3, 1, 2).cpu()
+        assert _rel(dx, xr.grad.float()) < 3e-3, case
+
+
 def test_conv_stem_7x7_simt(cuda):
     import torch.nn.functional as Fn
     kn = K()
@@ -653,3 +688,85 @@ def test_conv_full_size_tc_vs_simt(cuda):
     # linearity (size-independent property): conv(2x) - 2 conv(x) == -bias
     y2 = kn.conv_fprop(2 * x, w, shape, None, b, None, False, kn.CONV_TCGEN05)
     assert _rel(y2 - 2 * y_tc, (-b).expand_as(y_tc)) < 1e-3
+
+
+# ------------------------------------------------------------------------- mask targets / paste
+def _mask_target_fixture():
+    g = golden("mask_targets")
+    xy, poly_len, inst_npoly = g["xy"], g["poly_len"], g["inst_npoly"]
+    polys, pos = [], 0
+    for n in poly_len:
+        polys.append(torch.from_numpy(xy[pos:pos + 2 * int(n)].astype(np.float32)))
+        pos += 2 * int(n)
+    inst, pi = [], 0
+    for n in inst_npoly:
+        inst.append(polys[pi:pi + int(n)])
+        pi += int(n)
+    return inst, g["which"], g["boxes"], g["masks"]
+
+
+def test_rasterize_polygons_bit_exact_reference_golden(cuda):
+    """mmt_rasterize_polygons_f32 == the reference's project_masks_on_boxes + pycocotools (mask_head/loss.py:37-75,
+    segmentation_mask.py:94-137, pycoco/maskApi.c:166-206) on all 96 golden ROIs — bit for bit, incl. the sub-pixel
+    box, the integer box and two-polygon instances — and == oracle.polygon_ref on 300 more random ROIs."""
+    from mmt_psm_b200.structures.segmentation_mask import SegmentationMask
+    from oracle import polygon_ref
+    kn = K()
+    inst, which, boxes, masks = _mask_target_fixture()
+    sm = SegmentationMask(inst, (800, 800))
+    got = kn.rasterize_polygons(sm.packed(cuda), torch.from_numpy(boxes).to(cuda), torch.from_numpy(which).to(cuda), 28)
+    got = got.cpu().numpy()
+    assert got.shape == (96, 28, 28) and set(np.unique(got)) <= {0.0, 1.0}
+    bad = [i for i in range(96) if not np.array_equal(got[i].astype(np.uint8), masks[i])]
+    assert not bad, bad
+    # random ROIs (boxes partly outside the instance, tiny and huge boxes, image-border clamps) against the oracle
+    gen = torch.Generator().manual_seed(91)
+    K2 = 300
+    w2 = torch.randint(0, len(inst), (K2,), generator=gen)
+    b2 = []
+    for i in w2.tolist():
+        pts = torch.cat(inst[i]).view(-1, 2)
+        lo, hi = pts.min(0)[0], pts.max(0)[0]
+        jit = (torch.rand(4, generator=gen) - 0.5) * 1.2 * torch.cat([hi - lo, hi - lo])
+        b2.append((torch.cat([lo, hi]) + jit).clamp(0, 799))
+    b2 = torch.stack(b2)
+    b2[:, 2:] = torch.max(b2[:, 2:], b2[:, :2])
+    b2[::7] = b2[::7].round()
+    got2 = kn.rasterize_polygons(sm.packed(cuda), b2.to(cuda), w2.to(cuda), 28).cpu().numpy()
+    ref2 = polygon_ref.project_masks_on_boxes_ref([[p.numpy() for p in inst[i]] for i in w2.tolist()], b2.numpy(), 28)
+    bad = [i for i in range(K2) if not np.array_equal(got2[i], ref2[i])]
+    assert not bad, bad
+
+
+def test_paste_masks_sum_vs_oracle(cuda):
+    """mmt_paste_masks_sum_f32 == Masker paste (pad 1, expand, int box, bilinear resize, > 0.5, clip to the image) summed
+    over the detections of each image (mask_head/inference.py:169-231, generalized_rcnn.py:129-132) as restated by
+    oracle.model_cpu.paste_sum: integral foreground map identical except where the interpolated probability sits within
+    float rounding of the 0.5 threshold (<= 1e-4 of the pixels), boxes partly / wholly outside the image, 1-pixel boxes,
+    and an image without detections."""
+    from oracle.model_cpu import paste_sum
+    kn = K()
+    gen = torch.Generator().manual_seed(92)
+    H, W, M, n_img = 300, 420, 28, 3
+    D = 60
+    c = torch.rand(D, 2, generator=gen) * torch.tensor([W, H])
+    wh = torch.rand(D, 2, generator=gen) * 120 + 2
+    boxes = torch.cat([c - wh / 2, c + wh / 2], 1)
+    boxes[0] = torch.tensor([-30., -20., 40., 35.])       # sticks out top-left
+    boxes[1] = torch.tensor([400., 280., 470., 330.])     # sticks out bottom-right
+    boxes[2] = torch.tensor([500., 100., 560., 150.])     # wholly outside
+    boxes[3] = torch.tensor([100.3, 100.6, 100.9, 101.2])  # sub-pixel
+    yy, xx = torch.meshgrid(torch.arange(M, dtype=torch.float32), torch.arange(M, dtype=torch.float32), indexing="ij")
+    r = ((xx - 13.5) ** 2 + (yy - 13.5) ** 2).sqrt()
+    probs = torch.sigmoid((torch.rand(D, 1, 1, generator=gen) * 8 + 5 - r) * 0.7) * (0.6 + 0.4 * torch.rand(D, M, M, generator=gen))
+    img = torch.randint(0, 2, (D,), generator=gen)        # image 2 gets no detection
+    got = kn.paste_masks_sum(probs.to(cuda), boxes.to(cuda), img.to(cuda), n_img, H, W).cpu()
+    assert got.shape == (n_img, H, W) and float(got[2].abs().sum()) == 0.0
+    total_diff = 0
+    for i in range(2):
+        sel = img == i
+        ref = paste_sum(probs[sel], boxes[sel], H, W)
+        total_diff += int((got[i] != ref).sum())
+        assert float((got[i] - ref).abs().max()) <= 1.0      # a disagreeing pixel differs by ONE detection's vote
+        assert float(ref.max()) >= 2                              # overlapping detections are summed, not OR-ed
+    assert total_diff <= 1e-4 * 2 * H * W, total_diff

@@ -300,3 +300,33 @@ def test_oracle_properties_hypothesis():
     nms_props()
     coder_roundtrip()
     label_props()
+
+
+def _mask_target_fixture():
+    """tests/golden/mask_targets.npz -> (instances: per instance a list of flat fp32 polygons, which, boxes, masks)."""
+    g = golden("mask_targets")
+    xy, poly_len, inst_npoly = g["xy"], g["poly_len"], g["inst_npoly"]
+    polys, pos = [], 0
+    for n in poly_len:
+        polys.append(xy[pos:pos + 2 * int(n)].astype(np.float32))
+        pos += 2 * int(n)
+    inst, pi = [], 0
+    for n in inst_npoly:
+        inst.append(polys[pi:pi + int(n)])
+        pi += int(n)
+    return inst, g["which"], g["boxes"], g["masks"]
+
+
+def test_polygon_oracle_bit_exact_reference_mask_targets():
+    """oracle.polygon_ref (rleFrPoly / decode / merge restated) reproduces all 96 28x28 mask targets the reference's
+    project_masks_on_boxes + its own pycocotools build produced (mask_head/loss.py:37-75, structures/segmentation_mask.py:
+    94-137, pycoco/maskApi.c:166-206) — bit for bit, including the sub-pixel box (row 3: w, h < 1 clamp to 1), the
+    integer box (row 5) and the two-polygon instances."""
+    from oracle import polygon_ref
+    inst, which, boxes, masks = _mask_target_fixture()
+    assert masks.shape == (96, 28, 28) and any(len(p) == 2 for p in inst)
+    got = polygon_ref.project_masks_on_boxes_ref([inst[i] for i in which], boxes, 28)
+    assert got.dtype == np.float32 and set(np.unique(got)) <= {0.0, 1.0}
+    bad = [i for i in range(len(which)) if not np.array_equal(got[i].astype(np.uint8), masks[i])]
+    assert not bad, bad
+    assert masks.any(axis=(1, 2)).mean() > 0.9 and 0.2 < masks.mean() < 0.9     # the fixture is not trivially empty / full

@@ -19,14 +19,17 @@ from ..utils.comm import get_world_size
 from ..utils.miscellaneous import sigmoid_rampdown, sigmoid_rampup
 
 
-def reduce_loss_dict(loss_dict):
-    """Logging-only reduction to rank 0 (reference MTtrainer.py:16-41)."""
+def reduce_loss_dict(loss_dict, keys=None):
+    """Logging-only reduction to rank 0 (reference MTtrainer.py:16-41).  `keys`: the fixed set of terms every rank
+    contributes to the collective — a rank whose iteration skipped a branch (teacher without boxes: no mt_* terms)
+    sends zeros for the terms it lacks instead of a shorter tensor."""
     world = get_world_size()
     if world < 2:
         return loss_dict
     with torch.no_grad():
-        names = sorted(loss_dict.keys())
-        vals = torch.stack([loss_dict[k].reshape(()) for k in names], dim=0)
+        names = sorted(keys) if keys is not None else sorted(loss_dict.keys())
+        ref = next(iter(loss_dict.values()))
+        vals = torch.stack([loss_dict[k].reshape(()).to(ref.dtype) if k in loss_dict else ref.new_zeros(()) for k in names], dim=0)
         dist.reduce(vals, dst=0)
         if dist.get_rank() == 0:
             vals /= world
@@ -77,6 +80,11 @@ class MTtrainer(object):
         # land at random inside iterations that are ~30 ms long: pace it instead — automatic collection off, a young-
         # generation collection every `gc_every` iterations (0 = leave the interpreter's GC alone)
         self.gc_every, self._gc_steps = 50, 0
+        self.loss_keys = ["loss_classifier", "loss_box_reg", "loss_seg", "loss_objectness", "loss_rpn_box_reg"]
+        if cfg.MODEL.RELATION_NMS.USE_RELATION_NMS:
+            self.loss_keys.append("nms_loss")
+        if cfg.MT.LAMBDA > 0 and cfg.DATASETS.NO_LABEL:
+            self.loss_keys += [k for k, on in (("mt_classifier", cfg.MT.CLS_LOSS), ("mt_fg_loss", cfg.MT.FG_HINT)) if on]
         self.set_cuda_graphs(cuda_graphs)
 
     def set_cuda_graphs(self, on):
@@ -195,12 +203,13 @@ class MTtrainer(object):
             losses_dict, losses = sup_weighted, sup_total
             losses.backward()
         if self.world > 1:
-            dist.all_reduce(self.optimizer.flat_g)  # one NCCL all-reduce over the whole student gradient arena
+            # one NCCL all-reduce: the whole student gradient arena + the per-tensor "touched" flags behind it
+            dist.all_reduce(self.optimizer.reduce_buffer())
         ema = None
         if self.lambda_value > 0 and iteration > (self.start_mt - 10):
             ema = min(1 - 1 / (iteration - (self.start_mt - 10) + 1), self.alpha)
         self.optimizer.step(ema_alpha=ema, grad_scale=1.0 / self.world)
-        self.last_losses = losses_dict
+        self.last_losses = {k: v.detach() for k, v in losses_dict.items()}
         return losses_dict, losses
 
     def train(self):
@@ -217,7 +226,7 @@ class MTtrainer(object):
                 data_u, _ = self._next_unlabeled()   # fetched up front so that its trunks can be prefetched
             losses_dict, losses = self.train_step(iteration, data_s, target_s, data_u)
             if iteration % 20 == 0 or iteration == self.max_iter:  # the only host syncs of the loop
-                red = reduce_loss_dict(losses_dict)
+                red = reduce_loss_dict(losses_dict, self.loss_keys)
                 meters.update(loss=sum(v for v in red.values()), **red)
                 meters.update(time=(time.time() - end) / (20 if iteration else 1))
                 end = time.time()
@@ -227,18 +236,26 @@ class MTtrainer(object):
                     torch.cuda.max_memory_allocated() / 1024.0 / 1024.0))
             if iteration % self.checkpoint_period == 0:
                 self.save_model(iteration)
+            if iteration % 1000 == 999:
+                gc.collect()          # full collection (generation 2) at a point where a pause costs nothing measurable
         self.save_model(iteration + 1, final=True)
+        if self.gc_every > 0:
+            gc.enable()
         total = time.time() - t0
         self.logger.info("Total training time: %s (%.4f s / it)" % (datetime.timedelta(seconds=total), total / max(self.max_iter, 1)))
 
     def save_model(self, iteration=0, final=False):
         if self.ckpt_s is None:
             return
+        # `iteration` stored in the file = number of COMPLETED steps (the step the resumed run starts with): the periodic
+        # save runs after 0-based step `iteration` has been applied, the final one is called with iteration + 1 already.
+        # The teacher is saved whenever its EMA has started (MTtrainer.train_step: iteration > START_MT - 10).
+        ema_on = self.lambda_value > 0 and iteration > (self.start_mt - 10)
         if iteration > 0 and not final:
-            self.ckpt_s.save("model_{:07d}".format(iteration), iteration=iteration)
-            if iteration > self.start_mt:
-                self.ckpt_t.save("t_model_{:07d}".format(iteration), iteration=iteration)
+            self.ckpt_s.save("model_{:07d}".format(iteration), iteration=iteration + 1)
+            if ema_on:
+                self.ckpt_t.save("t_model_{:07d}".format(iteration), iteration=iteration + 1)
         if final:
             self.ckpt_s.save("model_final", iteration=iteration)
-            if iteration > self.start_mt:
+            if ema_on:
                 self.ckpt_t.save("t_model_final", iteration=iteration)

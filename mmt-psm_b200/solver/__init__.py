@@ -26,7 +26,13 @@ class FusedSGDEMA(object):
             total += (n + 3) // 4 * 4
         self.total = total
         self.flat_p = torch.zeros(total, dtype=torch.float32, device=device)
-        self.flat_g = torch.zeros(total, dtype=torch.float32, device=device)
+        # gradient arena + one "this tensor received a gradient" flag per tensor behind it: data-parallel ranks all-reduce
+        # BOTH in the one exchange of the path (`reduce_buffer`), so the set of tensors SGD updates is the same on every
+        # rank even when one rank's iteration skipped a branch (e.g. its teacher produced no boxes)
+        self._g_full = torch.zeros(total + (len(params) + 3) // 4 * 4, dtype=torch.float32, device=device)
+        self.flat_g = self._g_full[:total]
+        self._flags = self._g_full[total:total + len(params)]
+        self._agreed = False
         self.flat_m = torch.zeros(total, dtype=torch.float32, device=device)
         self.touched = [False] * len(params)
         self._index = {id(p): i for i, (_, p) in enumerate(params)}
@@ -71,8 +77,16 @@ class FusedSGDEMA(object):
         self.param_groups[0]["lr"] = lr
 
     def zero_grad(self):
-        self.flat_g.zero_()
+        self._g_full.zero_()
+        self._agreed = False
         self.touched = [False] * len(self.entries)
+
+    def reduce_buffer(self):
+        """The tensor a data-parallel trainer all-reduces (SUM): the gradient arena followed by this rank's per-tensor
+        touched flags.  After the reduction `step` updates every tensor ANY rank accumulated a gradient into."""
+        self._flags.copy_(torch.tensor(self.touched, dtype=torch.float32), non_blocking=True)
+        self._agreed = True
+        return self._g_full
 
     def _segments(self, touched):
         key = (self.lr, tuple(touched))
@@ -84,10 +98,16 @@ class FusedSGDEMA(object):
             self._seg_cache[key] = K.make_segments(ent, self.flat_p.device)
         return self._seg_cache[key]
 
+    def _agreed_segments(self):
+        """Segment table whose update mask comes from the all-reduced flags: built on the device, no read-back."""
+        segs = self._segments([True] * len(self.entries)).clone()
+        segs.view(torch.int32).view(-1, 8)[:, 6] *= (self._flags > 0).to(torch.int32)   # mmt_param_segment.trainable
+        return segs
+
     def step(self, ema_alpha=None, grad_scale=1.0):
         """SGD on every tensor that received a gradient this iteration (torch.optim.SGD skips grad-less params),
         then, if `ema_alpha` is given, teacher <- alpha * teacher + (1 - alpha) * student over ALL parameters."""
-        segs = self._segments(self.touched)
+        segs = self._agreed_segments() if self._agreed else self._segments(self.touched)
         teacher = self.flat_t if ema_alpha is not None else None
         K.sgd_ema_(self.flat_p, teacher, self.flat_g, self.flat_m, segs, len(self.entries), self.momentum,
                    0.0 if ema_alpha is None else ema_alpha, self.first_step, grad_scale)

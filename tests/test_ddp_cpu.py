@@ -48,10 +48,29 @@ def _worker(rank, world, port, out):
     assert torch.allclose(opt.flat_g, sum(gathered)), "arena all-reduce != sum of the local arenas"
     assert torch.equal(student[0].weight.grad, opt.flat_g[:35].view(7, 5))   # parameters see the reduced gradient
     assert all(opt.touched)
-    # logging reduce (reference MTtrainer.py:16-41): rank 0 receives the mean
+    # a rank whose iteration skipped a branch (rank 1: no gradient for the second layer) must still update the same
+    # tensors as everybody else: the touched flags travel with the gradient arena in the one all-reduce
+    opt.zero_grad()
+    (student(x).sum() if rank == 0 else student[0](x).sum()).backward()
+    assert opt.touched == ([True] * 4 if rank == 0 else [True, True, False, False])
+    dist.all_reduce(opt.reduce_buffer())
+    mask = opt._agreed_segments().view(torch.int32).view(-1, 8)[:, 6]
+    assert mask.tolist() == [1, 1, 1, 1], mask.tolist()                       # identical on both ranks
+    masks = [None] * world
+    dist.all_gather_object(masks, mask.tolist())
+    assert masks[0] == masks[1]
+    opt.zero_grad()
+    student[0](x).sum().backward()                                            # nobody touches layer 2: nobody updates it
+    dist.all_reduce(opt.reduce_buffer())
+    assert opt._agreed_segments().view(torch.int32).view(-1, 8)[:, 6].tolist() == [1, 1, 0, 0]
+    # logging reduce (reference MTtrainer.py:16-41): rank 0 receives the mean; a rank lacking a term sends zero for it
     red = reduce_loss_dict({"loss_a": torch.tensor(float(rank)), "mt_b": torch.tensor(2.0 * rank)})
     if rank == 0:
         assert abs(float(red["loss_a"]) - 0.5) < 1e-6 and abs(float(red["mt_b"]) - 1.0) < 1e-6
+    mine = {"loss_a": torch.tensor(1.0)} if rank == 1 else {"loss_a": torch.tensor(1.0), "mt_b": torch.tensor(4.0)}
+    red = reduce_loss_dict(mine, keys=["loss_a", "mt_b"])
+    if rank == 0:
+        assert abs(float(red["loss_a"]) - 1.0) < 1e-6 and abs(float(red["mt_b"]) - 2.0) < 1e-6
     # sharding: disjoint, covering, equal-sized
     ds = list(range(11))
     mine = list(DistributedSampler(ds, shuffle=True))

@@ -213,6 +213,10 @@ def run_ours(args):
     from mmt_psm_b200.utils.synthetic_init import init_model
     lib.lib()
 
+    prealloc_gb = float(os.environ.get("MMT_PREALLOC_GB", "0"))
+    if prealloc_gb > 0:
+        # one big block in the caching allocator's large pool: later large requests split it instead of calling cudaMalloc
+        torch.empty(int(prealloc_gb * (1 << 30)), dtype=torch.uint8, device=dev)
     mt = args.workload in ("mt", "mt_relation")
     cfg = mt_psm_cfg(start_mt=0, relation=args.workload == "mt_relation") if mt else supervised_cfg()
     torch.manual_seed(0)
@@ -252,6 +256,7 @@ def run_ours(args):
         h2d += sum(p.numel() * 4 for inst in t.get_field("masks").polygons for p in inst.polygons)
 
     it_counter = [2000]
+    e2e_warm = True
 
     def step(j, e2e):
         it = it_counter[0]
@@ -269,25 +274,41 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def alloc_counters():
+        st = torch.cuda.memory_stats(dev)
+        return (st.get("num_device_alloc", 0), st.get("num_device_free", 0), st.get("num_alloc_retries", 0),
+                st.get("reserved_bytes.all.current", 0) >> 20)
+
+    step_stats = {}
+
     def timed(k, e2e):
         barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(k + 1)]
         t0 = time.perf_counter()
-        e0.record()
+        marks[0].record()
         last = None
         trace = os.environ.get("MMT_BENCH_TRACE") == "1"
+        host_ms = []
         for j in range(k):
             if trace:
                 torch.cuda.synchronize()
-                ts = time.perf_counter()
+                a0 = alloc_counters()
+            ts = time.perf_counter()
             last = step(j, e2e)
+            marks[j + 1].record()             # no sync: per-step device time is read back after the region
+            host_ms.append((time.perf_counter() - ts) * 1e3)
             if trace:
                 torch.cuda.synchronize()
-                print("step %s %d: %.2f ms" % ("e2e" if e2e else "dev", j, (time.perf_counter() - ts) * 1e3), file=sys.stderr, flush=True)
-        e1.record()
+                a1 = alloc_counters()
+                print("step %s %d: %.2f ms (host enqueue %.2f)  cudaMalloc +%d cudaFree +%d retries +%d reserved %d MiB" % (
+                    "e2e" if e2e else "dev", j, (time.perf_counter() - ts) * 1e3, host_ms[-1], a1[0] - a0[0], a1[1] - a0[1],
+                    a1[2] - a0[2], a1[3]), file=sys.stderr, flush=True)
         barrier()
         wall = time.perf_counter() - t0
-        ms = e0.elapsed_time(e1)
+        ms = marks[0].elapsed_time(marks[k])
+        per = sorted(marks[j].elapsed_time(marks[j + 1]) for j in range(k))
+        step_stats["e2e" if e2e else "dev"] = {"median_ms": per[k // 2], "max_ms": per[-1], "min_ms": per[0],
+                                               "host_enqueue_median_ms": sorted(host_ms)[k // 2]}
         if e2e:
             ms = max(ms, wall * 1e3)         # the host is part of the e2e path
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -297,7 +318,10 @@ def run_ours(args):
 
     for j in range(args.warmup):
         step(j, False)
+        if j == 0 and e2e_warm:
+            step(j, True)                     # the e2e path's own first-use costs (pinned staging, target packing) too
     barrier()
+    a_before = alloc_counters()
     sampler = ClockSampler(local) if (rank == 0 and os.environ.get("MMT_NO_CLOCKS") != "1") else None
     lib.reset_launch_count()
     ms_dev, last = timed(args.steps, False)
@@ -305,6 +329,18 @@ def run_ours(args):
     final_loss = float(last)
     ms_e2e, last_e2e = timed(args.steps, True)
     clocks = sampler.stop() if sampler else None
+    a_after = alloc_counters()
+    # data-parallel replicas must be bit-identical: students see the same all-reduced gradient and the same update mask,
+    # teachers are an EMA of identical students (no traffic).  64-bit checksums of both arenas, gathered OUTSIDE the timed region
+    replicas_identical = None
+    if world > 1:
+        cs = torch.stack([opt.flat_p.view(torch.int32).to(torch.int64).sum(), opt.flat_t.view(torch.int32).to(torch.int64).sum(),
+                          (opt.flat_p.view(torch.int32).to(torch.int64) * torch.arange(1, opt.flat_p.numel() + 1, device=dev)).sum()])
+        allcs = [torch.zeros_like(cs) for _ in range(world)]
+        dist.all_gather(allcs, cs)
+        replicas_identical = all(torch.equal(allcs[0], c) for c in allcs)
+        if not replicas_identical:
+            raise RuntimeError("data-parallel replicas diverged: arena checksums %s" % [c.tolist() for c in allcs])
     if not (final_loss == final_loss and abs(final_loss) < 1e6):
         raise RuntimeError("non-finite / diverged loss in the timed region: %r" % final_loss)
 
@@ -370,7 +406,11 @@ def run_ours(args):
                           "final_loss": final_loss},
                "e2e": {"value": imgs / (ms_e2e * 1e-3), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                        "ms_per_step": ms_e2e / args.steps},
-               "gpu_launches": launches, "clocks": clocks}
+               "gpu_launches": launches, "clocks": clocks, "step_ms": step_stats,
+               "allocator": {"cudaMalloc_in_timed_region": a_after[0] - a_before[0], "cudaFree_in_timed_region": a_after[1] - a_before[1],
+                             "reserved_mib": a_after[3]}}
+        if replicas_identical is not None:
+            out["replicas_identical"] = replicas_identical
         if roof:
             out["roofline"] = roof
             out["kernel_families"] = families

@@ -77,11 +77,18 @@ __device__ __forceinline__ void named_bar_sync(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
+// Shared-memory map of one CTA.  Every address is affine in the stage index, so the per-stage lookups are computed
+// (base + stage * stride) instead of being read from an array indexed by a runtime value: such an array lives in
+// LOCAL memory (r01: a 160-byte stack frame, 20 STL in every prologue and an LDL per lookup inside the producer / MMA loops).
+struct StageAddr {
+  uint32_t base, stride;
+  __device__ __forceinline__ uint32_t operator[](int s) const { return base + (uint32_t)s * stride; }
+};
 struct SmemLayout {
-  uint32_t a[8], b[8];
-  uint32_t staging;  // 4 epilogue warps x 2 buffers x 4 KB (32 rows x 128 B, SWIZZLE_128B)
+  StageAddr a, b;
+  uint32_t staging;  // epilogue warps x 4 KB (32 rows x 128 B, SWIZZLE_128B)
   uint32_t affine;   // scale[BN] then shift[BN]
-  uint32_t full[8], empty[8], tfull[2], tempty[2];
+  StageAddr full, empty, tfull, tempty;
   uint32_t tmem_slot;
 };
 
@@ -90,25 +97,17 @@ __device__ __forceinline__ SmemLayout carve(uint8_t* raw) {
   SmemLayout L;
   const uint32_t base = smem_u32(raw);
   if (base & 1023u) __trap();  // extern __shared__ __align__(1024) was not honoured
-#pragma unroll
-  for (int s = 0; s < 8; ++s) {
-    L.a[s] = base + (s < STAGES ? s : 0) * (A_BYTES + B_BYTES);
-    L.b[s] = L.a[s] + A_BYTES;
-  }
+  L.a = StageAddr{base, (uint32_t)(A_BYTES + B_BYTES)};
+  L.b = StageAddr{base + (uint32_t)A_BYTES, (uint32_t)(A_BYTES + B_BYTES)};
   uint32_t p = base + STAGES * (A_BYTES + B_BYTES);
   L.staging = p;
   p += 2 * kStagingBytes;
   L.affine = p;
   p += AFFINE_BYTES;
-#pragma unroll
-  for (int s = 0; s < 8; ++s) {
-    L.full[s] = p + 8 * s;
-    L.empty[s] = p + 64 + 8 * s;
-  }
-  L.tfull[0] = p + 128;
-  L.tfull[1] = p + 136;
-  L.tempty[0] = p + 144;
-  L.tempty[1] = p + 152;
+  L.full = StageAddr{p, 8u};
+  L.empty = StageAddr{p + 64u, 8u};
+  L.tfull = StageAddr{p + 128u, 8u};
+  L.tempty = StageAddr{p + 144u, 8u};
   L.tmem_slot = p + 160;
   return L;
 }

@@ -24,6 +24,9 @@ import sys
 import threading
 import time
 
+# before torch initialises CUDA: grow the caching allocator by mapping pages instead of cudaMalloc (see MTtrainer.__init__)
+os.environ.setdefault("PYTORCH_CUDA_ALLOC_CONF", "expandable_segments:True")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

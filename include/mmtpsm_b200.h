@@ -374,6 +374,13 @@ typedef struct {
 /* Persistent-grid size of the tcgen05 conv kernels launched (or captured into a CUDA graph) from now on: n CTAs,
  * one per SM, leaving 148 - n SMs free for kernels of other streams.  Default 148. */
 int mmt_conv_set_max_ctas(int n);
+/* Tile configuration of the tcgen05 fprop / dgrad kernel: 0 = the library's cost model chooses per problem between one
+ * CTA per 128 x BN tile and a CTA pair (tcgen05 cta_group::2, cluster of 2) per 256 x BN tile; 1 / 2 force one of them
+ * (parity tests and per-layer benchmarks). */
+int mmt_conv_force_cta_group(int cta_group);
+/* Programmatic dependent launch of the tcgen05 kernels (default on): their prologue (barrier init, TMEM allocation,
+ * descriptor prefetch) overlaps the tail of the previous kernel of the stream; 0 = plain stream serialisation. */
+int mmt_conv_set_pdl(int on);
 size_t mmt_conv_workspace_bytes(const mmt_conv_shape* shape);
 int mmt_conv_fprop_f32(const float* x_nhwc, const float* w_ohwi, const float* scale /*nullable*/,
                        const float* bias /*nullable*/, const float* residual_nhwc /*nullable*/,
@@ -401,6 +408,23 @@ int mmt_conv_wgrad_f32(const float* x_nhwc, const float* dy_nhwc, float* dw_ohwi
  * temporary, no separate accumulation pass. */
 int mmt_conv_wgrad_accumulate_f32(const float* x_nhwc, const float* dy_nhwc, float* dw_ohwi, const mmt_conv_shape* shape,
                                   void* stream);
+
+/* Fused backward of Conv2d -> FrozenBatchNorm2d [-> ReLU] chains (layers/batch_norm.py:19-24, resnet.py:254-275 under
+ * autograd).  `dy` is the gradient of the BN OUTPUT; `k_scale` (nullable, per out channel) is the frozen-BN scale, folded
+ * into the transformed filter; the epilogue combines the result with `aux` (dense NHWC, shaped like dx):
+ *   MMT_DGRAD_AUX_ADD  : dx = conv_T(dy * scale, w) + aux        (gradient arriving through the skip connection)
+ *   MMT_DGRAD_AUX_MASK : dx = aux > 0 ? conv_T(dy * scale, w) : 0  (ReLU backward of the layer whose OUTPUT aux is — this
+ *                        conv's input)
+ * tcgen05 path only (MMT_ERR_UNSUPPORTED otherwise; aux needs stride 1); workspace as mmt_conv_dgrad_f32. */
+#define MMT_DGRAD_AUX_NONE 0
+#define MMT_DGRAD_AUX_ADD 1
+#define MMT_DGRAD_AUX_MASK 2
+int mmt_conv_dgrad_fused_f32(const float* dy_nhwc, const float* w_ohwi, const float* k_scale /*nullable*/,
+                             const float* aux_nhwc /*nullable*/, int aux_mode, float* dx_nhwc, const mmt_conv_shape* shape,
+                             void* workspace, size_t workspace_bytes, void* stream);
+/* dw (+)= row_scale[o] * wgrad(x, dy)[o]  (row_scale nullable; accumulate != 0: add into a live gradient buffer). */
+int mmt_conv_wgrad_scaled_f32(const float* x_nhwc, const float* dy_nhwc, const float* row_scale /*nullable*/,
+                              float* dw_ohwi, const mmt_conv_shape* shape, int accumulate, void* stream);
 
 /* Fused elementwise helpers around the convs (all NHWC fp32, contiguous) ------------------- */
 /* g_out = g_in * (y > 0) * scale[c]  (ReLU + FrozenBN backward; scale nullable, relu optional) */

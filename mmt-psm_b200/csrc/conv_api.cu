@@ -77,6 +77,47 @@ extern "C" int mmt_conv_dgrad_f32(const float* dy, const float* w, float* dx, co
   return mmt::conv_dgrad_tc(dy, w_t, dx, *s, stream);
 }
 
+// Fused backward of Conv -> FrozenBN(scale) [-> ReLU] chains (reference layers/batch_norm.py:19-24 + resnet.py:254-275 under
+// autograd): `dy` is the gradient of the BN OUTPUT; the BN scale is folded into the transformed filter, and the epilogue
+// either adds `aux` (the skip connection's gradient) or masks with aux > 0 (ReLU backward of the layer that produced this
+// conv's input) — the elementwise passes torch's autograd would launch around the convolution.  tcgen05 path only.
+extern "C" int mmt_conv_dgrad_fused_f32(const float* dy, const float* w, const float* k_scale, const float* aux,
+                                        int aux_mode, float* dx, const mmt_conv_shape* s, void* workspace,
+                                        size_t workspace_bytes, void* stream_) {
+  if (int rc = check_shape(s, "conv_dgrad_fused")) return rc;
+  if (s->batch == 0) return MMT_OK;
+  MMT_REQUIRE(dy && w && dx, "conv_dgrad_fused: null pointer");
+  MMT_REQUIRE(aux_mode == 0 || ((aux_mode == MMT_DGRAD_AUX_ADD || aux_mode == MMT_DGRAD_AUX_MASK) && aux != nullptr),
+              "conv_dgrad_fused: aux_mode %d needs an aux tensor", aux_mode);
+  if (!mmt::conv_tc_supported_dgrad(*s))
+    return mmt::fail(MMT_ERR_UNSUPPORTED, "conv_dgrad_fused: shape not supported by the tcgen05 kernel");
+  if (aux_mode && s->stride != 1)
+    return mmt::fail(MMT_ERR_UNSUPPORTED, "conv_dgrad_fused: the epilogue tensor needs a stride-1 convolution");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const size_t need = mmt::align_up(filter_bytes(*s), 256);
+  if (workspace == nullptr || workspace_bytes < need)
+    return mmt::fail(MMT_ERR_WORKSPACE_TOO_SMALL, "conv_dgrad_fused: workspace %zu < required %zu", workspace_bytes, need);
+  MMT_REQUIRE(((uintptr_t)workspace & 255) == 0, "conv_dgrad_fused: workspace must be 256-byte aligned");
+  float* w_t = (float*)workspace;
+  if (int rc = mmt::conv_filter_for_dgrad(w, w_t, *s, stream, k_scale)) return rc;
+  return mmt::conv_dgrad_tc(dy, w_t, dx, *s, stream, aux, aux_mode);
+}
+
+// dw (+)= row_scale[o] * wgrad(x, dy): `dy` is the gradient of the BN output, row_scale the frozen-BN scale.
+extern "C" int mmt_conv_wgrad_scaled_f32(const float* x, const float* dy, const float* row_scale, float* dw,
+                                         const mmt_conv_shape* s, int accumulate, void* stream_) {
+  if (int rc = check_shape(s, "conv_wgrad_scaled")) return rc;
+  MMT_REQUIRE(dw != nullptr, "conv_wgrad_scaled: null dw");
+  if (s->batch == 0) {
+    if (!accumulate) MMT_CUDA(cudaMemsetAsync(dw, 0, filter_bytes(*s), (cudaStream_t)stream_));
+    return MMT_OK;
+  }
+  MMT_REQUIRE(x && dy, "conv_wgrad_scaled: null pointer");
+  if (!mmt::conv_tc_supported_wgrad(*s))
+    return mmt::fail(MMT_ERR_UNSUPPORTED, "conv_wgrad_scaled: shape not supported by the tcgen05 kernel");
+  return mmt::conv_wgrad_tc(x, dy, dw, nullptr, *s, nullptr, 0, (cudaStream_t)stream_, accumulate != 0, row_scale);
+}
+
 extern "C" int mmt_conv_wgrad_f32(const float* x, const float* dy, float* dw, float* dbias,
                                   const mmt_conv_shape* s, int impl, void* workspace, size_t workspace_bytes,
                                   void* stream_) {

@@ -30,11 +30,16 @@ size_t conv_stem_tc_workspace(const mmt_conv_shape& s);
 int conv_stem_tc(const float* x, const float* w, const float* scale, const float* bias, float* y,
                  const mmt_conv_shape& s, int flags, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 // w_t must hold the dgrad-transformed filter [in_c][k_h][k_w][out_c] (rotated 180 degrees)
+// `aux` (dense, shaped like dx) with aux_mode MMT_DGRAD_AUX_ADD: dx = conv_T(dy) + aux;  MMT_DGRAD_AUX_MASK: dx = aux > 0 ? conv_T(dy) : 0
 int conv_dgrad_tc(const float* dy, const float* w_t, float* dx, const mmt_conv_shape& s,
-                  cudaStream_t stream);
+                  cudaStream_t stream, const float* aux = nullptr, int aux_mode = 0);
+// row_scale (nullable): dw[o] (+)= row_scale[o] * wgrad(x, dy)[o]
 int conv_wgrad_tc(const float* x, const float* dy, float* dw, float* dbias, const mmt_conv_shape& s,
-                  void* workspace, size_t workspace_bytes, cudaStream_t stream, bool accumulate = false);
-// [out_c][k_h][k_w][in_c] -> [in_c][k_h][k_w][out_c] with the taps rotated by 180 degrees
-int conv_filter_for_dgrad(const float* w, float* w_t, const mmt_conv_shape& s, cudaStream_t stream);
+                  void* workspace, size_t workspace_bytes, cudaStream_t stream, bool accumulate = false,
+                  const float* row_scale = nullptr);
+// [out_c][k_h][k_w][in_c] -> [in_c][k_h][k_w][out_c] with the taps rotated by 180 degrees; k_scale (nullable) multiplies
+// every element by its OUT channel's factor
+int conv_filter_for_dgrad(const float* w, float* w_t, const mmt_conv_shape& s, cudaStream_t stream,
+                          const float* k_scale = nullptr);
 
 }  // namespace mmt

@@ -43,9 +43,12 @@ constexpr int kABytes = kTileM * 128;  // 128 rows x 32 fp32
 constexpr int kStagingBytes = kTileM * 128;
 constexpr int kSmemLimit = 232448;  // 227 KB
 
-template <int BN>
+// CG = CTAs cooperating on one MMA (tcgen05 cta_group): 1, or 2 = a CTA pair computing a 256 x BN tile, each CTA staging
+// its own 128 rows of A and BN / 2 rows of B.
+template <int BN, int CG = 1>
 struct Cfg {
-  static constexpr int kBBytes = BN * 128;
+  static constexpr int kBRows = BN / CG;
+  static constexpr int kBBytes = kBRows * 128;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kAffineBytes = 2 * BN * 4;  // per-tile copy of the epilogue scale / shift vectors
   static constexpr int kFixedBytes = 2 * kStagingBytes + kAffineBytes + 256 /*barriers*/;
@@ -68,8 +71,10 @@ struct FpropParams {
   const float* scale;
   const float* bias;
   const float* residual;
+  int res_mode;  // 0: y += residual;  1: y = residual > 0 ? y : 0  (ReLU backward of the layer that produced this conv's input)
   int relu;
-  int total_tiles;
+  int total_tiles;  // work units: (pixel tile, column tile) pairs; with CTA pairs a unit covers TWO consecutive pixel tiles
+  int m_tiles;      // pixel tiles
   int sub_w;  // per-warp store box: 32 pixels = sub_w x (32 / sub_w) of the TW x TH patch
 };
 
@@ -132,15 +137,18 @@ __device__ __forceinline__ void st_shared_f32(uint32_t addr, float x) {
   asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(x) : "memory");
 }
 
-template <int BN>
+template <int BN, int CG>
 __global__ void __launch_bounds__(kFpropThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmY, const FpropParams p) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, CG>;
   constexpr int STAGES = C::kStages;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const SmemLayout L = carve<STAGES, kABytes, C::kBBytes, C::kAffineBytes>(smem_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // CTA pair: rank 0 (leader) issues the MMAs; both CTAs load operands and run the epilogue of their own 128 rows
+  const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
 
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&tmA);
@@ -155,50 +163,86 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       mbar_init(L.tfull[0], 1);
       mbar_init(L.tfull[1], 1);
-      mbar_init(L.tempty[0], 8);  // one arrival per epilogue warp
-      mbar_init(L.tempty[1], 8);
+      mbar_init(L.tempty[0], 8 * CG);  // one arrival per epilogue warp (of both CTAs of a pair, on the leader's barrier)
+      mbar_init(L.tempty[1], 8 * CG);
       fence_barrier_init();
     }
     __syncwarp();
-    tmem_alloc(L.tmem_slot, C::kTmemCols);
-    tmem_relinquish();
+    if constexpr (CG == 2) {
+      tmem_alloc_cg2(L.tmem_slot, C::kTmemCols);
+      tmem_relinquish_cg2();
+    } else {
+      tmem_alloc(L.tmem_slot, C::kTmemCols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();  // the peer's barriers are initialised and its TMEM allocated before anything remote
   tc_fence_after();
   const uint32_t tmem_base = ld_shared_u32(L.tmem_slot);
+  // PDL: the prologue above ran while the previous kernel of the stream was finishing; from here on this kernel reads
+  // (activations, a just-transposed filter) and writes global memory, so the predecessor must have completed
+  pdl_launch_dependents();
+  pdl_wait();
 
   const int kblocks = p.kh * p.kw * p.cblocks;
   const int tiles_per_img = p.tiles_w * p.tiles_h;
+  const int unit0 = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int n_units = CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  // work unit -> this CTA's (column tile, pixel tile origin).  In a pair CTA `rank` takes pixel tile 2 * i + rank; the odd
+  // tile out at the end is computed twice (dup: same loads and MMA rows, no stores) so that every TMA box stays in bounds
+  auto locate = [&](int t, int& nt, int& b, int& h0, int& w0, bool& dup) {
+    nt = t % p.n_tiles;
+    int mt = t / p.n_tiles;
+    dup = false;
+    if constexpr (CG == 2) {
+      mt = mt * 2 + (int)rank;
+      if (mt >= p.m_tiles) { dup = true; mt = p.m_tiles - 1; }
+    }
+    b = mt / tiles_per_img;
+    const int rem = mt % tiles_per_img;
+    h0 = (rem / p.tiles_w) * p.TH;
+    w0 = (rem % p.tiles_w) * p.TW;
+  };
 
   if (warp == 0) {
     if (lane == 0) {
+      // pair: the transaction bytes of BOTH CTAs' loads are counted on the leader's full barrier
+      const uint32_t full_base = CG == 2 ? mapa_shared(L.full[0], 0) : L.full[0];
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-        const int nt = t % p.n_tiles, mt = t / p.n_tiles;
-        const int b = mt / tiles_per_img, rem = mt % tiles_per_img;
-        const int h0 = (rem / p.tiles_w) * p.TH, w0 = (rem % p.tiles_w) * p.TW;
+      for (int t = unit0; t < p.total_tiles; t += n_units) {
+        int nt, b, h0, w0;
+        bool dup;
+        locate(t, nt, b, h0, w0, dup);
         int kb = 0;
         for (int r = 0; r < p.kh; ++r)
           for (int s = 0; s < p.kw; ++s)
             for (int cb = 0; cb < p.cblocks; ++cb, ++kb) {
               mbar_wait(L.empty[stage], phase ^ 1u);
-              mbar_arrive_expect_tx(L.full[stage], (uint32_t)C::kStageBytes);
-              tma_load_4d(L.a[stage], &tmA, L.full[stage], cb * 32, w0 + s - p.pad_w, h0 + r - p.pad_h, b);
-              tma_load_2d(L.b[stage], &tmB, L.full[stage], kb * 32, nt * BN);
+              if constexpr (CG == 2) {
+                const uint32_t full = full_base + 8u * (uint32_t)stage;
+                if (leader) mbar_arrive_expect_tx(L.full[stage], 2u * (uint32_t)C::kStageBytes);
+                tma_load_4d_cg2(L.a[stage], &tmA, full, cb * 32, w0 + s - p.pad_w, h0 + r - p.pad_h, b);
+                tma_load_2d_cg2(L.b[stage], &tmB, full, kb * 32, nt * BN + (int)rank * C::kBRows);
+              } else {
+                mbar_arrive_expect_tx(L.full[stage], (uint32_t)C::kStageBytes);
+                tma_load_4d(L.a[stage], &tmA, L.full[stage], cb * 32, w0 + s - p.pad_w, h0 + r - p.pad_h, b);
+                tma_load_2d(L.b[stage], &tmB, L.full[stage], kb * 32, nt * BN);
+              }
               if (++stage == STAGES) { stage = 0; phase ^= 1u; }
             }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_tf32(kTileM, BN, 0, 0);
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = umma_idesc_tf32(kTileM * CG, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+      for (int t = unit0; t < p.total_tiles; t += n_units, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
         mbar_wait(L.tempty[acc], acc_phase ^ 1u);
@@ -211,12 +255,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int k = 0; k < 4; ++k) {
             const uint64_t da = umma_desc_kmajor_sw128(L.a[stage] + k * 32);
             const uint64_t db = umma_desc_kmajor_sw128(L.b[stage] + k * 32);
-            mma_tf32_ss(d_tmem, da, db, idesc, (kb | k) ? 1u : 0u);
+            if constexpr (CG == 2) mma_tf32_ss_cg2(d_tmem, da, db, idesc, (kb | k) ? 1u : 0u);
+            else mma_tf32_ss(d_tmem, da, db, idesc, (kb | k) ? 1u : 0u);
           }
-          mma_commit(L.empty[stage]);
+          if constexpr (CG == 2) mma_commit_cg2(L.empty[stage], 3);  // frees the stage in BOTH CTAs
+          else mma_commit(L.empty[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
-        mma_commit(L.tfull[acc]);
+        if constexpr (CG == 2) mma_commit_cg2(L.tfull[acc], 3);
+        else mma_commit(L.tfull[acc]);
       }
     }
     __syncwarp();
@@ -233,6 +280,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int sub_tw0 = (q * 32) % p.TW, sub_th0 = (q * 32) / p.TW;  // origin of this warp's 32-pixel store box
     const bool affine = (p.scale != nullptr) || (p.bias != nullptr);
     const bool has_res = p.residual != nullptr;
+    const uint32_t tempty_base = CG == 2 ? mapa_shared(L.tempty[0], 0) : L.tempty[0];
     // coalesced residual fetch: instruction i reads rows 4i + lane/8 (four whole 128-byte lines per warp instruction)
     const int col4 = lane & 7;
     int rtw[8], rth[8];
@@ -244,14 +292,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     int it = 0;
     int affine_nt = -1;
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
-      const int nt = t % p.n_tiles, mt = t / p.n_tiles;
-      const int b = mt / tiles_per_img, rem = mt % tiles_per_img;
-      const int h0 = (rem / p.tiles_w) * p.TH, w0 = (rem % p.tiles_w) * p.TW;
+    for (int t = unit0; t < p.total_tiles; t += n_units, ++it) {
+      int nt, b, h0, w0;
+      bool dup;
+      locate(t, nt, b, h0, w0, dup);
       const int acc = it & 1;
       const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
       const int n0 = nt * BN;
-      const int chunks = min(BN / 32, (p.n_out - n0 + 31) / 32);
+      const int chunks = dup ? 0 : min(BN / 32, (p.n_out - n0 + 31) / 32);
 
       if (affine && nt != affine_nt) {  // (re)load this column block's scale / shift: uniform over the 8 warps
         named_bar_sync(1, 256);         // every warp is done reading the previous block's values
@@ -269,7 +317,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       long long roff[8];
       bool rok[8];
       float4 rr[8];
-      if (has_res) {
+      if (has_res && !dup) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           rok[i] = (w0 + rtw[i] < p.y_w) && (h0 + rth[i] < p.y_h);
@@ -328,7 +376,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint32_t addr = buf + lane * 128 + ((g ^ (lane & 7)) << 4);
           if (has_res) {
             const float4 r4 = ld_shared_v4(addr);
-            o0 += r4.x; o1 += r4.y; o2 += r4.z; o3 += r4.w;
+            if (p.res_mode) {
+              o0 = r4.x > 0.f ? o0 : 0.f; o1 = r4.y > 0.f ? o1 : 0.f;
+              o2 = r4.z > 0.f ? o2 : 0.f; o3 = r4.w > 0.f ? o3 : 0.f;
+            } else {
+              o0 += r4.x; o1 += r4.y; o2 += r4.z; o3 += r4.w;
+            }
           }
           if (p.relu) {
             o0 = fmaxf(o0, 0.f); o1 = fmaxf(o1, 0.f); o2 = fmaxf(o2, 0.f); o3 = fmaxf(o3, 0.f);
@@ -345,16 +398,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // this warp has finished its tcgen05.ld of the accumulator
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(L.tempty[acc]);
+      if (lane == 0) {
+        if constexpr (CG == 2) mbar_arrive_cluster(tempty_base + 8u * (uint32_t)acc);
+        else mbar_arrive(L.tempty[acc]);
+      }
     }
     if (lane == 0) tma_wait_group<0>();
   }
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();  // nobody leaves while the leader may still read this CTA's smem / write its TMEM
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, C::kTmemCols);
+    if constexpr (CG == 2) tmem_dealloc_cg2(tmem_base, C::kTmemCols);
+    else tmem_dealloc(tmem_base, C::kTmemCols);
   }
 }
 
@@ -366,6 +424,8 @@ struct WgradParams {
   int co_tiles, ci_tiles, splits;
   int pixel_tiles, tiles_per_split;
   int cin;
+  int cout;
+  const float* row_scale;  // nullable: per-out-channel multiplier of the result (frozen-BN scale: dw = scale[o] * wgrad(x, g_bn_out))
   int total_items;
 };
 
@@ -404,6 +464,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = ld_shared_u32(L.tmem_slot);
+  pdl_launch_dependents();
+  pdl_wait();
   const int tiles_per_img = p.tiles_w * p.tiles_h;
   const int taps = p.kh * p.kw;
 
@@ -485,6 +547,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
       const int acc = it & 1;
       const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
       const bool empty_range = pe <= pb;  // nothing accumulated: MMA warp still commits, D undefined
+      const int orow = co_t * 128 + row;
+      const float rs = empty_range ? 0.f : ((p.row_scale && orow < p.cout) ? __ldg(p.row_scale + orow) : 1.f);
       mbar_wait(L.tfull[acc], acc_phase);
       tc_fence_after();
 #pragma unroll 1
@@ -499,10 +563,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
 #pragma unroll
         for (int g = 0; g < 8; ++g)
           st_shared_v4(buf + row * 128 + ((g ^ (row & 7)) << 4),
-                       empty_range ? 0.f : __uint_as_float(v[g * 4 + 0]),
-                       empty_range ? 0.f : __uint_as_float(v[g * 4 + 1]),
-                       empty_range ? 0.f : __uint_as_float(v[g * 4 + 2]),
-                       empty_range ? 0.f : __uint_as_float(v[g * 4 + 3]));
+                       empty_range ? 0.f : rs * __uint_as_float(v[g * 4 + 0]),
+                       empty_range ? 0.f : rs * __uint_as_float(v[g * 4 + 1]),
+                       empty_range ? 0.f : rs * __uint_as_float(v[g * 4 + 2]),
+                       empty_range ? 0.f : rs * __uint_as_float(v[g * 4 + 3]));
         fence_proxy_async_smem();
         named_bar_sync(1, 128);
         if (epi_tid == 0) {
@@ -524,8 +588,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
 }
 
 // [out_c][kh][kw][in_c] -> [in_c][kh][kw][out_c], taps rotated 180 degrees
+// `k_scale` (nullable): per-OUT-channel multiplier folded into the transformed filter — the frozen-BN scale of the
+// layer, so that dgrad consumes the gradient of the BN OUTPUT directly (dx = conv_T(g * scale, w) = conv_T(g, w * scale))
 __global__ void __launch_bounds__(256) filter_dgrad_kernel(const float* __restrict__ w, float* __restrict__ wt,
-                                                           int out_c, int taps, int in_c) {
+                                                           int out_c, int taps, int in_c,
+                                                           const float* __restrict__ k_scale) {
   __shared__ float tile[32][33];
   // per tap: transpose the [out_c][in_c] matrix (row stride taps*in_c) into [in_c][out_c]
   const int tap = blockIdx.z;
@@ -534,7 +601,7 @@ __global__ void __launch_bounds__(256) filter_dgrad_kernel(const float* __restri
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   for (int k = ty; k < 32; k += 8) {
     const int o = o0 + k, i = i0 + tx;
-    if (o < out_c && i < in_c) tile[k][tx] = w[((long long)o * taps + tap) * in_c + i];
+    if (o < out_c && i < in_c) tile[k][tx] = w[((long long)o * taps + tap) * in_c + i] * (k_scale ? __ldg(k_scale + o) : 1.f);
   }
   __syncthreads();
   for (int k = ty; k < 32; k += 8) {
@@ -673,6 +740,7 @@ struct GemmProblem {
   const float* bias;
   const float* residual;  // addressed like y with strides r_*
   long long r_sw, r_sh, r_sn;
+  int res_mode = 0;       // 0 add, 1 mask (see FpropParams)
   int relu;
   int prof_family;  // MMT_PROF_CONV_FPROP / MMT_PROF_CONV_DGRAD
   double flops_override = 0.0;  // algorithmic flops when the GEMM is padded (stem)
@@ -688,15 +756,41 @@ inline double gemm_bytes(const GemmProblem& g) {
   return 4.0 * (pix * g.a.c + (double)g.n_out * g.kh * g.kw * g.a.c + pix * g.n_out * (g.residual ? 2.0 : 1.0));
 }
 
-template <int BN>
+// Launch attributes of the tcgen05 kernels: the CTA pair (cluster of 2 = the two SMs of a TPC) and programmatic dependent
+// launch (the kernel's prologue overlaps the tail of the previous kernel of the stream; see tc_ptx.cuh pdl_wait).
+std::atomic<int> g_pdl{1};
+void fill_launch(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, int grid, int threads, size_t smem, cudaStream_t stream,
+                 int cluster) {
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  int n = 0;
+  if (cluster > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = (unsigned)cluster;
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (g_pdl.load(std::memory_order_relaxed)) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = (unsigned)n;
+}
+
+template <int BN, int CG>
 int launch_gemm(const GemmProblem& g, cudaStream_t stream) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, CG>;
   int TW, TH;
   pick_patch(g.y.w, g.y.h, kTileM, TW, TH);
   CUtensorMap tmA, tmB, tmY;
   if (int rc = make_map(&tmA, g.a, 32, TW, TH, "conv A operand")) return rc;
   const long long Ktot = (long long)g.kh * g.kw * g.a.c;
-  if (int rc = make_map_2d(&tmB, g.b, Ktot, g.n_out, Ktot, 32, BN, "conv filter")) return rc;
+  if (int rc = make_map_2d(&tmB, g.b, Ktot, g.n_out, Ktot, 32, C::kBRows, "conv filter")) return rc;
   const int sub_w = TW < 32 ? TW : 32;  // each epilogue warp stores its own 32-pixel box
   if (int rc = make_map(&tmY, g.y, 32, sub_w, 32 / sub_w, "conv output")) return rc;
   FpropParams p;
@@ -710,47 +804,72 @@ int launch_gemm(const GemmProblem& g, cudaStream_t stream) {
   p.pad_h = g.pad_h; p.pad_w = g.pad_w;
   p.y_w = (int)g.y.w; p.y_h = (int)g.y.h;
   p.r_sb = g.r_sn; p.r_sh = g.r_sh; p.r_sw = g.r_sw;
-  p.scale = g.scale; p.bias = g.bias; p.residual = g.residual; p.relu = g.relu;
-  const long long total = (long long)p.tiles_w * p.tiles_h * p.tiles_b * p.n_tiles;
-  if (total > 0x7fffffffll) return mmt::fail(MMT_ERR_UNSUPPORTED, "conv: too many tiles");
+  p.scale = g.scale; p.bias = g.bias; p.residual = g.residual; p.res_mode = g.res_mode; p.relu = g.relu;
+  const long long m_tiles = (long long)p.tiles_w * p.tiles_h * p.tiles_b;
+  const long long total = mmt::ceil_div<long long>(m_tiles, CG) * p.n_tiles;
+  if (m_tiles * p.n_tiles > 0x7fffffffll) return mmt::fail(MMT_ERR_UNSUPPORTED, "conv: too many tiles");
+  p.m_tiles = (int)m_tiles;
   p.total_tiles = (int)total;
   p.sub_w = sub_w;
   static bool attr_set = false;
   if (!attr_set) {
-    MMT_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+    MMT_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
     attr_set = true;
   }
-  const int grid = persistent_grid(total);
+  const int max_units = std::max(1, g_max_ctas.load(std::memory_order_relaxed) / CG);
+  const int grid = CG * (int)std::min<long long>(total, max_units);
   mmt::ProfScope prof(g.prof_family, gemm_flops(g), gemm_bytes(g), stream);
-  conv_tc_kernel<BN><<<grid, kFpropThreads, C::kSmemBytes, stream>>>(tmA, tmB, tmY, p);
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[2];
+  fill_launch(cfg, attr, grid, kFpropThreads, C::kSmemBytes, stream, CG);
+  MMT_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, CG>, tmA, tmB, tmY, p));
   return mmt::check_launch("conv_tc_kernel");
 }
 
-// Column-tile width.  Every BN handles every n_out (weights beyond n_out are zero-filled by TMA, stores are clipped),
-// so the choice is purely a cost question: per tile the K loop streams (128 + BN) * 128 B per 32-channel block from L2
-// (~85 GB/s per SM measured) and the epilogue moves 128 * BN * 4 B (x2 with a residual) at the SM's share of HBM
-// (~44 GB/s); the kernel takes ceil(tiles / CTAs) rounds of that.  Narrow tiles lose on operand re-reads, wide tiles
-// on wave quantisation when there are few pixel tiles.
-int pick_bn(const GemmProblem& g) {
-  // Measured (profiles/r01_conv_layers_v3.log): with >= one full round of 128 x 256 tiles the widest tile wins
-  // (fewest re-reads of the A operand through the ~85 GB/s-per-SM L2 path); with fewer tiles than half the SMs a
-  // narrower tile doubles the CTAs — and with them the bytes in flight chip-wide — for the same total traffic.
+// Tile configuration: column-tile width BN and CTAs per MMA (1, or 2 = cta_group::2 pair on a 256 x BN tile).  Every BN
+// handles every n_out (weights beyond n_out are zero-filled by TMA, stores are clipped), so the choice is a cost question.
+// Per 32-channel K block a CTA streams (128 + BN / CG) rows of 128 B from L2 into shared memory — measured ~56 B/clk
+// per SM sustained with every SM pulling (profiles/r01_conv_layers_v3.log) — and the tensor core needs 2 * BN cycles
+// for the four K = 8 MMAs; a launch takes ceil(units / resident units) rounds of kblocks * max(those two).  Narrow tiles
+// lose on operand re-reads, wide / paired tiles on wave quantisation when there are few pixel tiles.
+struct TileCfg { int bn, cg; };
+std::atomic<int> g_force_cg{0};   // 0 = cost model, 1 / 2 = force (tests, per-layer benchmarks)
+
+TileCfg pick_cfg(const GemmProblem& g) {
   int TW, TH;
   pick_patch(g.y.w, g.y.h, kTileM, TW, TH);
   const long long m_tiles = mmt::ceil_div<long long>(g.y.w, TW) * mmt::ceil_div<long long>(g.y.h, TH) * g.y.n;
   const int ctas = g_max_ctas.load(std::memory_order_relaxed);
-  int bn = 256;
-  while (bn > 32 && bn / 2 >= g.n_out) bn /= 2;                                      // no tile that is mostly padding
-  while (bn > 64 && m_tiles * ((g.n_out + bn - 1) / bn) * 2 <= ctas) bn /= 2;       // fill the machine
-  return bn;
+  const int force = g_force_cg.load(std::memory_order_relaxed);
+  TileCfg best{64, 1};
+  double best_cost = -1.0;
+  for (int cg = 1; cg <= 2; ++cg) {
+    if (force && cg != force) continue;
+    for (int bn = 256; bn >= 32; bn >>= 1) {
+      if (bn > 32 && bn / 2 >= g.n_out) continue;          // no tile that is mostly padding
+      if (bn == 32 && g.n_out > 32) continue;              // N = 32 MMAs only for the narrow heads
+      if (cg == 2 && (bn < 128 || ctas < 2)) continue;     // pair kernels are instantiated for BN = 128 / 256
+      const long long units = mmt::ceil_div<long long>(m_tiles, cg) * ((g.n_out + bn - 1) / bn);
+      const long long resident = std::max(1, ctas / cg);
+      const double rounds = (double)mmt::ceil_div<long long>(units, resident);
+      const double load_clk = (128.0 + bn / cg) * 128.0 / 56.0, mma_clk = 2.0 * bn;
+      // + a per-round fixed cost (pipeline fill, epilogue of the last tile): ~4 K-blocks' worth
+      const double cost = rounds * std::max(load_clk, mma_clk) * (1.0 + 4.0 / (g.kh * g.kw * (g.a.c / 32.0)));
+      if (best_cost < 0 || cost < best_cost * 0.999) { best_cost = cost; best = TileCfg{bn, cg}; }
+    }
+  }
+  if (force == 2 && best_cost < 0) best = TileCfg{g.n_out > 128 ? 256 : 128, 2};
+  return best;
 }
 
 int dispatch_gemm(const GemmProblem& g, cudaStream_t stream) {
-  switch (pick_bn(g)) {
-    case 256: return launch_gemm<256>(g, stream);
-    case 128: return launch_gemm<128>(g, stream);
-    case 64: return launch_gemm<64>(g, stream);
-    default: return launch_gemm<32>(g, stream);
+  const TileCfg c = pick_cfg(g);
+  if (c.cg == 2) return c.bn == 256 ? launch_gemm<256, 2>(g, stream) : launch_gemm<128, 2>(g, stream);
+  switch (c.bn) {
+    case 256: return launch_gemm<256, 1>(g, stream);
+    case 128: return launch_gemm<128, 1>(g, stream);
+    case 64: return launch_gemm<64, 1>(g, stream);
+    default: return launch_gemm<32, 1>(g, stream);
   }
 }
 
@@ -771,11 +890,25 @@ int launch_wgrad(const CUtensorMap& tmDY, const CUtensorMap& tmX, const CUtensor
     attr_set = true;
   }
   const int grid = persistent_grid(p.total_items);
-  wgrad_tc_kernel<BN><<<grid, kThreads, C::kSmemBytes, stream>>>(tmDY, tmX, tmDW, p);
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[2];
+  fill_launch(cfg, attr, grid, kThreads, C::kSmemBytes, stream, 1);
+  MMT_CUDA(cudaLaunchKernelEx(&cfg, wgrad_tc_kernel<BN>, tmDY, tmX, tmDW, p));
   return mmt::check_launch("wgrad_tc_kernel");
 }
 
 }  // namespace
+
+extern "C" int mmt_conv_set_pdl(int on) {
+  g_pdl.store(on ? 1 : 0);
+  return MMT_OK;
+}
+
+extern "C" int mmt_conv_force_cta_group(int cg) {
+  if (cg < 0 || cg > 2) return mmt::fail(MMT_ERR_INVALID_ARGUMENT, "conv_force_cta_group: %d not in {0, 1, 2}", cg);
+  g_force_cg.store(cg);
+  return MMT_OK;
+}
 
 extern "C" int mmt_conv_set_max_ctas(int n) {
   if (n < 1 || n > mmt::kNumSMs) return mmt::fail(MMT_ERR_INVALID_ARGUMENT, "conv_set_max_ctas: %d not in [1, %d]", n, mmt::kNumSMs);
@@ -868,7 +1001,8 @@ int conv_stem_tc(const float* x, const float* w, const float* scale, const float
   return dispatch_gemm(g, stream);
 }
 
-int conv_dgrad_tc(const float* dy, const float* w_t, float* dx, const mmt_conv_shape& s, cudaStream_t stream) {
+int conv_dgrad_tc(const float* dy, const float* w_t, float* dx, const mmt_conv_shape& s, cudaStream_t stream,
+                  const float* aux, int aux_mode) {
   GemmProblem g;
   const bool pointwise = s.k_h == 1 && s.k_w == 1 && s.pad == 0;
   if (pointwise && s.stride == 1) {
@@ -885,23 +1019,26 @@ int conv_dgrad_tc(const float* dy, const float* w_t, float* dx, const mmt_conv_s
     g.a = dense_nhwc(dy, s.batch, s.out_h, s.out_w, s.out_c);
     g.y = dense_nhwc(dx, s.batch, s.in_h, s.in_w, s.in_c);
   }
-  g.r_sw = g.r_sh = g.r_sn = 0;
+  // the epilogue's auxiliary tensor (dense, shaped like dx) is addressed through the same strides as the output view
+  g.r_sw = g.y.sw; g.r_sh = g.y.sh; g.r_sn = g.y.sn;
   g.b = w_t; g.n_out = s.in_c;
   g.kh = s.k_h; g.kw = s.k_w; g.pad_h = s.k_h - 1 - s.pad; g.pad_w = s.k_w - 1 - s.pad;
-  g.scale = nullptr; g.bias = nullptr; g.residual = nullptr; g.relu = 0;
+  g.scale = nullptr; g.bias = nullptr; g.relu = 0;
+  g.residual = aux_mode ? aux : nullptr;
+  g.res_mode = aux_mode == MMT_DGRAD_AUX_MASK ? 1 : 0;
   g.prof_family = MMT_PROF_CONV_DGRAD;
   return dispatch_gemm(g, stream);
 }
 
-int conv_filter_for_dgrad(const float* w, float* w_t, const mmt_conv_shape& s, cudaStream_t stream) {
+int conv_filter_for_dgrad(const float* w, float* w_t, const mmt_conv_shape& s, cudaStream_t stream, const float* k_scale) {
   const int taps = s.k_h * s.k_w;
   dim3 grid((unsigned)ceil_div(s.in_c, 32), (unsigned)ceil_div(s.out_c, 32), (unsigned)taps);
-  filter_dgrad_kernel<<<grid, 256, 0, stream>>>(w, w_t, s.out_c, taps, s.in_c);
+  filter_dgrad_kernel<<<grid, 256, 0, stream>>>(w, w_t, s.out_c, taps, s.in_c, k_scale);
   return check_launch("filter_dgrad");
 }
 
 int conv_wgrad_tc(const float* x, const float* dy, float* dw, float* dbias, const mmt_conv_shape& s,
-                  void* workspace, size_t workspace_bytes, cudaStream_t stream, bool accumulate) {
+                  void* workspace, size_t workspace_bytes, cudaStream_t stream, bool accumulate, const float* row_scale) {
   (void)workspace; (void)workspace_bytes; (void)dbias;
   const bool pointwise = s.k_h == 1 && s.k_w == 1 && s.pad == 0;
   View4 vdy, vx;
@@ -937,6 +1074,8 @@ int conv_wgrad_tc(const float* x, const float* dy, float* dw, float* dbias, cons
   p.co_tiles = (s.out_c + 127) / 128;
   p.ci_tiles = (s.in_c + BN - 1) / BN;
   p.cin = s.in_c;
+  p.cout = s.out_c;
+  p.row_scale = row_scale;
   const long long ptiles = (long long)p.tiles_w * p.tiles_h * p.tiles_b;
   if (ptiles > 0x7fffffffll) return fail(MMT_ERR_UNSUPPORTED, "wgrad: too many pixel tiles");
   p.pixel_tiles = (int)ptiles;

@@ -80,6 +80,15 @@ class MTtrainer(object):
         # land at random inside iterations that are ~30 ms long: pace it instead — automatic collection off, a young-
         # generation collection every `gc_every` iterations (0 = leave the interpreter's GC alone)
         self.gc_every, self._gc_steps = 50, 0
+        # Data-dependent ROI counts keep producing block sizes the caching allocator has not seen: each miss is a
+        # cudaMalloc, which blocks the host for 15-100 ms while the device is busy (profiles/r02_stall_trace.md: every
+        # isolated 40-235 ms step of round 1 coincides with one).  Expandable segments grow by mapping 2 MB pages
+        # (cuMemMap) instead — same trace, no stall.
+        if self.device.type == "cuda":
+            try:
+                torch.cuda.memory._set_allocator_settings("expandable_segments:True")
+            except Exception as e:   # older torch: keep going, only the stalls stay
+                self.logger.warning("could not switch the CUDA caching allocator to expandable segments: %s", e)
         self.loss_keys = ["loss_classifier", "loss_box_reg", "loss_seg", "loss_objectness", "loss_rpn_box_reg"]
         if cfg.MODEL.RELATION_NMS.USE_RELATION_NMS:
             self.loss_keys.append("nms_loss")
@@ -147,6 +156,12 @@ class MTtrainer(object):
             if self._gc_steps == 0:
                 gc.collect()
                 gc.disable()
+            elif self._gc_steps == 4:
+                # everything alive now (models, captured graphs, cached anchors, the config tree) lives as long as the
+                # trainer: park it in the permanent generation so that the paced collections below only walk the objects
+                # of the last iterations (17-20 ms -> well under a millisecond per collection)
+                gc.collect()
+                gc.freeze()
             elif self._gc_steps % self.gc_every == 0:
                 gc.collect(1)
             self._gc_steps += 1

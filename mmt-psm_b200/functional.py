@@ -66,6 +66,78 @@ def conv_bn_act(x, w, scale=None, bias=None, residual=None, relu=False, stride=1
     return _ConvBnAct.apply(x, w, scale, bias, residual, relu, stride, pad)
 
 
+class _Bottleneck(torch.autograd.Function):
+    """One ResNet bottleneck (reference modeling/backbone/resnet.py:254-275: conv1-bn1-relu, conv2-bn2-relu, conv3-bn3,
+    + identity / downsample-bn, relu) as ONE autograd node.
+
+    Forward: the same 3 (4) fused conv launches as the layer-by-layer path.  Backward: what autograd would spread over
+    ~5 elementwise passes per block (ReLU masks, frozen-BN scales, the skip-connection add) is folded into the conv
+    kernels — BN scale into the transformed dgrad filter and the wgrad epilogue, the ReLU mask of each inner activation
+    into the epilogue of the dgrad that produces its gradient, the skip add into conv1's dgrad epilogue
+    (mmt_conv_dgrad_fused_f32 / mmt_conv_wgrad_scaled_f32); one elementwise pass (the block output's ReLU mask) remains."""
+
+    @staticmethod
+    def forward(ctx, x, w1, w2, w3, wd, s1, b1, s2, b2, s3, b3, sd, bd, stride):
+        B, H, W, Cin = x.shape
+        Cmid, Cout = w1.shape[0], w3.shape[0]
+        sh1 = K.conv_shape(B, H, W, Cin, Cmid, 1, stride, 0)
+        o1 = K.conv_fprop(x, w1, sh1, s1, b1, None, True)
+        sh2 = K.conv_shape(B, sh1.out_h, sh1.out_w, Cmid, Cmid, 3, 1, 1)
+        o2 = K.conv_fprop(o1, w2, sh2, s2, b2, None, True)
+        shd = None
+        if wd is not None:
+            shd = K.conv_shape(B, H, W, Cin, Cout, 1, stride, 0)
+            idt = K.conv_fprop(x, wd, shd, sd, bd, None, False)
+        else:
+            idt = x
+        sh3 = K.conv_shape(B, sh2.out_h, sh2.out_w, Cmid, Cout, 1, 1, 0)
+        y = K.conv_fprop(o2, w3, sh3, s3, b3, idt, True)
+        ctx.shapes = (sh1, sh2, sh3, shd)
+        ctx.save_for_backward(x, o1, o2, y, w1, w2, w3, wd, s1, s2, s3, sd)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, o1, o2, y, w1, w2, w3, wd, s1, s2, s3, sd = ctx.saved_tensors
+        sh1, sh2, sh3, shd = ctx.shapes
+        need = ctx.needs_input_grad
+        g3 = K.bn_relu_backward(gy.contiguous(), y, None, True)          # gradient of (bn3 output + identity)
+        grads = {}
+
+        def wgrad(idx, xin, g, shape, w, scale):
+            if not need[idx]:
+                return
+            if _fused_grad_sink is not None and w.is_leaf and w.grad is not None and w.grad.is_contiguous():
+                K.conv_wgrad_scaled(xin, g, shape, scale, into=w.grad)   # straight into the optimizer's gradient arena
+                _fused_grad_sink([w])
+            else:
+                grads[idx] = K.conv_wgrad_scaled(xin, g, shape, scale)
+
+        d_o2 = K.conv_dgrad_fused(g3, w3, sh3, s3, o2, K.DGRAD_AUX_MASK)  # through conv3, bn3 and relu(bn2)
+        wgrad(3, o2, g3, sh3, w3, s3)
+        d_o1 = K.conv_dgrad_fused(d_o2, w2, sh2, s2, o1, K.DGRAD_AUX_MASK)
+        wgrad(2, o1, d_o2, sh2, w2, s2)
+        wgrad(1, x, d_o1, sh1, w1, s1)
+        dx = None
+        if wd is not None:
+            wgrad(4, x, g3, shd, wd, sd)
+        if need[0]:
+            if wd is None:
+                dx = K.conv_dgrad_fused(d_o1, w1, sh1, s1, g3, K.DGRAD_AUX_ADD)   # + the identity branch's gradient
+            else:
+                dxd = K.conv_dgrad_fused(g3, wd, shd, sd)
+                if sh1.stride == 1:
+                    dx = K.conv_dgrad_fused(d_o1, w1, sh1, s1, dxd, K.DGRAD_AUX_ADD)
+                else:
+                    dx = K.conv_dgrad_fused(d_o1, w1, sh1, s1)
+                    dx += dxd
+        return (dx, grads.get(1), grads.get(2), grads.get(3), grads.get(4)) + (None,) * 9
+
+
+def bottleneck(x, w1, w2, w3, wd, s1, b1, s2, b2, s3, b3, sd, bd, stride):
+    return _Bottleneck.apply(x, w1, w2, w3, wd, s1, b1, s2, b2, s3, b3, sd, bd, stride)
+
+
 def linear(x, w, bias=None, relu=False):
     """x [N,K] @ w[O,K]^T (+bias)(+relu) on the conv engine: a 1x1 convolution over N 'pixels'.
     Replaces nn.Linear of the box head (reference roi_box_feature_extractors.py:97-98,119-121;

@@ -583,6 +583,11 @@ def conv_shape(batch, in_h, in_w, in_c, out_c, k, stride, pad):
     return ConvShape(batch, in_h, in_w, in_c, out_c, k, k, stride, pad, oh, ow)
 
 
+def conv_force_cta_group(cta_group):
+    """0 = per-problem cost model (default); 1 = one CTA per 128 x BN tile; 2 = CTA pairs (tcgen05 cta_group::2)."""
+    check(_l.lib().mmt_conv_force_cta_group(int(cta_group)), "conv_force_cta_group")
+
+
 def conv_fprop(x, w, shape, scale=None, bias=None, residual=None, relu=False, impl=None, out=None):
     """x NHWC [B,H,W,Ci] dense, w OHWI [Co,kh,kw,Ci] dense -> y NHWC [B,OH,OW,Co]."""
     _need_cuda(x, w, scale, bias, residual)
@@ -656,6 +661,56 @@ def conv_wgrad_accumulate_(x, dy, shape, dw):
         return False
     check(rc, "conv_wgrad_accumulate")
     return True
+
+
+DGRAD_AUX_NONE, DGRAD_AUX_ADD, DGRAD_AUX_MASK = 0, 1, 2
+
+
+def conv_dgrad_fused(dy, w, shape, k_scale=None, aux=None, aux_mode=DGRAD_AUX_NONE):
+    """dx = E(conv_T(dy * k_scale[out_c], w)) with E = identity | + aux | masked by (aux > 0): the data gradient of a
+    Conv -> FrozenBN chain given the gradient of the BN output, with the skip-connection add or the previous layer's ReLU
+    backward in the epilogue (mmt_conv_dgrad_fused_f32).  In fp32 conv math (parity mode) or for shapes outside the tcgen05
+    kernel the same result is composed from the unfused pieces."""
+    _need_cuda(dy, w, k_scale, aux)
+    L = _l.lib()
+    assert dy.is_contiguous() and w.is_contiguous() and (aux is None or aux.is_contiguous())
+    if _conv_impl == CONV_AUTO:
+        dx = torch.empty((shape.batch, shape.in_h, shape.in_w, shape.in_c), dtype=torch.float32, device=dy.device)
+        wsb = L.mmt_conv_workspace_bytes(ctypes.byref(shape))
+        ws = torch.empty(wsb, dtype=torch.uint8, device=dy.device)
+        rc = L.mmt_conv_dgrad_fused_f32(_p(dy), _p(w), _p(k_scale), _p(aux), int(aux_mode), _p(dx), ctypes.byref(shape),
+                                        _p(ws), wsb, _stream())
+        if rc != 4:  # MMT_ERR_UNSUPPORTED -> composition below
+            check(rc, "conv_dgrad_fused")
+            return dx
+    g = dy if k_scale is None else dy * k_scale
+    dx = conv_dgrad(g, w, shape)
+    if aux_mode == DGRAD_AUX_ADD:
+        dx += aux
+    elif aux_mode == DGRAD_AUX_MASK:
+        dx = dx * (aux > 0)
+    return dx
+
+
+def conv_wgrad_scaled(x, dy, shape, row_scale=None, into=None):
+    """row_scale[o] * wgrad(x, dy)[o]: accumulated into `into` (a live gradient buffer; returns None) or returned."""
+    _need_cuda(x, dy, row_scale, into)
+    L = _l.lib()
+    assert x.is_contiguous() and dy.is_contiguous()
+    if _conv_impl == CONV_AUTO and (into is None or (into.is_contiguous() and into.dtype == torch.float32)):
+        dw = into if into is not None else torch.empty((shape.out_c, shape.k_h, shape.k_w, shape.in_c),
+                                                       dtype=torch.float32, device=x.device)
+        rc = L.mmt_conv_wgrad_scaled_f32(_p(x), _p(dy), _p(row_scale), _p(dw), ctypes.byref(shape),
+                                         1 if into is not None else 0, _stream())
+        if rc != 4:
+            check(rc, "conv_wgrad_scaled")
+            return None if into is not None else dw
+    g = dy if row_scale is None else dy * row_scale
+    dw, _ = conv_wgrad(x, g, shape)
+    if into is not None:
+        into += dw
+        return None
+    return dw
 
 
 def bn_relu_backward(grad_y, y, scale, relu):

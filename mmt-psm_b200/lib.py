@@ -82,6 +82,10 @@ _PROTOS = {
     "mmt_ema_f32": (c_int, [P, P, c_int64, c_float, P]),
     "mmt_sgd_ema_f32": (c_int, [P, P, P, P, c_int64, P, c_int, c_float, c_float, c_int, c_float, P]),
     "mmt_conv_set_max_ctas": (c_int, [c_int]),
+    "mmt_conv_force_cta_group": (c_int, [c_int]),
+    "mmt_conv_set_pdl": (c_int, [c_int]),
+    "mmt_conv_dgrad_fused_f32": (c_int, [P, P, P, P, c_int, P, POINTER(ConvShape), P, c_size_t, P]),
+    "mmt_conv_wgrad_scaled_f32": (c_int, [P, P, P, P, POINTER(ConvShape), c_int, P]),
     "mmt_conv_workspace_bytes": (c_size_t, [POINTER(ConvShape)]),
     "mmt_conv_fprop_f32": (c_int, [P, P, P, P, P, P, POINTER(ConvShape), c_int, c_int, P]),
     "mmt_conv_stem_workspace_bytes": (c_size_t, [POINTER(ConvShape)]),
@@ -120,6 +124,11 @@ def lib():
             fn.restype = res
             fn.argtypes = args
         _lib = handle
+        # experiment knobs of the conv engine (benchmarks / bisecting): MMT_CONV_PDL=0, MMT_CONV_CTA_GROUP=1|2
+        if os.environ.get("MMT_CONV_PDL") in ("0", "1"):
+            handle.mmt_conv_set_pdl(int(os.environ["MMT_CONV_PDL"]))
+        if os.environ.get("MMT_CONV_CTA_GROUP") in ("0", "1", "2"):
+            handle.mmt_conv_force_cta_group(int(os.environ["MMT_CONV_CTA_GROUP"]))
     return _lib
 
 

@@ -41,7 +41,19 @@ class BottleneckWithFixedBatchNorm(nn.Module):
         self.conv3 = Conv2d(bottleneck_channels, out_channels, 1, 1, 0, bias=False)
         self.bn3 = FrozenBatchNorm2d(out_channels)
 
+    fused_backward = True   # one autograd node per block with the elementwise backward folded into the conv kernels
+
     def forward(self, x):
+        if self.fused_backward and self.conv1.stride in (1, 2) and self.conv2.stride == 1:
+            s1, b1 = self.bn1.affine()
+            s2, b2 = self.bn2.affine()
+            s3, b3 = self.bn3.affine()
+            wd = sd = bd = None
+            if self.downsample is not None:
+                wd = self.downsample[0].weight
+                sd, bd = self.downsample[1].affine()
+            return Fk.bottleneck(x, self.conv1.weight, self.conv2.weight, self.conv3.weight, wd, s1, b1, s2, b2, s3, b3,
+                                 sd, bd, self.conv1.stride)
         identity = x if self.downsample is None else self.downsample[0](x, bn=self.downsample[1])
         out = self.conv1(x, bn=self.bn1, relu=True)
         out = self.conv2(out, bn=self.bn2, relu=True)

@@ -164,8 +164,11 @@ def test_step_full_size_matches_reference_golden(cuda, restore, math, tol):
 def test_step_tf32_matches_tf32_oracle(cuda, restore):
     """The SHIPPED conv math (tcgen05 kind::tf32) at step level against the oracle evaluated with the same operand
     precision (oracle/model_cpu.py Cfg.tf32_operands: operands cut to 10 mantissa bits, fp32 accumulate; pinned in
-    fp32 mode by step_small.npz).  Only accumulation order differs, so the bound is the fp32-mode one, not the 3e-2 a
-    TF32-vs-fp32 comparison needs."""
+    fp32 mode by step_small.npz).  Only accumulation order differs, so the deterministic terms (classifier, mask, RPN
+    losses) are held to 2e-4 — measured 3e-6 .. 8e-5 — instead of the 3e-2 a TF32-vs-fp32 comparison needs; the terms that
+    depend on WHICH ROIs the random sampler drew (loss_box_reg over the few positives of this small fixture, and both
+    consistency terms, computed on the teacher's sampled ROI set) move by 1e-3 .. 3e-3 when one near-tie candidate flips:
+    bound 5e-3."""
     from mmt_psm_b200 import kernels, lib
     from mmt_psm_b200.modeling.detector import reference_state_dict
     from oracle import model_cpu
@@ -187,7 +190,8 @@ def test_step_tf32_matches_tf32_oracle(cuda, restore):
     rows = [(k, got[k], ref[k]) for k in got]
     _drift_report("tf32_vs_tf32_oracle", rows)
     for k, v, r in rows:
-        assert abs(v - r) <= (1e-3 if k.startswith("mt_") else 2e-4) * max(abs(r), 1e-2), (k, v, r)
+        tol = 5e-3 if (k.startswith("mt_") or k == "sup_loss_box_reg") else 2e-4
+        assert abs(v - r) <= tol * abs(r), (k, v, r)
     assert lib.launch_count() > 150
 
 

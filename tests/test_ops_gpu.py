@@ -612,6 +612,127 @@ def test_conv_dgrad_wgrad(cuda, impl):
         assert _rel(db.cpu(), dy.sum((0, 2, 3))) < 1e-5
 
 
+PAIR_CASES = [
+    # B, H, W, Cin, Cout, k, stride, pad              pixel tiles (128 px)            column tiles
+    (1, 48, 40, 128, 256, 3, 1, 1),       # 15 (odd: the last pair computes its tile twice)     1 x 256
+    (1, 29, 30, 256, 384, 1, 1, 0),       # 7 flat-pixel tiles (odd)           2 x 256, the second half empty
+    (2, 50, 50, 256, 512, 1, 2, 0),       # strided 1x1, 10 tiles              2 x 256
+    (2, 25, 25, 128, 128, 3, 1, 1),       # BN = 128 pair (64 filter rows per CTA)
+    (4, 50, 50, 256, 256, 3, 1, 1),       # 112 tiles: more pairs than one round of 74 clusters -> persistent loop, both TMEM buffers
+    (1, 1, 1024, 12544, 1024, 1, 1, 0),   # FC6: 392 K blocks per tile
+]
+
+
+@pytest.mark.parametrize("cg", [1, 2])
+def test_conv_cta_pair_matches_reference(cuda, cg):
+    """The cta_group::2 kernel (256 x BN tile over a CTA pair, leader-issued MMA, multicast commits, peer-signalled TMA)
+    against the TF32-truncated fp64 reference and against the one-CTA kernel: fprop with the full epilogue (scale, shift,
+    residual, ReLU) and dgrad (same kernel, transposed filter)."""
+    import torch.nn.functional as Fn
+    kn = K()
+    gen = torch.Generator().manual_seed(34)
+    try:
+        for case in PAIR_CASES:
+            B, H, W, Ci, Co, k, s, p = case
+            x, w = _conv_inputs(case, gen, cuda)
+            scale = torch.rand(Co, generator=gen) + 0.5
+            bias = torch.randn(Co, generator=gen)
+            shape = kn.conv_shape(B, H, W, Ci, Co, k, s, p)
+            res = torch.randn(B, Co, shape.out_h, shape.out_w, generator=gen)
+            dy = torch.randn(B, Co, shape.out_h, shape.out_w, generator=gen)
+            xd = x.permute(0, 2, 3, 1).contiguous().to(cuda)
+            wd = w.permute(0, 2, 3, 1).contiguous().to(cuda)
+            rd = res.permute(0, 2, 3, 1).contiguous().to(cuda)
+            dyd = dy.permute(0, 2, 3, 1).contiguous().to(cuda)
+            kn.conv_force_cta_group(cg)
+            y = kn.conv_fprop(xd, wd, shape, scale.to(cuda), bias.to(cuda), rd, True, kn.CONV_TCGEN05)
+            dx = kn.conv_dgrad(dyd, wd, shape, kn.CONV_TCGEN05)
+            torch.cuda.synchronize()
+            kn.conv_force_cta_group(1)
+            y1 = kn.conv_fprop(xd, wd, shape, scale.to(cuda), bias.to(cuda), rd, True, kn.CONV_TCGEN05)
+            dx1 = kn.conv_dgrad(dyd, wd, shape, kn.CONV_TCGEN05)
+            # same operands, same K order inside a tile: the pair kernel reproduces the one-CTA kernel to accumulation noise
+            assert _rel(y, y1) < 2e-6, (case, "fprop pair vs single", _rel(y, y1))
+            assert _rel(dx, dx1) < 2e-6, (case, "dgrad pair vs single", _rel(dx, dx1))
+            trunc = R.conv_bn_act_ref(x, w, scale, bias, res, True, s, p, operands="tf32")
+            assert _rel(y.permute(0, 3, 1, 2).cpu(), trunc) < 1e-4, (case, _rel(y.permute(0, 3, 1, 2).cpu(), trunc))
+            if Ci * k * k <= 4096:
+                xr = x.double().requires_grad_(True)
+                Fn.conv2d(xr, w.double(), None, s, p).backward(dy.double())
+                assert _rel(dx.permute(0, 3, 1, 2).cpu(), xr.grad.float()) < 3e-3, case
+    finally:
+        kn.conv_force_cta_group(0)
+
+
+def test_conv_fused_backward_ops(cuda):
+    """mmt_conv_dgrad_fused_f32 / mmt_conv_wgrad_scaled_f32 (BN scale folded into the transformed filter / the wgrad
+    epilogue; skip-add or ReLU mask in the dgrad epilogue) against their definition composed from exact fp64 pieces."""
+    import torch.nn.functional as Fn
+    kn = K()
+    gen = torch.Generator().manual_seed(35)
+    cases = [(2, 25, 25, 128, 128, 3, 1, 1), (2, 50, 50, 256, 64, 1, 1, 0), (2, 50, 50, 256, 512, 1, 2, 0),
+             (1, 48, 40, 128, 256, 3, 1, 1), (4, 50, 50, 1024, 256, 1, 1, 0)]
+    for case in cases:
+        B, H, W, Ci, Co, k, s, p = case
+        x, w = _conv_inputs(case, gen, cuda)
+        shape = kn.conv_shape(B, H, W, Ci, Co, k, s, p)
+        dy = torch.randn(B, Co, shape.out_h, shape.out_w, generator=gen)
+        scale = torch.rand(Co, generator=gen) + 0.5
+        aux = torch.randn(B, Ci, H, W, generator=gen)
+        xr, wr = x.double().requires_grad_(True), w.double().requires_grad_(True)
+        Fn.conv2d(xr, wr, None, s, p).backward(dy.double() * scale.double().view(1, -1, 1, 1))
+        dx_ref, dw_ref = xr.grad.float(), wr.grad.float()
+        xd = x.permute(0, 2, 3, 1).contiguous().to(cuda)
+        wd = w.permute(0, 2, 3, 1).contiguous().to(cuda)
+        dyd = dy.permute(0, 2, 3, 1).contiguous().to(cuda)
+        auxd = aux.permute(0, 2, 3, 1).contiguous().to(cuda)
+        nchw = lambda t: t.permute(0, 3, 1, 2).cpu()
+        got = nchw(kn.conv_dgrad_fused(dyd, wd, shape, scale.to(cuda)))
+        assert _rel(got, dx_ref) < 3e-3, ("scaled dgrad", case, _rel(got, dx_ref))
+        if s == 1:
+            got = nchw(kn.conv_dgrad_fused(dyd, wd, shape, scale.to(cuda), auxd, kn.DGRAD_AUX_ADD))
+            assert _rel(got, dx_ref + aux) < 3e-3, ("dgrad + aux", case)
+            got = nchw(kn.conv_dgrad_fused(dyd, wd, shape, scale.to(cuda), auxd, kn.DGRAD_AUX_MASK))
+            ref = torch.where(aux > 0, dx_ref, torch.zeros_like(dx_ref))
+            assert _rel(got, ref) < 3e-3, ("masked dgrad", case)
+            assert bool((got[aux <= 0] == 0).all())            # the mask is exact, not approximately zero
+        dw = kn.conv_wgrad_scaled(xd, dyd, shape, scale.to(cuda)).permute(0, 3, 1, 2).cpu()
+        assert _rel(dw, dw_ref) < 3e-3, ("scaled wgrad", case, _rel(dw, dw_ref))
+        acc = torch.full((Co, k, k, Ci), 0.25, device=cuda)
+        assert kn.conv_wgrad_scaled(xd, dyd, shape, scale.to(cuda), into=acc) is None
+        assert _rel(acc.permute(0, 3, 1, 2).cpu() - 0.25, dw_ref) < 3e-3, ("accumulating scaled wgrad", case)
+
+
+@pytest.mark.parametrize("downsample,stride", [(False, 1), (True, 2)])
+def test_bottleneck_fused_backward_matches_layerwise(cuda, downsample, stride):
+    """One bottleneck, forward + backward: the block-level autograd node with the fused backward kernels against the
+    layer-by-layer autograd path (same forward kernels; backward differs in WHERE the BN scale meets TF32 rounding)."""
+    from mmt_psm_b200.modeling.backbone import BottleneckWithFixedBatchNorm
+    torch.manual_seed(3)
+    cin, mid, cout = (256, 128, 512) if downsample else (512, 128, 512)
+    blk = BottleneckWithFixedBatchNorm(cin, mid, cout, 1, True, stride).to(cuda)
+    for m in blk.modules():
+        if hasattr(m, "running_var"):
+            m.weight.uniform_(0.5, 1.5); m.bias.normal_(0, 0.1); m.running_mean.normal_(0, 0.1); m.running_var.uniform_(0.5, 1.5)
+    x0 = torch.randn(4, 50, 50, cin, device=cuda).relu()
+    gy = torch.randn(4, 50 // stride, 50 // stride, cout, device=cuda)
+    outs = []
+    for fused in (True, False):
+        blk.fused_backward = fused
+        for p_ in blk.parameters():
+            p_.grad = None
+        x = x0.clone().requires_grad_(True)
+        y = blk(x)
+        y.backward(gy)
+        outs.append((y.detach(), x.grad, {n: p_.grad.clone() for n, p_ in blk.named_parameters()}))
+    blk.fused_backward = True
+    (y0, dx0, g0), (y1, dx1, g1) = outs
+    assert torch.equal(y0, y1)
+    assert _rel(dx0, dx1) < 3e-3, _rel(dx0, dx1)
+    for n in g0:
+        assert _rel(g0[n], g1[n]) < 3e-3, (n, _rel(g0[n], g1[n]))
+
+
 def test_conv_padded_heads_tc(cuda):
     """16-channel (15 padded) heads: fprop + wgrad on the tcgen05 kernels (BN = 32 tile, TMA clips the stores); dgrad of
     these shapes (GEMM K = 16) is routed to the FFMA kernel by CONV_AUTO and must agree as well."""

@@ -99,7 +99,13 @@ class ClockSampler(object):
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def window(self, t0, t1):
+        """Keep only the samples taken inside [t0, t1] (perf_counter): the sampler is started BEFORE the warm-up —
+        spawning nvidia-smi right before the timed region stalls this process's first CUDA calls for 20-250 ms
+        (NVML initialisation holds a driver lock; profiles/r02_stall_trace.md) — and read over the timed window."""
+        self.t0, self.t1 = t0, t1
 
     def stop(self):
         if self.proc is None:
@@ -111,7 +117,10 @@ class ClockSampler(object):
             self.proc.kill()
         sm, mx, reasons, power = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        t0, t1 = getattr(self, "t0", None), getattr(self, "t1", None)
+        for ts, r in self.rows:
+            if t0 is not None and not (t0 <= ts <= t1 + 0.25):
+                continue
             if len(r) < 7:
                 continue
             try:
@@ -201,6 +210,8 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    # started here, seconds before the timed region (model build + graph capture come first): see ClockSampler.window
+    sampler = ClockSampler(local) if (rank == 0 and os.environ.get("MMT_NO_CLOCKS") != "1") else None
     if world != args.gpus and rank == 0:
         print("warning: --gpus %d but WORLD_SIZE %d; reporting n_gpus = WORLD_SIZE" % (args.gpus, world), file=sys.stderr)
 
@@ -325,12 +336,14 @@ def run_ours(args):
             step(j, True)                     # the e2e path's own first-use costs (pinned staging, target packing) too
     barrier()
     a_before = alloc_counters()
-    sampler = ClockSampler(local) if (rank == 0 and os.environ.get("MMT_NO_CLOCKS") != "1") else None
     lib.reset_launch_count()
+    t_window = time.perf_counter()
     ms_dev, last = timed(args.steps, False)
     launches = lib.launch_count()
     final_loss = float(last)
     ms_e2e, last_e2e = timed(args.steps, True)
+    if sampler:
+        sampler.window(t_window, time.perf_counter())
     clocks = sampler.stop() if sampler else None
     a_after = alloc_counters()
     # data-parallel replicas must be bit-identical: students see the same all-reduced gradient and the same update mask,

@@ -828,12 +828,19 @@ int launch_gemm(const GemmProblem& g, cudaStream_t stream) {
 
 // Tile configuration: column-tile width BN and CTAs per MMA (1, or 2 = cta_group::2 pair on a 256 x BN tile).  Every BN
 // handles every n_out (weights beyond n_out are zero-filled by TMA, stores are clipped), so the choice is a cost question.
-// Per 32-channel K block a CTA streams (128 + BN / CG) rows of 128 B from L2 into shared memory — measured ~56 B/clk
-// per SM sustained with every SM pulling (profiles/r01_conv_layers_v3.log) — and the tensor core needs 2 * BN cycles
-// for the four K = 8 MMAs; a launch takes ceil(units / resident units) rounds of kblocks * max(those two).  Narrow tiles
-// lose on operand re-reads, wide / paired tiles on wave quantisation when there are few pixel tiles.
+//
+// One CTA per tile: per 32-channel K block a CTA streams (128 + BN) rows of 128 B from L2 into shared memory (~56 B/clk
+// per SM sustained with every SM pulling) and the tensor core needs 2 * BN cycles for the four K = 8 MMAs; a launch takes
+// ceil(tiles / CTAs) rounds of kblocks * max(those two).  Narrow tiles lose on operand re-reads, wide tiles on wave
+// quantisation when there are few pixel tiles.
+//
+// CTA pairs: measured per layer (profiles/r02_conv_tile_cfg.log, every trunk conv at the batches the trainer runs): the
+// pair wins 3-10 % where the main loop is long and the machine is full — K = k*k*C_in >= 512, >= 256 output channels,
+// >= 48 pair tiles: the 3x3 256 -> 256 convs of FPN / RPN / layer3 / mask head, the 512 -> 1024 and 1024 -> 2048
+// projections, layer4 at the teacher's batch — and LOSES 5-20 % on the short-K 1x1 convs (K <= 256), whose time is the
+// epilogue's HBM traffic: a pair's two epilogues start and end together, a lone CTA's overlap other CTAs' main loops.
 struct TileCfg { int bn, cg; };
-std::atomic<int> g_force_cg{0};   // 0 = cost model, 1 / 2 = force (tests, per-layer benchmarks)
+std::atomic<int> g_force_cg{0};   // 0 = rule above, 1 / 2 = force (tests, per-layer benchmarks)
 
 TileCfg pick_cfg(const GemmProblem& g) {
   int TW, TH;
@@ -841,24 +848,23 @@ TileCfg pick_cfg(const GemmProblem& g) {
   const long long m_tiles = mmt::ceil_div<long long>(g.y.w, TW) * mmt::ceil_div<long long>(g.y.h, TH) * g.y.n;
   const int ctas = g_max_ctas.load(std::memory_order_relaxed);
   const int force = g_force_cg.load(std::memory_order_relaxed);
+  const long long k_total = (long long)g.kh * g.kw * g.a.c;
+  if (force == 2) return TileCfg{g.n_out > 128 ? 256 : 128, 2};
+  if (force == 0 && ctas >= 2 && k_total >= 512 && g.n_out >= 256 &&
+      mmt::ceil_div<long long>(m_tiles, 2) * ((g.n_out + 255) / 256) >= 48)
+    return TileCfg{256, 2};
   TileCfg best{64, 1};
   double best_cost = -1.0;
-  for (int cg = 1; cg <= 2; ++cg) {
-    if (force && cg != force) continue;
-    for (int bn = 256; bn >= 32; bn >>= 1) {
-      if (bn > 32 && bn / 2 >= g.n_out) continue;          // no tile that is mostly padding
-      if (bn == 32 && g.n_out > 32) continue;              // N = 32 MMAs only for the narrow heads
-      if (cg == 2 && (bn < 128 || ctas < 2)) continue;     // pair kernels are instantiated for BN = 128 / 256
-      const long long units = mmt::ceil_div<long long>(m_tiles, cg) * ((g.n_out + bn - 1) / bn);
-      const long long resident = std::max(1, ctas / cg);
-      const double rounds = (double)mmt::ceil_div<long long>(units, resident);
-      const double load_clk = (128.0 + bn / cg) * 128.0 / 56.0, mma_clk = 2.0 * bn;
-      // + a per-round fixed cost (pipeline fill, epilogue of the last tile): ~4 K-blocks' worth
-      const double cost = rounds * std::max(load_clk, mma_clk) * (1.0 + 4.0 / (g.kh * g.kw * (g.a.c / 32.0)));
-      if (best_cost < 0 || cost < best_cost * 0.999) { best_cost = cost; best = TileCfg{bn, cg}; }
-    }
+  for (int bn = 256; bn >= 32; bn >>= 1) {
+    if (bn > 32 && bn / 2 >= g.n_out) continue;          // no tile that is mostly padding
+    if (bn == 32 && g.n_out > 32) continue;              // N = 32 MMAs only for the narrow heads
+    const long long units = m_tiles * ((g.n_out + bn - 1) / bn);
+    const double rounds = (double)mmt::ceil_div<long long>(units, std::max(1, ctas));
+    const double load_clk = (128.0 + bn) * 128.0 / 56.0, mma_clk = 2.0 * bn;
+    // + a per-round fixed cost (pipeline fill, epilogue of the last tile): ~4 K-blocks' worth
+    const double cost = rounds * std::max(load_clk, mma_clk) * (1.0 + 4.0 / (double)(k_total / 32));
+    if (best_cost < 0 || cost < best_cost * 0.999) { best_cost = cost; best = TileCfg{bn, 1}; }
   }
-  if (force == 2 && best_cost < 0) best = TileCfg{g.n_out > 128 ? 256 : 128, 2};
   return best;
 }
 

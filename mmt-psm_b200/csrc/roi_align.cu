@@ -319,6 +319,119 @@ __global__ void __launch_bounds__(256) roi_align_fpn_bwd_kernel(
   }
 }
 
+
+// ---- v2: one CTA per ROI, bilinear tap table in shared memory ---------------------------------------------------------
+// The kernels above recompute the ROI geometry and the 4 bilinear taps of every sample in EVERY thread (64 threads per
+// bin at 256 channels: ~13 IEEE divisions each) and hand consecutive bins of a ROI to different CTAs, so neighbouring
+// bins — whose taps overlap — never share an L1.  Here a CTA owns a whole ROI: its threads first compute each sample's
+// taps ONCE (one sample per thread) into shared memory, then sweep the ROI's bins in raster order, a warp covering 32
+// consecutive channel-quads of one bin per step (512-byte coalesced tap reads, table entries broadcast from shared
+// memory), so a tap row fetched for one bin is still in this SM's L1 for the next bin and the next row.  Same
+// arithmetic, same order of additions: the forward result stays bit-identical to the reference.
+struct TapEntry {
+  int o1, o2, o3, o4;      // pixel offsets (in pixels: y * width + x) of the four taps; o1 < 0 = sample outside the map
+  float w1, w2, w3, w4;
+};
+constexpr int kMaxSamplesV2 = 1024;   // pooled_h * pooled_w * sampling_ratio^2 (14 x 14 x 4 = 784; 7 x 7 x 4 = 196)
+
+__device__ __forceinline__ void build_tap_table(TapEntry* tab, const RoiGeom& g, int pooled_h, int pooled_w, int height,
+                                                int width) {
+  const int per_bin = g.grid_h * g.grid_w;
+  const int n_samples = pooled_h * pooled_w * per_bin;
+  for (int s = threadIdx.x; s < n_samples; s += blockDim.x) {
+    const int bin = s / per_bin, k = s % per_bin;
+    const int ph = bin / pooled_w, pw = bin % pooled_w;
+    const int iy = k / g.grid_w, ix = k % g.grid_w;
+    const float y = sample_coord(g.start_h, ph, g.bin_h, iy, g.grid_h);
+    const float x = sample_coord(g.start_w, pw, g.bin_w, ix, g.grid_w);
+    const Taps t = bilinear_taps(y, x, height, width);
+    TapEntry e;
+    e.o1 = t.valid ? t.y_low * width + t.x_low : -1;
+    e.o2 = t.y_low * width + t.x_high;
+    e.o3 = t.y_high * width + t.x_low;
+    e.o4 = t.y_high * width + t.x_high;
+    e.w1 = t.w1; e.w2 = t.w2; e.w3 = t.w3; e.w4 = t.w4;
+    tab[s] = e;
+  }
+}
+
+__global__ void __launch_bounds__(256) roi_align_fpn_fwd2_kernel(
+    LevelTab tab, int channels, const float* __restrict__ rois, const int* __restrict__ levels, int pooled_h,
+    int pooled_w, int sampling_ratio, float* __restrict__ out) {
+  __shared__ TapEntry taps[kMaxSamplesV2];
+  const int n = blockIdx.x;
+  const int l = levels[n];
+  const int height = tab.h[l], width = tab.w[l];
+  const RoiGeom g = roi_geometry(rois + (long long)n * 5, tab.scale[l], pooled_h, pooled_w, sampling_ratio);
+  build_tap_table(taps, g, pooled_h, pooled_w, height, width);
+  __syncthreads();
+  const int cvecs = channels >> 2;
+  const int per_bin = g.grid_h * g.grid_w;
+  const float4* base = reinterpret_cast<const float4*>(tab.feat[l] + (long long)g.batch_ind * height * width * channels);
+  float4* o = reinterpret_cast<float4*>(out) + (long long)n * pooled_h * pooled_w * cvecs;
+  const int total = pooled_h * pooled_w * cvecs;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const int cv = i % cvecs, bin = i / cvecs;
+    const TapEntry* e = taps + bin * per_bin;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    for (int k = 0; k < per_bin; ++k) {   // iy outer, ix inner: the reference's accumulation order
+      const TapEntry t = e[k];
+      if (t.o1 < 0) continue;  // contributes +0
+      const float4 a = __ldg(base + (long long)t.o1 * cvecs + cv);
+      const float4 b = __ldg(base + (long long)t.o2 * cvecs + cv);
+      const float4 c = __ldg(base + (long long)t.o3 * cvecs + cv);
+      const float4 d = __ldg(base + (long long)t.o4 * cvecs + cv);
+      Taps w;
+      w.w1 = t.w1; w.w2 = t.w2; w.w3 = t.w3; w.w4 = t.w4;
+      a0 = __fadd_rn(a0, blend(w, a.x, b.x, c.x, d.x));
+      a1 = __fadd_rn(a1, blend(w, a.y, b.y, c.y, d.y));
+      a2 = __fadd_rn(a2, blend(w, a.z, b.z, c.z, d.z));
+      a3 = __fadd_rn(a3, blend(w, a.w, b.w, c.w, d.w));
+    }
+    float4 r;
+    r.x = __fdiv_rn(a0, g.count); r.y = __fdiv_rn(a1, g.count);
+    r.z = __fdiv_rn(a2, g.count); r.w = __fdiv_rn(a3, g.count);
+    o[i] = r;   // i enumerates [ph][pw][cvec] == NHWC order inside the ROI
+  }
+}
+
+__global__ void __launch_bounds__(256) roi_align_fpn_bwd2_kernel(
+    LevelTab tab, int channels, const float* __restrict__ gout, const float* __restrict__ rois,
+    const int* __restrict__ levels, int pooled_h, int pooled_w, int sampling_ratio) {
+  __shared__ TapEntry taps[kMaxSamplesV2];
+  const int n = blockIdx.x;
+  const int l = levels[n];
+  const int height = tab.h[l], width = tab.w[l];
+  const RoiGeom g = roi_geometry(rois + (long long)n * 5, tab.scale[l], pooled_h, pooled_w, sampling_ratio);
+  build_tap_table(taps, g, pooled_h, pooled_w, height, width);
+  __syncthreads();
+  const int cvecs = channels >> 2;
+  const int per_bin = g.grid_h * g.grid_w;
+  float* base = tab.grad[l] + (long long)g.batch_ind * height * width * channels;
+  const float4* go4 = reinterpret_cast<const float4*>(gout) + (long long)n * pooled_h * pooled_w * cvecs;
+  const int total = pooled_h * pooled_w * cvecs;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const int cv = i % cvecs, bin = i / cvecs;
+    const TapEntry* e = taps + bin * per_bin;
+    const float4 go = __ldg(go4 + i);
+    for (int k = 0; k < per_bin; ++k) {
+      const TapEntry t = e[k];
+      if (t.o1 < 0) continue;
+      const float ws[4] = {t.w1, t.w2, t.w3, t.w4};
+      const int os[4] = {t.o1, t.o2, t.o3, t.o4};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float4 v;   // g_k = top_diff * w_k / count  (ROIAlign_cuda.cu:238-241)
+        v.x = __fdiv_rn(__fmul_rn(go.x, ws[q]), g.count);
+        v.y = __fdiv_rn(__fmul_rn(go.y, ws[q]), g.count);
+        v.z = __fdiv_rn(__fmul_rn(go.z, ws[q]), g.count);
+        v.w = __fdiv_rn(__fmul_rn(go.w, ws[q]), g.count);
+        mmt::red_add_v4(base + ((long long)os[q] * cvecs + cv) * 4, v);
+      }
+    }
+  }
+}
+
 inline int grid_for(long long total, int block) {
   long long blocks = (total + block - 1) / block;
   const long long cap = (long long)mmt::kNumSMs * 8 * 4;  // 8 CTAs of 256 thr/SM resident, 4 waves
@@ -501,8 +614,12 @@ extern "C" int mmt_roi_align_fpn_forward_f32(const float* const* level_feats_hos
   const long long total = (long long)n_rois * pooled_h * pooled_w * (channels / 4);
   // algorithmic bytes: the pooled output written once (the taps are gathers from L2-resident maps)
   mmt::ProfScope prof(MMT_PROF_ROI_ALIGN, 0.0, 16.0 * total, (cudaStream_t)stream_);
-  roi_align_fpn_fwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream_>>>(
-      tab, channels, rois, roi_levels, pooled_h, pooled_w, sampling_ratio, output, total);
+  if (sampling_ratio > 0 && pooled_h * pooled_w * sampling_ratio * sampling_ratio <= kMaxSamplesV2)
+    roi_align_fpn_fwd2_kernel<<<n_rois, 256, 0, (cudaStream_t)stream_>>>(tab, channels, rois, roi_levels, pooled_h,
+                                                                        pooled_w, sampling_ratio, output);
+  else   // adaptive sampling grid (sampling_ratio <= 0): per-thread geometry
+    roi_align_fpn_fwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream_>>>(
+        tab, channels, rois, roi_levels, pooled_h, pooled_w, sampling_ratio, output, total);
   return mmt::check_launch("roi_align_fpn_forward");
 }
 
@@ -522,7 +639,11 @@ extern "C" int mmt_roi_align_fpn_backward_f32(const float* grad_output, const fl
                               n_levels, "roi_align_fpn_backward")) return rc;
   const long long total = (long long)n_rois * pooled_h * pooled_w * (channels / 4);
   mmt::ProfScope prof(MMT_PROF_ROI_ALIGN, 0.0, 16.0 * total, (cudaStream_t)stream_);
-  roi_align_fpn_bwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream_>>>(
-      tab, channels, grad_output, rois, roi_levels, pooled_h, pooled_w, sampling_ratio, total);
+  if (sampling_ratio > 0 && pooled_h * pooled_w * sampling_ratio * sampling_ratio <= kMaxSamplesV2)
+    roi_align_fpn_bwd2_kernel<<<n_rois, 256, 0, (cudaStream_t)stream_>>>(tab, channels, grad_output, rois, roi_levels,
+                                                                        pooled_h, pooled_w, sampling_ratio);
+  else
+    roi_align_fpn_bwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream_>>>(
+        tab, channels, grad_output, rois, roi_levels, pooled_h, pooled_w, sampling_ratio, total);
   return mmt::check_launch("roi_align_fpn_backward");
 }

@@ -165,6 +165,7 @@ class MTtrainer(object):
             elif self._gc_steps % self.gc_every == 0:
                 gc.collect(1)
             self._gc_steps += 1
+        reduced = False
         mt_on = iteration > self.start_mt and self.lambda_value > 0 and bool(self.cfg.DATASETS.NO_LABEL)
         stacked = False
         if self.cuda_graphs:
@@ -210,14 +211,26 @@ class MTtrainer(object):
             losses_dict.update(mt_weighted)
             mt_total = sum(v for v in mt_weighted.values()) if mt_weighted else None
             if stacked:
-                self.student.backward_deferred(mt_total)
+                # heads first; their gradient bucket (fc6 alone is 51 MB of the 185 MB arena) is then final and its
+                # all-reduce runs on NCCL's stream UNDER the trunk's backward graph; the trunk bucket follows it
+                self.student.backward_deferred_heads(mt_total)
+                if self.world > 1:
+                    early, late = self.optimizer.reduce_buckets()
+                    pending = [dist.all_reduce(t, async_op=True) for t in early]
+                self.student.backward_deferred_trunk()
+                if self.world > 1:
+                    self.optimizer.publish_touched()
+                    pending += [dist.all_reduce(t, async_op=True) for t in late]
+                    for w in pending:
+                        w.wait()
+                    reduced = True
             elif mt_total is not None:
                 mt_total.backward()
             losses = sup_total.detach() + (mt_total.detach() if mt_total is not None else 0)
         else:
             losses_dict, losses = sup_weighted, sup_total
             losses.backward()
-        if self.world > 1:
+        if self.world > 1 and not reduced:
             # one NCCL all-reduce: the whole student gradient arena + the per-tensor "touched" flags behind it
             dist.all_reduce(self.optimizer.reduce_buffer())
         ema = None

@@ -209,8 +209,17 @@ class GeneralizedRCNN(nn.Module):
         their heads down to the boundary leaves; then every boundary gradient — the supervised branch's, produced by
         the early supervised backward, and the consistency branch's — is written into its half of the trunk graph's
         gradient buffers and the captured trunk backward is replayed ONCE."""
+        self.backward_deferred_heads(extra_losses)
+        self.backward_deferred_trunk()
+
+    def backward_deferred_heads(self, extra_losses=None):
+        """First half of `backward_deferred`: the consistency terms' backward through their heads.  After it every
+        gradient that does NOT come out of the trunk graph (box / mask / relation heads) is final — a data-parallel
+        trainer starts all-reducing that bucket here, under the trunk's backward (MTtrainer.train_step)."""
         if extra_losses is not None:
             extra_losses.backward()
+
+    def backward_deferred_trunk(self):
         g = self._stu_graph
         covered = set()
         for out_index, lo, hi, leaf in self._deferred:

@@ -98,6 +98,29 @@ class FusedSGDEMA(object):
             self._seg_cache[key] = K.make_segments(ent, self.flat_p.device)
         return self._seg_cache[key]
 
+    def reduce_buckets(self, head_prefixes=("box_heads.", "mask_heads.", "relation_nms.")):
+        """(early, late): two lists of contiguous views of the all-reduce buffer.  `early` = the gradient ranges of the
+        parameters whose names start with `head_prefixes` (final once the heads' backward has run: they can be reduced
+        UNDER the trunk's backward); `late` = everything else — the trunk's ranges and the touched flags.  Together they
+        tile the whole buffer, so reducing both is reducing `reduce_buffer()`."""
+        cuts, on = [], False
+        for e in self.entries:
+            head = e["name"].startswith(tuple(head_prefixes))
+            if head != on:
+                cuts.append(e["begin"])
+                on = head
+        if on:
+            cuts.append(self.total)
+        bounds = [0] + cuts + [self._g_full.numel()]
+        early = [self._g_full[bounds[i]:bounds[i + 1]] for i in range(1, len(bounds) - 1, 2)]
+        late = [self._g_full[bounds[i]:bounds[i + 1]] for i in range(0, len(bounds) - 1, 2)]
+        return [t for t in early if t.numel()], [t for t in late if t.numel()]
+
+    def publish_touched(self):
+        """Write this rank's touched flags behind the gradient arena (they ride in the LAST bucket's all-reduce)."""
+        self._flags.copy_(torch.tensor(self.touched, dtype=torch.float32), non_blocking=True)
+        self._agreed = True
+
     def _agreed_segments(self):
         """Segment table whose update mask comes from the all-reduced flags: built on the device, no read-back."""
         segs = self._segments([True] * len(self.entries)).clone()

@@ -63,6 +63,24 @@ def _worker(rank, world, port, out):
     student[0](x).sum().backward()                                            # nobody touches layer 2: nobody updates it
     dist.all_reduce(opt.reduce_buffer())
     assert opt._agreed_segments().view(torch.int32).view(-1, 8)[:, 6].tolist() == [1, 1, 0, 0]
+    # bucketed exchange (heads' bucket reduced under the trunk's backward, trunk bucket + flags after it): the buckets tile
+    # the buffer exactly, and reducing them one by one equals the single all-reduce of the whole buffer
+    opt.zero_grad()
+    student(x * (rank + 2)).sum().backward()
+    early, late = opt.reduce_buckets(head_prefixes=("1.",))
+    spans = sorted((t.data_ptr(), t.numel()) for t in early + late)
+    assert spans[0][0] == opt._g_full.data_ptr() and sum(n for _, n in spans) == opt._g_full.numel()
+    assert all(a + 4 * n == b for (a, n), (b, _) in zip(spans, spans[1:]))
+    assert sum(t.numel() for t in early) == 28 and early[0].data_ptr() == student[1].weight.grad.data_ptr()
+    whole = opt._g_full.clone()
+    pending = [dist.all_reduce(t, async_op=True) for t in early]
+    opt.publish_touched()
+    whole[opt.total:opt.total + 4] = 1.0
+    pending += [dist.all_reduce(t, async_op=True) for t in late]
+    for w in pending:
+        w.wait()
+    dist.all_reduce(whole)
+    assert torch.equal(opt._g_full, whole)
     # logging reduce (reference MTtrainer.py:16-41): rank 0 receives the mean; a rank lacking a term sends zero for it
     red = reduce_loss_dict({"loss_a": torch.tensor(float(rank)), "mt_b": torch.tensor(2.0 * rank)})
     if rank == 0:

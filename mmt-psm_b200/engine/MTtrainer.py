@@ -10,11 +10,14 @@ teachers stay bit-identical across ranks without any traffic because EMA is a fu
 import datetime
 import gc
 import logging
+import os
 import time
+from concurrent.futures import ThreadPoolExecutor
 
 import torch
 import torch.distributed as dist
 
+from ..modeling.balanced_positive_negative_sampler import BalancedPositiveNegativeSampler as _Sampler
 from ..utils.comm import get_world_size
 from ..utils.miscellaneous import sigmoid_rampdown, sigmoid_rampup
 
@@ -89,6 +92,13 @@ class MTtrainer(object):
                 torch.cuda.memory._set_allocator_settings("expandable_segments:True")
             except Exception as e:   # older torch: keep going, only the stalls stay
                 self.logger.warning("could not switch the CUDA caching allocator to expandable segments: %s", e)
+        # Second host thread for the (no-grad, independent) teacher pass: the supervised pass and the teacher pass are each
+        # a string of ~300 small launches separated by ~8 device read-backs (data-dependent ROI counts); run one after the
+        # other the host sits in cudaStreamSynchronize ~10 ms per iteration with an empty device queue behind every one of
+        # them (profiles/r02_profile_step_d.md).  On two threads / two streams one pass enqueues while the other waits.
+        # Only with CUDA graphs on (the production / bench configuration); parity tests run the passes in order.
+        self.teacher_thread = os.environ.get("MMT_TEACHER_THREAD", "1") == "1"
+        self._t_stream, self._t_pool = None, None
         self.loss_keys = ["loss_classifier", "loss_box_reg", "loss_seg", "loss_objectness", "loss_rpn_box_reg"]
         if cfg.MODEL.RELATION_NMS.USE_RELATION_NMS:
             self.loss_keys.append("nms_loss")
@@ -123,22 +133,42 @@ class MTtrainer(object):
             self._iter_u = iter(self.dataloader_u)
             return next(self._iter_u)
 
-    def forward_unlabel(self, data_u_list=None):
+    def _teacher_pass(self, teacher_list):
+        """The no-grad teacher forward; None when the teacher produced no boxes for an image (the pair is skipped)."""
+        with torch.no_grad():
+            try:
+                return self.teacher.forward_teacher(teacher_list)
+            except ValueError as e:  # the reference swallows everything; only "no boxes" is expected
+                if "boxes available" not in str(e):
+                    raise
+                self.logger.warning("teacher produced no boxes for one image, skip this pair (%s)", e)
+                return None
+
+    def _teacher_job(self, teacher_list, main_stream):
+        """Body of the second host thread: the teacher pass on its own CUDA stream (ordered after everything the main
+        stream had enqueued when the job was submitted: the previous iteration's SGD + EMA, this iteration's uploads)."""
+        torch.cuda.set_device(self.device)
+        if self._t_stream is None:
+            self._t_stream = torch.cuda.Stream(device=self.device)
+        self._t_stream.wait_stream(main_stream)
+        with torch.cuda.stream(self._t_stream):
+            return self._teacher_pass(teacher_list)
+
+    def forward_unlabel(self, data_u_list=None, teacher_future=None):
         unlabel, loss_dict = [], {}
         for _ in range(self.n_step_unlabel):
             if data_u_list is None:
                 data_u_list, _ = self._next_unlabeled()
-            teacher_list = [f.to(self.device) for f in data_u_list[:self.teacher_bs]]
             student = [s.to(self.device) for s in data_u_list[-self.student_bs:]]
-            with torch.no_grad():
-                try:
-                    teacher_results = self.teacher.forward_teacher(teacher_list)
-                except ValueError as e:  # the reference swallows everything; only "no boxes" is expected
-                    if "boxes available" not in str(e):
-                        raise
-                    self.logger.warning("teacher produced no boxes for one image, skip this pair (%s)", e)
-                    data_u_list = None
-                    continue
+            if teacher_future is not None:
+                teacher_results = teacher_future.result()          # re-raises whatever the teacher thread raised
+                torch.cuda.current_stream(self.device).wait_stream(self._t_stream)
+                teacher_future = None
+            else:
+                teacher_results = self._teacher_pass([f.to(self.device) for f in data_u_list[:self.teacher_bs]])
+            if teacher_results is None:
+                data_u_list = None
+                continue
             unlabel.append(self.student.forward_student(student, teacher_results))
             data_u_list = None
         if not unlabel:
@@ -194,6 +224,13 @@ class MTtrainer(object):
                 self.student.prefetch_trunk("sup", img_s)
         self.scheduler.step()
         self.optimizer.zero_grad()
+        teacher_future = None
+        if stacked and self.teacher_thread and self.n_step_unlabel == 1 and _Sampler.rng_device is None:
+            # (parity mode draws from torch's global CPU generator in the reference's order: passes stay sequential there)
+            if self._t_pool is None:
+                self._t_pool = ThreadPoolExecutor(max_workers=1, thread_name_prefix="mmt-teacher")
+            teacher_future = self._t_pool.submit(self._teacher_job, list(data_u_list[:self.teacher_bs]),
+                                                 torch.cuda.current_stream(self.device))
         loss_dict = self.forward_source(data_s, target_s)
         # The supervised terms carry weight 1 (no 'mt' in their keys, MTtrainer.py:99 of the reference), so their
         # backward does not depend on the consistency ramp: run it NOW — its device work overlaps the teacher pass's
@@ -205,7 +242,7 @@ class MTtrainer(object):
         sup_total = sum(v for v in sup_weighted.values())
         if mt_on:
             sup_total.backward()
-            mt_dict = self.forward_unlabel(data_u_list)
+            mt_dict = self.forward_unlabel(data_u_list, teacher_future)
             mt_weighted = self.weight_sum_loss(mt_dict, iteration)
             losses_dict = dict(sup_weighted)
             losses_dict.update(mt_weighted)

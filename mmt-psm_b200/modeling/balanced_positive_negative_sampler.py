@@ -10,12 +10,18 @@ import torch
 class BalancedPositiveNegativeSampler(object):
     rng_device = None  # None = the labels' device
 
+    _instances = 0
+    _offset_cache = {}
+
     def __init__(self, batch_size_per_image, positive_fraction):
         self.batch_size_per_image = batch_size_per_image
         self.positive_fraction = positive_fraction
-
-    _calls = 0          # stream position of the device-side sampler (with torch.initial_seed() = its seed)
-    _offset_cache = {}
+        # the device-side sampler's random stream: (torch.initial_seed(), this sampler's ordinal, its own call count) —
+        # per instance, so that the draws do not depend on how the passes of an iteration interleave (the trainer runs
+        # the teacher pass on a second host thread)
+        BalancedPositiveNegativeSampler._instances += 1
+        self._ordinal = BalancedPositiveNegativeSampler._instances
+        self._calls = 0
 
     def _sample_on_device(self, matched_idxs):
         """One launch for the whole batch (libmmtpsm_b200 `mmt_balanced_sample_f32`): per image a uniformly random
@@ -36,8 +42,8 @@ class BalancedPositiveNegativeSampler(object):
             offs = torch.tensor(acc, dtype=torch.int32, device=dev)
             BalancedPositiveNegativeSampler._offset_cache[key] = offs
         labels = matched_idxs[0] if len(matched_idxs) == 1 else torch.cat(list(matched_idxs))
-        BalancedPositiveNegativeSampler._calls += 1
-        seed = (torch.initial_seed() * 0x9E3779B1 + BalancedPositiveNegativeSampler._calls * 0x85EBCA77) & 0xFFFFFFFFFFFFFFFF
+        self._calls += 1
+        seed = (torch.initial_seed() * 0x9E3779B1 + self._calls * 0x85EBCA77 + self._ordinal * 0xC2B2AE3D27D4EB4F) & 0xFFFFFFFFFFFFFFFF
         pos, neg = K.balanced_sample(labels.to(torch.float32), offs, len(sizes), self.batch_size_per_image,
                                      int(self.batch_size_per_image * self.positive_fraction), seed)
         return list(pos.split(sizes)), list(neg.split(sizes))

@@ -53,6 +53,7 @@ KNOBS = {
     "nopdl": dict(pdl=0, cg=0, fused=True),
     "cg1": dict(pdl=1, cg=1, fused=True),
     "unfused": dict(pdl=1, cg=0, fused=False),
+    "nothread": dict(pdl=1, cg=0, fused=True, thread=False),
 }
 it = [2000]
 
@@ -78,6 +79,7 @@ for visit in range(2):
         L.mmt_conv_set_pdl(k["pdl"])
         L.mmt_conv_force_cta_group(k["cg"])
         BottleneckWithFixedBatchNorm.fused_backward = k["fused"]
+        trainer.teacher_thread = k.get("thread", True)
         trainer.set_cuda_graphs(True)
         run(4)
         t = run(args.steps)

@@ -276,3 +276,40 @@ def test_cuda_graph_trunks_match_eager(cuda, restore):
         assert abs(s0[k] - s1[k]) <= 2e-2 * max(abs(s0[k]), 1e-2), (k, s0[k], s1[k])
     # replayed launches are accounted for; the graphed run stacks the two student trunks into one pass (fewer launches)
     assert 0.5 * n0 <= n1 <= 1.05 * n0, (n0, n1)
+
+
+def test_teacher_thread_matches_sequential(cuda, restore):
+    """The trainer's second host thread (teacher pass on its own stream, concurrent with the supervised pass) changes WHEN
+    kernels are enqueued, not what they compute: with the device-side sampler (per-sampler counter-based streams, so the
+    draws do not depend on the interleaving) two iterations give the same losses and the same updated weights as the
+    sequential schedule, up to the wgrad reduction order."""
+    from mmt_psm_b200.engine import MTtrainer
+    from mmt_psm_b200.modeling.balanced_positive_negative_sampler import BalancedPositiveNegativeSampler
+    from mmt_psm_b200.solver import make_lr_scheduler, make_optimizer
+    results = []
+    for threaded in (False, True):
+        cfg, student, teacher, sd, images, targets, views, g = _build(cuda)
+        BalancedPositiveNegativeSampler.rng_device = None          # the shipped sampler
+        for m in (student, teacher):                                # same sampler streams in both runs
+            for s in (m.rpn.loss_evaluator.fg_bg_sampler, m.box_heads.box.loss_evaluator.fg_bg_sampler):
+                s._calls = 0
+        student.rpn.loss_evaluator.fg_bg_sampler._ordinal, student.box_heads.box.loss_evaluator.fg_bg_sampler._ordinal = 1, 2
+        teacher.rpn.loss_evaluator.fg_bg_sampler._ordinal, teacher.box_heads.box.loss_evaluator.fg_bg_sampler._ordinal = 3, 4
+        opt = make_optimizer(cfg, student, teacher)
+        trainer = MTtrainer(student, teacher, None, opt, make_lr_scheduler(cfg, opt), None, None, 10 ** 9, cfg, cuda_graphs=True)
+        trainer.teacher_thread = threaded
+        torch.manual_seed(7)
+        losses = []
+        dimg, dtg, dviews = images.to(cuda), [t.to(cuda) for t in targets], [v.to(cuda) for v in views]
+        for it in (5, 6, 7):
+            ld, total = trainer.train_step(it, dimg, dtg, dviews)
+            losses.append({k: float(v) for k, v in ld.items()})
+        assert (trainer._t_pool is not None) == threaded
+        results.append((losses, opt.flat_p.clone(), opt.flat_t.clone()))
+    (l0, p0, t0), (l1, p1, t1) = results
+    for a, b in zip(l0[:1], l1[:1]):          # first iteration: identical weights and draws
+        for k in a:
+            assert abs(a[k] - b[k]) <= 1e-5 * max(abs(a[k]), 1e-2), (k, a[k], b[k])
+    for a, b in zip(l0[1:], l1[1:]):          # later iterations: 1e-7 weight differences may flip a discrete decision
+        for k in a:
+            assert abs(a[k] - b[k]) <= 2e-2 * max(abs(a[k]), 1e-2), (k, a[k], b[k])

@@ -99,6 +99,8 @@ class MTtrainer(object):
         # Only with CUDA graphs on (the production / bench configuration); parity tests run the passes in order.
         self.teacher_thread = os.environ.get("MMT_TEACHER_THREAD", "1") == "1"
         self._t_stream, self._t_pool = None, None
+        self.pool_gb = tuple(float(v) for v in os.environ.get("MMT_POOL_GB", "6,4").split(","))   # main stream, teacher stream
+        self._pregrow_pool(self.pool_gb[0])
         self.loss_keys = ["loss_classifier", "loss_box_reg", "loss_seg", "loss_objectness", "loss_rpn_box_reg"]
         if cfg.MODEL.RELATION_NMS.USE_RELATION_NMS:
             self.loss_keys.append("nms_loss")
@@ -144,14 +146,29 @@ class MTtrainer(object):
                 self.logger.warning("teacher produced no boxes for one image, skip this pair (%s)", e)
                 return None
 
+    def _pregrow_pool(self, gigabytes, small_blocks=2048):
+        """Grow the caching allocator's pools OF THE CURRENT STREAM once, up front: one large block and a few thousand
+        small ones, allocated and released again, stay mapped in the stream's (expandable) segments, so the data-dependent
+        block sizes of later iterations are carved out of them instead of mapping fresh pages — an operation that stalls
+        the calling thread AND every other thread waiting for the allocator lock for ~10 ms each while the device is busy
+        (profiles/r02_stall_trace.md, second half)."""
+        if self.device.type != "cuda" or gigabytes <= 0:
+            return
+        big = torch.empty(int(gigabytes * (1 << 30)), dtype=torch.uint8, device=self.device)
+        small = [torch.empty(256 << 10, dtype=torch.uint8, device=self.device) for _ in range(small_blocks)]
+        del big, small
+
     def _teacher_job(self, teacher_list, main_stream):
         """Body of the second host thread: the teacher pass on its own CUDA stream (ordered after everything the main
         stream had enqueued when the job was submitted: the previous iteration's SGD + EMA, this iteration's uploads)."""
         torch.cuda.set_device(self.device)
-        if self._t_stream is None:
+        fresh = self._t_stream is None
+        if fresh:
             self._t_stream = torch.cuda.Stream(device=self.device)
         self._t_stream.wait_stream(main_stream)
         with torch.cuda.stream(self._t_stream):
+            if fresh:
+                self._pregrow_pool(self.pool_gb[1])
             return self._teacher_pass(teacher_list)
 
     def forward_unlabel(self, data_u_list=None, teacher_future=None):

@@ -291,7 +291,8 @@ def run_ours(args):
     def alloc_counters():
         st = torch.cuda.memory_stats(dev)
         return (st.get("num_device_alloc", 0), st.get("num_device_free", 0), st.get("num_alloc_retries", 0),
-                st.get("reserved_bytes.all.current", 0) >> 20)
+                st.get("reserved_bytes.all.current", 0) >> 20, st.get("active_bytes.all.current", 0) >> 20,
+                st.get("reserved_bytes.small_pool.current", 0) >> 20, st.get("inactive_split_bytes.all.current", 0) >> 20)
 
     step_stats = {}
 
@@ -316,7 +317,7 @@ def run_ours(args):
                 a1 = alloc_counters()
                 print("step %s %d: %.2f ms (host enqueue %.2f)  cudaMalloc +%d cudaFree +%d retries +%d reserved %d MiB" % (
                     "e2e" if e2e else "dev", j, (time.perf_counter() - ts) * 1e3, host_ms[-1], a1[0] - a0[0], a1[1] - a0[1],
-                    a1[2] - a0[2], a1[3]), file=sys.stderr, flush=True)
+                    a1[2] - a0[2], a1[3]) + " active %d small-pool %d inactive-split %d" % (a1[4], a1[5], a1[6]), file=sys.stderr, flush=True)
         barrier()
         wall = time.perf_counter() - t0
         ms = marks[0].elapsed_time(marks[k])

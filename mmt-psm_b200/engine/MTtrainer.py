@@ -100,7 +100,7 @@ class MTtrainer(object):
         self.teacher_thread = os.environ.get("MMT_TEACHER_THREAD", "1") == "1"
         self._t_stream, self._t_pool = None, None
         self.pool_gb = tuple(float(v) for v in os.environ.get("MMT_POOL_GB", "6,4").split(","))   # main stream, teacher stream
-        self._pregrow_pool(self.pool_gb[0])
+        self._pregrow_main = self._pregrow_teacher = False
         self.loss_keys = ["loss_classifier", "loss_box_reg", "loss_seg", "loss_objectness", "loss_rpn_box_reg"]
         if cfg.MODEL.RELATION_NMS.USE_RELATION_NMS:
             self.loss_keys.append("nms_loss")
@@ -162,12 +162,12 @@ class MTtrainer(object):
         """Body of the second host thread: the teacher pass on its own CUDA stream (ordered after everything the main
         stream had enqueued when the job was submitted: the previous iteration's SGD + EMA, this iteration's uploads)."""
         torch.cuda.set_device(self.device)
-        fresh = self._t_stream is None
-        if fresh:
+        if self._t_stream is None:
             self._t_stream = torch.cuda.Stream(device=self.device)
         self._t_stream.wait_stream(main_stream)
         with torch.cuda.stream(self._t_stream):
-            if fresh:
+            if self._pregrow_teacher:
+                self._pregrow_teacher = False
                 self._pregrow_pool(self.pool_gb[1])
             return self._teacher_pass(teacher_list)
 
@@ -209,6 +209,9 @@ class MTtrainer(object):
                 # of the last iterations (17-20 ms -> well under a millisecond per collection)
                 gc.collect()
                 gc.freeze()
+                # (after the graphs have been captured: torch.cuda.graph() empties the allocator's cache when it starts)
+                self._pregrow_pool(self.pool_gb[0])
+                self._pregrow_teacher = True
             elif self._gc_steps % self.gc_every == 0:
                 gc.collect(1)
             self._gc_steps += 1

@@ -60,14 +60,23 @@ def peaks():
 
 
 def ncu_traffic():
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the tcgen05 conv family, from the committed ncu capture
-    of this command (profiles/r01_conv_traffic_v3.json); None if the summary is absent."""
-    p = os.path.join(ROOT, "profiles", "r01_conv_traffic_v3.json")
-    try:
-        fam = json.load(open(p))["families"]
-        return [f for f in fam if f["kernel"].startswith("all")][0]["dram_bytes_per_launch"]
-    except (OSError, KeyError, IndexError, ValueError):
-        return None
+    """(dram__bytes_read.sum + dram__bytes_write.sum per launch of the tcgen05 conv family, provenance) from the newest
+    committed ncu capture profiles/r*_conv_traffic.json — but ONLY if that capture was taken on THIS build: the file
+    records the sha256 of the kernel sources (scripts/source_hash.py); a stale capture yields (None, why)."""
+    import glob
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    from source_hash import source_hash
+    cur = source_hash()
+    for p in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_conv_traffic.json")), reverse=True):
+        try:
+            d = json.load(open(p))
+            if d.get("source_hash") != cur:
+                continue
+            fam = [f for f in d["families"] if f["kernel"].startswith("all")][0]
+            return fam["dram_bytes_per_launch"], "%s (build %s)" % (os.path.basename(p), cur)
+        except (OSError, KeyError, IndexError, ValueError):
+            continue
+    return None, "no ncu capture of build %s under profiles/ (run scripts/refresh_profiles.sh)" % cur
 
 
 def workload_name(args):
@@ -385,11 +394,12 @@ def run_ours(args):
         fl_tc = sum(f["flops"] for f in tc)
         n_tc = sum(f["launches"] for f in tc)
         achieved = fl_tc / (ms_tc * 1e-3) / 1e12 if ms_tc > 0 else 0.0
+        traffic, traffic_src = ncu_traffic()
         roof = {"bound": "tensor", "kernel": "conv_tc_kernel<BN> + wgrad_tc_kernel<BN> (TMA + tcgen05 kind::tf32 implicit GEMM)",
                 "achieved": achieved, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": achieved / pk["tensor"],
                 "peak_source": pk["source"] + ": bf16 cuBLAS sustained; the kernel feeds TF32 operands (fp32 storage), whose "
                 "hardware rate is half the bf16 rate, so frac <= 0.5 by construction",
-                "frac_of_tf32_rate": achieved / (pk["tensor"] / 2), "traffic": ncu_traffic(),
+                "frac_of_tf32_rate": achieved / (pk["tensor"] / 2), "traffic": traffic, "traffic_source": traffic_src,
                 "algorithmic_bytes_per_launch": sum(f["bytes"] for f in tc) / max(n_tc, 1),
                 "launches_per_step": n_tc / nprof, "avg_launch_us": ms_tc / max(n_tc, 1) * 1e3,
                 "gflop_per_launch": fl_tc / max(n_tc, 1) / 1e9,

@@ -42,6 +42,14 @@ __global__ void __launch_bounds__(256) sgd_ema_kernel(
   for (long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i4 < n4;
        i4 += (long long)gridDim.x * blockDim.x) {
     const long long e = i4 * 4;
+    // The four streams are read FIRST, unconditionally (the arenas are padded to whole float4 groups, so the vector
+    // loads are always in bounds): 64 bytes per thread are in flight while the segment lookup below runs, instead of
+    // the loads waiting for a 9-step dependent search.  Frozen tensors (< 1 % of the arena) pay two unused loads.
+    const float4 P = *reinterpret_cast<const float4*>(p + e);
+    const float4 G = __ldg(reinterpret_cast<const float4*>(g + e));
+    float4 B = make_float4(0.f, 0.f, 0.f, 0.f), T = B;
+    if (!first_step) B = *reinterpret_cast<const float4*>(buf + e);
+    if (t) T = *reinterpret_cast<const float4*>(t + e);
     // segment lookup: last segment whose begin <= e
     int lo = 0, hi = n_segs - 1;
     while (lo < hi) {
@@ -52,23 +60,8 @@ __global__ void __launch_bounds__(256) sgd_ema_kernel(
     const mmt_param_segment sg = segs[lo];
     if (e < sg.begin || e >= sg.end) continue;  // padding between tensors
     const int cnt = (int)min((long long)4, sg.end - e);
-    float pv[4], tv[4], gv[4], bv[4];
-    if (cnt == 4) {
-      const float4 P = *reinterpret_cast<const float4*>(p + e);
-      pv[0] = P.x; pv[1] = P.y; pv[2] = P.z; pv[3] = P.w;
-      if (t) { const float4 T = *reinterpret_cast<const float4*>(t + e); tv[0] = T.x; tv[1] = T.y; tv[2] = T.z; tv[3] = T.w; }
-      if (sg.trainable) {
-        const float4 G = __ldg(reinterpret_cast<const float4*>(g + e));
-        gv[0] = G.x; gv[1] = G.y; gv[2] = G.z; gv[3] = G.w;
-        if (!first_step) { const float4 B = *reinterpret_cast<const float4*>(buf + e); bv[0] = B.x; bv[1] = B.y; bv[2] = B.z; bv[3] = B.w; }
-      }
-    } else {
-      for (int k = 0; k < cnt; ++k) {
-        pv[k] = p[e + k];
-        if (t) tv[k] = t[e + k];
-        if (sg.trainable) { gv[k] = g[e + k]; if (!first_step) bv[k] = buf[e + k]; }
-      }
-    }
+    float pv[4] = {P.x, P.y, P.z, P.w}, tv[4] = {T.x, T.y, T.z, T.w};
+    float gv[4] = {G.x, G.y, G.z, G.w}, bv[4] = {B.x, B.y, B.z, B.w};
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       if (k < cnt) {
@@ -89,7 +82,7 @@ __global__ void __launch_bounds__(256) sgd_ema_kernel(
         *reinterpret_cast<float4*>(buf + e) = make_float4(bv[0], bv[1], bv[2], bv[3]);
       }
       if (t) *reinterpret_cast<float4*>(t + e) = make_float4(tv[0], tv[1], tv[2], tv[3]);
-    } else {
+    } else {  // last group of a tensor: the elements behind it are padding and stay untouched
       for (int k = 0; k < cnt; ++k) {
         if (sg.trainable) { p[e + k] = pv[k]; buf[e + k] = bv[k]; }
         if (t) t[e + k] = tv[k];
@@ -127,6 +120,7 @@ extern "C" int mmt_sgd_ema_f32(float* student, float* teacher, const float* grad
   MMT_REQUIRE(n >= 0 && n_segments >= 0, "sgd_ema: bad sizes");
   if (n == 0 || n_segments == 0) return MMT_OK;
   MMT_REQUIRE(student && grad && momentum_buf && segments_dev, "sgd_ema: null pointer");
+  MMT_REQUIRE(n % 4 == 0, "sgd_ema: the arenas must be padded to a multiple of 4 elements (got %lld)", (long long)n);
   MMT_REQUIRE(((uintptr_t)student % 16 == 0) && ((uintptr_t)grad % 16 == 0) &&
                   ((uintptr_t)momentum_buf % 16 == 0) && (!teacher || (uintptr_t)teacher % 16 == 0),
               "sgd_ema: arenas must be 16-byte aligned");

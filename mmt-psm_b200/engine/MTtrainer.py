@@ -100,7 +100,7 @@ class MTtrainer(object):
         self.teacher_thread = os.environ.get("MMT_TEACHER_THREAD", "1") == "1"
         self._t_stream, self._t_pool = None, None
         self.pool_gb = tuple(float(v) for v in os.environ.get("MMT_POOL_GB", "6,4").split(","))   # main stream, teacher stream
-        self._pregrow_main = self._pregrow_teacher = False
+        self._pregrown_for, self._pregrow_teacher = 0, False
         self.loss_keys = ["loss_classifier", "loss_box_reg", "loss_seg", "loss_objectness", "loss_rpn_box_reg"]
         if cfg.MODEL.RELATION_NMS.USE_RELATION_NMS:
             self.loss_keys.append("nms_loss")
@@ -203,18 +203,21 @@ class MTtrainer(object):
             if self._gc_steps == 0:
                 gc.collect()
                 gc.disable()
-            elif self._gc_steps == 4:
-                # everything alive now (models, captured graphs, cached anchors, the config tree) lives as long as the
-                # trainer: park it in the permanent generation so that the paced collections below only walk the objects
-                # of the last iterations (17-20 ms -> well under a millisecond per collection)
-                gc.collect()
-                gc.freeze()
-                # (after the graphs have been captured: torch.cuda.graph() empties the allocator's cache when it starts)
-                self._pregrow_pool(self.pool_gb[0])
-                self._pregrow_teacher = True
             elif self._gc_steps % self.gc_every == 0:
                 gc.collect(1)
             self._gc_steps += 1
+        # First iteration after a CUDA-graph capture (torch.cuda.graph() empties the allocator's cache when it starts, so
+        # anything grown earlier is gone): grow the per-stream pools now, and park everything alive — models, captured
+        # graphs, cached anchors, the config tree: as long-lived as the trainer — in the GC's permanent generation, so
+        # that the paced collections above only walk the objects of the last iterations (17-20 ms -> < 1 ms each).
+        n_graphs = len(getattr(self.student, "_graphs", ())) + len(getattr(self.teacher, "_graphs", ()))
+        if self.cuda_graphs and n_graphs and n_graphs != self._pregrown_for:
+            self._pregrown_for = n_graphs
+            if self.gc_every > 0:
+                gc.collect()
+                gc.freeze()
+            self._pregrow_pool(self.pool_gb[0])
+            self._pregrow_teacher = True
         reduced = False
         mt_on = iteration > self.start_mt and self.lambda_value > 0 and bool(self.cfg.DATASETS.NO_LABEL)
         stacked = False

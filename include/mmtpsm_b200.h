@@ -130,6 +130,16 @@ int mmt_rpn_gather_f32(const float* fused_nhwc, int padded_channels, int num_anc
                        const int64_t* topk_idx, const float* topk_vals, const float* level_anchors, int n_images,
                        int k, int k_total, int col_offset, float* deltas_out, float* anchors_out, float* scores_out,
                        void* stream);
+/* RPN candidate selection for ALL (image, level) problems of a pass in one launch: per row of `level_scores[l]` ([n_images,
+ * n_l] sigmoid objectness in (h, w, anchor) order) the k_l highest scores in descending order — reference
+ * rpn/inference.py:92-94 `objectness.topk(pre_nms_top_n, dim=1, sorted=True)`; equal scores are ordered by ascending
+ * anchor index — fused with mmt_rpn_gather_f32: deltas / anchors / scores of the selected candidates are written to
+ * columns [sum_{m<l} k_m, +k_l) of the [n_images, k_total] tables.  The level tables are HOST arrays of device pointers /
+ * sizes.  k_l <= 2048 (MMT_ERR_UNSUPPORTED otherwise: use torch.topk + mmt_rpn_gather_f32). */
+int mmt_rpn_topk_gather_f32(const float* const* level_scores_host, const float* const* level_fused_host,
+                            const float* const* level_anchors_host, const int* level_n_host, const int* level_k_host,
+                            int n_levels, int n_images, int num_anchors, int padded_channels, int k_total,
+                            float* deltas_out, float* anchors_out, float* scores_out, void* stream);
 /* Single problem convenience form (exactly `_C.nms(dets, scores, thr)` minus the tensor plumbing). */
 int mmt_nms_f32(const float* boxes_xyxy, const float* scores, int n, float iou_threshold,
                 int64_t* keep_out, int* n_keep_out, void* workspace, size_t workspace_bytes,

@@ -501,3 +501,174 @@ extern "C" int mmt_rpn_gather_f32(const float* fused_nhwc, int padded_channels, 
       reinterpret_cast<float4*>(deltas_out), reinterpret_cast<float4*>(anchors_out), scores_out);
   return mmt::check_launch("rpn_gather");
 }
+
+
+// ------------------------------------------------------------------------------------------------
+// RPN candidate selection: per (image, level) the pre_nms_top_n highest objectness scores in descending order
+// (reference modeling/rpn/inference.py:92-94: `objectness.topk(pre_nms_top_n, dim=1, sorted=True)`) FUSED with the gather
+// above — ONE launch for every (image, level) problem of a pass instead of, per level, torch's multi-block radix top-k
+// (5-6 kernels, ~55 us) + a sort + the gather.  One 1024-thread CTA per problem:
+//   * rows of <= 2048 anchors (the two coarsest levels) are sorted whole;
+//   * otherwise an MSB-first radix select (4 passes of 8 bits over the row, per-warp shared-memory histograms) finds the
+//     bit pattern T of the k-th largest score exactly, a compaction pass collects the scores > T plus the lowest-index
+//     scores == T, and a bitonic sort of (score bits, ~index) orders the <= 2048 survivors: descending score, ascending
+//     anchor index among equal scores (torch.topk leaves that order unspecified).
+namespace {
+constexpr int kTopkThreads = 1024;
+constexpr int kTopkCap = 2048;
+constexpr int kTopkLevels = 8;
+
+struct TopkTab {
+  const float* scores[kTopkLevels];   // [N, n]
+  const float* fused[kTopkLevels];    // [N, n / A, Cp]
+  const float4* anchors[kTopkLevels]; // [n]
+  int n[kTopkLevels], k[kTopkLevels], col[kTopkLevels];
+};
+
+__device__ __forceinline__ uint32_t ordered_key(float x) {   // monotone: a < b  <=>  key(a) < key(b)
+  const uint32_t u = __float_as_uint(x);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key_to_float(uint32_t key) {
+  return __uint_as_float((key & 0x80000000u) ? (key & 0x7fffffffu) : ~key);
+}
+
+__global__ void __launch_bounds__(kTopkThreads) rpn_topk_gather_kernel(TopkTab tab, int n_levels, int N, int A, int Cp,
+                                                                      int K_total, float4* __restrict__ deltas,
+                                                                      float4* __restrict__ anch, float* __restrict__ scores_out) {
+  __shared__ int hist[16][256];   // one histogram per pair of warps
+  __shared__ unsigned long long buf[kTopkCap];
+  __shared__ int s_total[256];
+  __shared__ uint32_t s_prefix;
+  __shared__ int s_want, s_cnt, s_tie_base, s_ties;
+  const int l = blockIdx.x % n_levels, img = blockIdx.x / n_levels;
+  const int n = tab.n[l], k = tab.k[l];
+  const float* __restrict__ s = tab.scores[l] + (long long)img * n;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  for (int i = tid; i < kTopkCap; i += kTopkThreads) buf[i] = 0ull;   // 0 sorts behind every real entry (keys are >= 1)
+  if (tid == 0) { s_prefix = 0u; s_want = k; s_cnt = 0; s_tie_base = 0; s_ties = 0; }
+  __syncthreads();
+
+  if (n <= kTopkCap) {
+    for (int i = tid; i < n; i += kTopkThreads)
+      buf[i] = ((unsigned long long)ordered_key(__ldg(s + i)) << 32) | (uint32_t)(~(uint32_t)i);
+  } else {
+    // ---- radix select: after pass p the top 8 * (p + 1) bits of the k-th largest key are known
+    for (int pass = 0; pass < 4; ++pass) {
+      const int shift = 24 - 8 * pass;
+      for (int i = tid; i < 16 * 256; i += kTopkThreads) (&hist[0][0])[i] = 0;
+      __syncthreads();
+      const uint32_t prefix = s_prefix;
+      const uint32_t hi_mask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
+      for (int i = tid; i < n; i += kTopkThreads) {
+        const uint32_t key = ordered_key(__ldg(s + i));
+        if ((key & hi_mask) == prefix) atomicAdd(&hist[warp >> 1][(key >> shift) & 255u], 1);
+      }
+      __syncthreads();
+      if (tid < 256) {
+        int t = 0;
+#pragma unroll 8
+        for (int w = 0; w < 16; ++w) t += hist[w][tid];
+        s_total[tid] = t;
+      }
+      __syncthreads();
+      if (tid == 0) {
+        int want = s_want, d = 255, above = 0;
+        while (d > 0 && above + s_total[d] < want) { above += s_total[d]; --d; }
+        s_want = want - above;                       // how many of the elements with this digit are still needed
+        s_prefix = prefix | ((uint32_t)d << shift);
+        if (pass == 3) s_ties = s_total[d];          // elements whose key equals the threshold exactly
+      }
+      __syncthreads();
+    }
+    const uint32_t T = s_prefix;
+    const int want = s_want, ties = s_ties;          // want >= 1 of the `ties` elements equal to T
+    // ---- compaction: everything above T (count = k - want), then `want` of the ties — the lowest indices
+    if (ties == want) {                              // common case: take them all, order restored by the sort
+      for (int i = tid; i < n; i += kTopkThreads) {
+        const uint32_t key = ordered_key(__ldg(s + i));
+        if (key >= T) buf[atomicAdd(&s_cnt, 1)] = ((unsigned long long)key << 32) | (uint32_t)(~(uint32_t)i);
+      }
+    } else {
+      __shared__ int warp_ties[32];
+      for (int base = 0; base < n; base += kTopkThreads) {
+        const int i = base + tid;
+        const uint32_t key = i < n ? ordered_key(__ldg(s + i)) : 0u;
+        const bool gt = i < n && key > T, eq = i < n && key == T;
+        if (gt) buf[atomicAdd(&s_cnt, 1)] = ((unsigned long long)key << 32) | (uint32_t)(~(uint32_t)i);
+        const unsigned m = __ballot_sync(0xffffffffu, eq);
+        if (lane == 0) warp_ties[warp] = __popc(m);
+        __syncthreads();
+        int before = s_tie_base;
+        for (int w = 0; w < warp; ++w) before += warp_ties[w];
+        const int rank = before + __popc(m & ((1u << lane) - 1u));
+        if (eq && rank < want) buf[(k - want) + rank] = ((unsigned long long)key << 32) | (uint32_t)(~(uint32_t)i);
+        __syncthreads();
+        if (tid == 0) {
+          int t = s_tie_base;
+          for (int w = 0; w < 32; ++w) t += warp_ties[w];
+          s_tie_base = t;
+        }
+        __syncthreads();
+      }
+    }
+  }
+  __syncthreads();
+  // ---- bitonic sort, descending, of the kTopkCap 64-bit entries (empty slots are 0 and end up last)
+  for (int size = 2; size <= kTopkCap; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      const int pos = 2 * tid - (tid & (stride - 1));
+      const bool desc = (pos & size) == 0;
+      const unsigned long long a = buf[pos], b = buf[pos + stride];
+      if ((a < b) == desc) { buf[pos] = b; buf[pos + stride] = a; }
+      __syncthreads();
+    }
+  }
+  // ---- gather: deltas from the fused head map, anchors, scores -> the pass-wide tables at this level's columns
+  const int HW = n / A;
+  const float* __restrict__ f = tab.fused[l] + (long long)img * HW * Cp;
+  for (int j = tid; j < k; j += kTopkThreads) {
+    const unsigned long long e = buf[j];
+    const uint32_t i = ~(uint32_t)(e & 0xffffffffull);
+    const int pix = (int)(i / (uint32_t)A), a = (int)(i - (uint32_t)pix * A);
+    const float* src = f + (long long)pix * Cp + A + 4 * a;
+    const long long o = (long long)img * K_total + tab.col[l] + j;
+    deltas[o] = make_float4(__ldg(src), __ldg(src + 1), __ldg(src + 2), __ldg(src + 3));
+    anch[o] = __ldg(tab.anchors[l] + i);
+    scores_out[o] = key_to_float((uint32_t)(e >> 32));
+  }
+}
+}  // namespace
+
+extern "C" int mmt_rpn_topk_gather_f32(const float* const* level_scores_host, const float* const* level_fused_host,
+                                       const float* const* level_anchors_host, const int* level_n_host,
+                                       const int* level_k_host, int n_levels, int n_images, int num_anchors,
+                                       int padded_channels, int k_total, float* deltas_out, float* anchors_out,
+                                       float* scores_out, void* stream_) {
+  MMT_REQUIRE(n_levels >= 1 && n_levels <= kTopkLevels && n_images >= 0 && num_anchors > 0, "rpn_topk_gather: bad sizes");
+  if (n_images == 0) return MMT_OK;
+  MMT_REQUIRE(level_scores_host && level_fused_host && level_anchors_host && level_n_host && level_k_host && deltas_out &&
+                  anchors_out && scores_out, "rpn_topk_gather: null pointer");
+  MMT_REQUIRE(padded_channels >= 5 * num_anchors, "rpn_topk_gather: head map narrower than 5 x anchors");
+  MMT_REQUIRE((((uintptr_t)deltas_out | (uintptr_t)anchors_out) & 15) == 0, "rpn_topk_gather: box arrays must be 16-byte aligned");
+  TopkTab tab;
+  int col = 0;
+  for (int l = 0; l < n_levels; ++l) {
+    MMT_REQUIRE(level_scores_host[l] && level_fused_host[l] && level_anchors_host[l], "rpn_topk_gather: null level pointer");
+    MMT_REQUIRE(((uintptr_t)level_anchors_host[l] & 15) == 0, "rpn_topk_gather: anchors must be 16-byte aligned");
+    MMT_REQUIRE(level_n_host[l] > 0 && level_n_host[l] % num_anchors == 0 && level_k_host[l] > 0 &&
+                    level_k_host[l] <= level_n_host[l], "rpn_topk_gather: bad level size");
+    if (level_k_host[l] > kTopkCap)
+      return mmt::fail(MMT_ERR_UNSUPPORTED, "rpn_topk_gather: k = %d exceeds the in-kernel sort capacity %d", level_k_host[l], kTopkCap);
+    tab.scores[l] = level_scores_host[l]; tab.fused[l] = level_fused_host[l];
+    tab.anchors[l] = reinterpret_cast<const float4*>(level_anchors_host[l]);
+    tab.n[l] = level_n_host[l]; tab.k[l] = level_k_host[l]; tab.col[l] = col;
+    col += level_k_host[l];
+  }
+  MMT_REQUIRE(col == k_total, "rpn_topk_gather: k_total %d != sum of the level k (%d)", k_total, col);
+  rpn_topk_gather_kernel<<<n_images * n_levels, kTopkThreads, 0, (cudaStream_t)stream_>>>(
+      tab, n_levels, n_images, num_anchors, padded_channels, k_total, reinterpret_cast<float4*>(deltas_out),
+      reinterpret_cast<float4*>(anchors_out), scores_out);
+  return mmt::check_launch("rpn_topk_gather");
+}

@@ -126,6 +126,27 @@ def rpn_gather(fused, num_anchors, topk_idx, topk_vals, level_anchors, deltas_ou
                                _p(scores_out), _stream()), "rpn_gather")
 
 
+def rpn_topk_gather(scores, fused, num_anchors, level_anchors, ks, deltas_out, anchors_out, scores_out):
+    """All levels of a pass in ONE launch: per image and level the ks[l] best objectness scores (descending; ties by
+    ascending anchor index) and, for them, the deltas (from the fused head maps), anchors and scores written into the
+    pass-wide [N, sum(ks)] tables.  Returns False — nothing done — if a level asks for more than the kernel's 2048."""
+    _need_cuda(*scores, *fused, *level_anchors, deltas_out, anchors_out, scores_out)
+    L = _l.lib()
+    n_levels, N = len(scores), scores[0].shape[0]
+    sc = [_f32c(t) for t in scores]
+    fu = [_f32c(t) for t in fused]
+    an = [_f32c(t) for t in level_anchors]
+    arr = lambda ts: (ctypes.c_void_p * n_levels)(*[t.data_ptr() for t in ts])
+    ns = (ctypes.c_int * n_levels)(*[int(t.shape[1]) for t in sc])
+    kk = (ctypes.c_int * n_levels)(*[int(k) for k in ks])
+    rc = L.mmt_rpn_topk_gather_f32(arr(sc), arr(fu), arr(an), ns, kk, n_levels, N, int(num_anchors), int(fu[0].shape[-1]),
+                                   int(sum(ks)), _p(deltas_out), _p(anchors_out), _p(scores_out), _stream())
+    if rc == 4:
+        return False
+    check(rc, "rpn_topk_gather")
+    return True
+
+
 def nms(dets, scores, iou_threshold):
     """`_C.nms(dets, scores, thr)` (reference csrc/nms.h:10-28): int64 kept indices, ascending.
     Empty input returns an empty int64 CPU tensor exactly like the reference (nms.h:17-18)."""

@@ -40,6 +40,8 @@ _PROTOS = {
     "mmt_nms_segmented_f32": (c_int, [P, P, POINTER(c_int), c_int, c_float, P, P, P, c_size_t, P]),
     "mmt_nms_segmented_flags_f32": (c_int, [P, P, POINTER(c_int), c_int, c_float, P, P, P, P, c_size_t, P]),
     "mmt_rpn_gather_f32": (c_int, [P, c_int, c_int, c_int64, P, P, P, c_int, c_int, c_int, c_int, P, P, P, P]),
+    "mmt_rpn_topk_gather_f32": (c_int, [POINTER(P), POINTER(P), POINTER(P), POINTER(c_int), POINTER(c_int), c_int, c_int, c_int,
+                                        c_int, c_int, P, P, P, P]),
     "mmt_nms_f32": (c_int, [P, P, c_int, c_float, P, P, P, c_size_t, P]),
     "mmt_decode_clip_boxes_f32": (c_int, [P, P, P, P, c_int, c_int, c_float, c_float, c_float, c_float, c_float,
                                           c_float, P, P, P, P]),

@@ -151,11 +151,17 @@ class FPN(nn.Module):
         self.top_blocks = top_blocks
 
     def forward(self, x):
-        last_inner = getattr(self, self.inner_blocks[-1])(x[-1])
-        results = [getattr(self, self.layer_blocks[-1])(last_inner)]
-        for feat, inner, layer in zip(x[:-1][::-1], self.inner_blocks[:-1][::-1], self.layer_blocks[:-1][::-1]):
-            last_inner = Fk.upsample_add(getattr(self, inner)(feat), last_inner)
-            results.insert(0, getattr(self, layer)(last_inner))
+        """Reference fpn.py:43-69.  The four lateral 1x1 convs are independent of each other, and so are the four 3x3
+        output convs once the top-down sums exist: each group is issued on parallel streams (utils/streams.py)."""
+        from ..utils.streams import run_parallel
+        dev = x[0].device
+        call = lambda name, t: (lambda: getattr(self, name)(t))
+        laterals = run_parallel([call(n, f) for n, f in zip(self.inner_blocks, x)], dev)
+        inners = [None] * len(x)
+        inners[-1] = laterals[-1]
+        for i in range(len(x) - 2, -1, -1):
+            inners[i] = Fk.upsample_add(laterals[i], inners[i + 1])
+        results = list(run_parallel([call(n, t) for n, t in zip(self.layer_blocks, inners)], dev))
         if self.top_blocks is not None:
             results.extend(self.top_blocks(results[-1]))
         return tuple(results)

@@ -48,7 +48,9 @@ class MaskRCNNFPNAdaptor(nn.Module):
             self.add_module("adapter_%d" % i, m)
 
     def forward(self, feats):
-        return [getattr(self, "adapter_%d" % (i + 1))(feats[i]) for i in range(5)]
+        from ..utils.streams import run_parallel
+        level = lambda i: (lambda: getattr(self, "adapter_%d" % (i + 1))(feats[i]))
+        return run_parallel([level(i) for i in range(5)], feats[0].device)
 
 
 @registry.ROI_BOX_FEATURE_EXTRACTORS.register("FPN2MLPFeatureExtractor")

@@ -48,7 +48,9 @@ class RPNHead(nn.Module):
                        self.conv.weight.new_zeros((pad, 1, 1, self.conv.in_channels))], 0)
         b = torch.cat([self.cls_logits.bias, self.bbox_pred.bias, self.conv.bias.new_zeros(pad)], 0)
         from .. import functional as Fk
-        return [Fk.conv_bn_act(self.conv(feat, relu=True), w, None, b, None, False, 1, 0) for feat in x]
+        from ..utils.streams import run_parallel
+        level = lambda feat: (lambda: Fk.conv_bn_act(self.conv(feat, relu=True), w, None, b, None, False, 1, 0))
+        return run_parallel([level(feat) for feat in x], x[0].device)   # the levels are independent: parallel streams
 
     @torch.no_grad()
     def proposal_scores(self, fused):
@@ -126,11 +128,13 @@ class RPNPostProcessor(nn.Module):
         deltas = torch.empty((N, K_, 4), dtype=torch.float32, device=device)
         anch = torch.empty((N, K_, 4), dtype=torch.float32, device=device)
         cand_scores = torch.empty((N, K_), dtype=torch.float32, device=device)
-        col = 0
-        for l, (s_l, k) in enumerate(zip(scores_l, sizes)):
-            vals, idx = s_l.topk(k, dim=1, sorted=True)
-            K.rpn_gather(fused[l], A_, idx, vals, anchors[0][l].bbox, deltas, anch, cand_scores, col)
-            col += k
+        level_anchors = [anchors[0][l].bbox for l in range(num_levels)]
+        if not (device.type == "cuda" and K.rpn_topk_gather(scores_l, fused, A_, level_anchors, sizes, deltas, anch, cand_scores)):
+            col = 0   # pre_nms_top_n beyond the fused kernel's capacity: torch's top-k + the gather kernel, per level
+            for l, (s_l, k) in enumerate(zip(scores_l, sizes)):
+                vals, idx = s_l.topk(k, dim=1, sorted=True)
+                K.rpn_gather(fused[l], A_, idx, vals, level_anchors[l], deltas, anch, cand_scores, col)
+                col += k
         flat_scores = cand_scores.reshape(-1)                 # image-major: row = j * K_ + (level offset + rank)
         boxes, scores_nms, valid = K.decode_clip_boxes(deltas.reshape(-1, 4), anch.reshape(-1, 4), self.box_coder.weights,
                                                        self.box_coder.bbox_xform_clip, image_wh, K_, flat_scores,

@@ -21,6 +21,7 @@ from mmt_psm_b200.engine import MTtrainer  # noqa: E402
 from mmt_psm_b200.modeling.backbone import BottleneckWithFixedBatchNorm  # noqa: E402
 from mmt_psm_b200.modeling.detector import build_detection_model  # noqa: E402
 from mmt_psm_b200.solver import make_lr_scheduler, make_optimizer  # noqa: E402
+from mmt_psm_b200.utils import streams  # noqa: E402
 from mmt_psm_b200.utils.synthetic_init import init_model  # noqa: E402
 
 ap = argparse.ArgumentParser()
@@ -54,6 +55,7 @@ KNOBS = {
     "cg1": dict(pdl=1, cg=1, fused=True),
     "unfused": dict(pdl=1, cg=0, fused=False),
     "nothread": dict(pdl=1, cg=0, fused=True, thread=False),
+    "nolevels": dict(pdl=1, cg=0, fused=True, levels=False),
 }
 it = [2000]
 
@@ -80,6 +82,7 @@ for visit in range(2):
         L.mmt_conv_force_cta_group(k["cg"])
         BottleneckWithFixedBatchNorm.fused_backward = k["fused"]
         trainer.teacher_thread = k.get("thread", True)
+        streams.set_enabled(k.get("levels", True))
         trainer.set_cuda_graphs(True)
         run(4)
         t = run(args.steps)

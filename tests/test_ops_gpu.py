@@ -519,6 +519,55 @@ def test_decode_clip_boxes_golden_and_oracle(cuda):
     assert 0 < ref_valid.sum() < ref_valid.size
 
 
+def test_rpn_topk_gather_matches_torch_topk(cuda):
+    """mmt_rpn_topk_gather_f32 == per level `scores.topk(k, dim=1, sorted=True)` (reference rpn/inference.py:92-94) +
+    the delta / anchor gathers: the selected SCORES are identical; the selected anchors are identical wherever scores are
+    unique, and among equal scores the lowest anchor indices are taken in ascending order (torch leaves ties unspecified).
+    Levels as at 800x800 (120000 .. 507 anchors), a row of all-equal scores, and a row with 5000 copies of the k-th value."""
+    kn = K()
+    gen = torch.Generator().manual_seed(44)
+    A, Cp, N = 3, 16, 2
+    hw = [200 * 200, 100 * 100, 50 * 50, 25 * 25, 13 * 13]
+    scores, fused, anchors = [], [], []
+    for l, p in enumerate(hw):
+        s_ = torch.sigmoid(torch.randn(N, p * A, generator=gen) * 3 - 3)
+        if l == 1:
+            s_[1] = 0.5                                   # every score equal: the first k anchor indices win
+        if l == 0:
+            v = float(s_[0].sort(descending=True)[0][1999])
+            pos = torch.randperm(p * A, generator=gen)[:5000]
+            s_[0][pos] = torch.where(s_[0][pos] < v, torch.full_like(s_[0][pos], v), s_[0][pos])   # 5000 ties at the cut
+        scores.append(s_.to(cuda))
+        fused.append(torch.randn(N, p, Cp, generator=gen).to(cuda))
+        anchors.append(torch.rand(p * A, 4, generator=gen).to(cuda))
+    ks = [min(2000, p * A) for p in hw]
+    K_ = sum(ks)
+    deltas = torch.full((N, K_, 4), float("nan"), device=cuda)
+    anch = torch.full((N, K_, 4), float("nan"), device=cuda)
+    out_s = torch.full((N, K_), float("nan"), device=cuda)
+    assert kn.rpn_topk_gather(scores, fused, A, anchors, ks, deltas, anch, out_s)
+    col = 0
+    for l, (p, k) in enumerate(zip(hw, ks)):
+        vals, idx = scores[l].topk(k, dim=1, sorted=True)
+        got_s = out_s[:, col:col + k]
+        assert torch.equal(got_s, vals), l
+        # recover the selected indices through the (unique) anchor rows
+        for n in range(N):
+            s_row = scores[l][n]
+            # reference selection with the documented tie rule: sort by (score desc, index asc)
+            key = (-s_row.double()).cpu().numpy()
+            ref_idx = torch.from_numpy(np.lexsort((np.arange(p * A), key))[:k].copy()).to(cuda)
+            assert torch.equal(anch[n, col:col + k], anchors[l][ref_idx]), (l, n)
+            pix, a = ref_idx // A, ref_idx % A
+            ref_d = torch.stack([fused[l][n, pix, A + 4 * a + c] for c in range(4)], 1)
+            assert torch.equal(deltas[n, col:col + k], ref_d), (l, n)
+        col += k
+    assert not torch.isnan(out_s).any() and not torch.isnan(deltas).any()
+    # capacity: k > 2048 is refused (the caller falls back to torch.topk + the gather kernel)
+    assert kn.rpn_topk_gather(scores[:1], fused[:1], A, anchors[:1], [3000], torch.empty(N, 3000, 4, device=cuda),
+                              torch.empty(N, 3000, 4, device=cuda), torch.empty(N, 3000, device=cuda)) is False
+
+
 # ------------------------------------------------------------------------------------ convs
 CONV_CASES = [
     # B, H, W, Cin, Cout, k, stride, pad

@@ -381,6 +381,8 @@ def run_ours(args):
     pk = peaks()
     if not args.no_roofline:             # every rank runs the two extra iterations (they all-reduce); rank 0 records
         trainer.set_cuda_graphs(False)   # the library's per-launch event bracketing needs eager launches (same kernels)
+        from mmt_psm_b200.utils import streams as _streams
+        _streams.set_enabled(False)      # ... one at a time: kernels overlapping on parallel streams would each be charged the other's time
         if rank == 0:
             lib.prof_enable(True)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -297,8 +297,8 @@ extern "C" int mmt_fpn_rois_f32(const float* boxes_xyxy, const int* image_counts
 // a uniformly random subset of min(#pos, quota_pos) positives (label >= 1) and min(#neg, batch - #pos_taken)
 // negatives (label == 0).  The reference draws torch.randperm(count)[:n] — which needs the counts on the host (a sync
 // per image) and ~30 launches.  Here: every candidate gets a counter-based random 32-bit key (hash of seed, image,
-// index); the n smallest keys of a class are its sample, found by a bitwise threshold search on the key value
-// (32 counting passes over the image's labels, one CTA per image), ties resolved by index.  Same distribution
+// index); the n smallest keys of a class are its sample, found by a radix select on the key value (4 passes of 8 bits
+// over a prefiltered key list in shared memory, one CTA per image), ties resolved by ticket.  Same distribution
 // (every subset of the required size is equally likely), no host round trip, one launch for the whole batch.
 namespace {
 
@@ -334,7 +334,7 @@ constexpr int kSampleCap = 8192;   // candidate keys held in shared memory durin
 // list; only if the prefilter caught too few / too many (probability ~0) does the search stream the whole image.
 __device__ unsigned int select_threshold(const float* __restrict__ labels, int n, int cls_pos, unsigned long long seed,
                                          unsigned int img, int want, int cls_size, int* s_part, int* s_bcast,
-                                         unsigned int* s_keys) {
+                                         unsigned int* s_keys, int* s_hist) {
   // a class that fits in the list is collected whole (T0 = max key); a larger one is prefiltered to ~4 x want keys
   const unsigned long long target = (unsigned long long)want * 4ull + 64ull;
   const bool whole = cls_size <= kSampleCap;
@@ -361,24 +361,43 @@ __device__ unsigned int select_threshold(const float* __restrict__ labels, int n
     __syncthreads();
   }
   const bool use_list = prefilter && m >= want && m <= kSampleCap;
-  unsigned int T = 0u;
-  for (int bit = 31; bit >= 0; --bit) {
-    const unsigned int trial = T | ((1u << bit) - 1u);   // all keys <= trial have the decided prefix and this bit 0
-    int c = 0;
+  // T = the want-th smallest key: MSB-first radix select, 4 passes of 8 bits with a 256-bin shared-memory histogram
+  // (uniform keys: no bin is hot) — 4 block-wide steps instead of the 32 of a bit-by-bit search
+  unsigned int prefix = 0u;
+  int need = want;
+  for (int pass = 0; pass < 4; ++pass) {
+    const int shift = 24 - 8 * pass;
+    const unsigned int hi_mask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_hist[i] = 0;
+    __syncthreads();
     if (use_list) {
-      for (int i = threadIdx.x; i < m; i += blockDim.x) c += (s_keys[i] <= trial);
+      for (int i = threadIdx.x; i < m; i += blockDim.x) {
+        const unsigned int k = s_keys[i];
+        if ((k & hi_mask) == prefix) atomicAdd(&s_hist[(k >> shift) & 255u], 1);
+      }
     } else {
       for (int i = threadIdx.x; i < n; i += blockDim.x) {
         const float l = labels[i];
         const bool in_cls = cls_pos ? (l >= 1.f) : (l == 0.f);
-        if (in_cls && hash_key(seed, img, (unsigned int)i) <= trial) ++c;
+        if (in_cls) {
+          const unsigned int k = hash_key(seed, img, (unsigned int)i);
+          if ((k & hi_mask) == prefix) atomicAdd(&s_hist[(k >> shift) & 255u], 1);
+        }
       }
     }
-    c = block_count(c, s_part);
     __syncthreads();
-    if (c < want) T |= (1u << bit);
+    if (threadIdx.x == 0) {
+      int d = 0, below = 0;
+      while (d < 255 && below + s_hist[d] < need) { below += s_hist[d]; ++d; }
+      *s_bcast = d;
+      s_part[0] = need - below;
+    }
+    __syncthreads();
+    prefix |= (unsigned int)(*s_bcast) << shift;
+    need = s_part[0];
+    __syncthreads();
   }
-  return T;
+  return prefix;
 }
 
 __global__ void __launch_bounds__(1024) balanced_sample_kernel(const float* __restrict__ labels,
@@ -389,6 +408,7 @@ __global__ void __launch_bounds__(1024) balanced_sample_kernel(const float* __re
   __shared__ int s_part[32];
   __shared__ int s_bcast;
   __shared__ unsigned int s_keys[kSampleCap];
+  __shared__ int s_hist[256];
   const unsigned int img = blockIdx.x;
   const int base = offsets[img], n = offsets[img + 1] - base;
   const float* lab = labels + base;
@@ -413,8 +433,8 @@ __global__ void __launch_bounds__(1024) balanced_sample_kernel(const float* __re
   const int num_neg = min(cn, batch_per_image - num_pos);
   const bool all_pos = num_pos == cp, all_neg = num_neg == cn;
   unsigned int tp = 0xffffffffu, tn = 0xffffffffu;
-  if (!all_pos && num_pos > 0) tp = select_threshold(lab, n, 1, seed, img, num_pos, cp, s_part, &s_bcast, s_keys);
-  if (!all_neg && num_neg > 0) tn = select_threshold(lab, n, 0, seed, img, num_neg, cn, s_part, &s_bcast, s_keys);
+  if (!all_pos && num_pos > 0) tp = select_threshold(lab, n, 1, seed, img, num_pos, cp, s_part, &s_bcast, s_keys, s_hist);
+  if (!all_neg && num_neg > 0) tn = select_threshold(lab, n, 0, seed, img, num_neg, cn, s_part, &s_bcast, s_keys, s_hist);
   // keys strictly below the threshold are in; the keys equal to it (the threshold element itself, plus ties — a 2^-32
   // event per pair) are admitted by ticket until the quota is met
   __shared__ int s_tie_p, s_tie_n;

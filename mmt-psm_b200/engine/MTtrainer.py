@@ -99,8 +99,8 @@ class MTtrainer(object):
         # Only with CUDA graphs on (the production / bench configuration); parity tests run the passes in order.
         self.teacher_thread = os.environ.get("MMT_TEACHER_THREAD", "1") == "1"
         self._t_stream, self._t_pool = None, None
-        self._copy_stream, self._staged = None, None
-        self.pool_gb = tuple(float(v) for v in os.environ.get("MMT_POOL_GB", "6,4").split(","))   # main stream, teacher stream
+        self._copy_stream, self._staged, self._pregrow_copy = None, None, False
+        self.pool_gb = tuple(float(v) for v in os.environ.get("MMT_POOL_GB", "6,4,0.5").split(","))   # main, teacher, copy stream
         self._pregrown_for, self._pregrow_teacher = 0, False
         self.loss_keys = ["loss_classifier", "loss_box_reg", "loss_seg", "loss_objectness", "loss_rpn_box_reg"]
         if cfg.MODEL.RELATION_NMS.USE_RELATION_NMS:
@@ -159,6 +159,7 @@ class MTtrainer(object):
             return
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(device=self.device)
+            self._pregrow_copy = True
         order = []
         if data_s is not None:
             order.append(data_s.tensors if hasattr(data_s, "tensors") else data_s)
@@ -167,6 +168,9 @@ class MTtrainer(object):
             order += views[len(views) - self.student_bs:] + views[:len(views) - self.student_bs]
         staged = {}
         with torch.cuda.stream(self._copy_stream):
+            if self._pregrow_copy:      # the copy stream has its own allocator pool: two generations of staged batches
+                self._pregrow_copy = False
+                self._pregrow_pool(self.pool_gb[2] if len(self.pool_gb) > 2 else 0.5, small_blocks=0)
             for t in order:
                 if isinstance(t, torch.Tensor) and not t.is_cuda and id(t) not in staged:
                     staged[id(t)] = (t, t.to(self.device, non_blocking=True))
@@ -260,6 +264,7 @@ class MTtrainer(object):
                 gc.freeze()
             self._pregrow_pool(self.pool_gb[0])
             self._pregrow_teacher = True
+            self._pregrow_copy = self._copy_stream is not None
         reduced = False
         mt_on = iteration > self.start_mt and self.lambda_value > 0 and bool(self.cfg.DATASETS.NO_LABEL)
         stacked = False

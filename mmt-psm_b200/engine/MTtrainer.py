@@ -98,6 +98,9 @@ class MTtrainer(object):
         # them (profiles/r02_profile_step_d.md).  On two threads / two streams one pass enqueues while the other waits.
         # Only with CUDA graphs on (the production / bench configuration); parity tests run the passes in order.
         self.teacher_thread = os.environ.get("MMT_TEACHER_THREAD", "1") == "1"
+        self.teacher_first = os.environ.get("MMT_TEACHER_FIRST", "1") == "1"
+        if self.teacher_first:
+            self.teacher.side_priority = -1
         self._t_stream, self._t_pool = None, None
         self._copy_stream, self._staged, self._pregrow_copy = None, None, False
         self.pool_gb = tuple(float(v) for v in os.environ.get("MMT_POOL_GB", "6,4,0.5").split(","))   # main, teacher, copy stream
@@ -209,7 +212,7 @@ class MTtrainer(object):
         stream had enqueued when the job was submitted: the previous iteration's SGD + EMA, this iteration's uploads)."""
         torch.cuda.set_device(self.device)
         if self._t_stream is None:
-            self._t_stream = torch.cuda.Stream(device=self.device)
+            self._t_stream = torch.cuda.Stream(device=self.device, priority=-1 if self.teacher_first else 0)
         self._t_stream.wait_stream(main_stream)
         with torch.cuda.stream(self._t_stream):
             if self._pregrow_teacher:
@@ -279,17 +282,30 @@ class MTtrainer(object):
                 # engine is still bringing in the teacher's views
                 data_u_list = list(data_u_list)
                 n_u = len(data_u_list)
-                for i in range(n_u - self.student_bs, n_u):
-                    data_u_list[i] = self._take(data_u_list[i])
-                stacked = self.student.prefetch_student(img_s, data_u_list[-self.student_bs:])
-                if not stacked:
-                    self.student.prefetch_trunk("sup", img_s)
-                for i in range(n_u - self.student_bs):
-                    data_u_list[i] = self._take(data_u_list[i])
-                with torch.no_grad():
-                    self.teacher.prefetch_trunk("aug", data_u_list[:self.teacher_bs])
-                if not stacked:
-                    self.student.prefetch_trunk("unl", data_u_list[-self.student_bs:])
+                if self.teacher_first:
+                    # The teacher's trunk ([2K*B] views, the larger one) heads the iteration's critical path — teacher trunk
+                    # -> teacher heads (read-backs) -> student heads on the teacher's ROIs -> trunk backward — while the
+                    # supervised pass has slack until the two join: enqueue it first, on a high-priority stream.
+                    for i in range(n_u):
+                        data_u_list[i] = self._take(data_u_list[i])
+                    with torch.no_grad():
+                        self.teacher.prefetch_trunk("aug", data_u_list[:self.teacher_bs])
+                    stacked = self.student.prefetch_student(img_s, data_u_list[-self.student_bs:])
+                    if not stacked:
+                        self.student.prefetch_trunk("sup", img_s)
+                        self.student.prefetch_trunk("unl", data_u_list[-self.student_bs:])
+                else:
+                    for i in range(n_u - self.student_bs, n_u):
+                        data_u_list[i] = self._take(data_u_list[i])
+                    stacked = self.student.prefetch_student(img_s, data_u_list[-self.student_bs:])
+                    if not stacked:
+                        self.student.prefetch_trunk("sup", img_s)
+                    for i in range(n_u - self.student_bs):
+                        data_u_list[i] = self._take(data_u_list[i])
+                    with torch.no_grad():
+                        self.teacher.prefetch_trunk("aug", data_u_list[:self.teacher_bs])
+                    if not stacked:
+                        self.student.prefetch_trunk("unl", data_u_list[-self.student_bs:])
             else:
                 self.student.prefetch_trunk("sup", img_s)
         self.scheduler.step()

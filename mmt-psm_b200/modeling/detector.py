@@ -73,6 +73,7 @@ class GeneralizedRCNN(nn.Module):
         self.hint_adaptor = MaskRCNNFPNAdaptor(cfg)
         self._graphs, self._graphs_on, self._graph_on_backward = {}, False, None
         self._pending, self._side = {}, None
+        self.side_priority = 0     # CUDA priority of the trunk-prefetch stream (-1 = high; the trainer raises the teacher's)
         self._stu, self._stu_ptrs, self._deferred = None, {}, []
 
     # ------------------------------------------------------------------------------ CUDA graphs
@@ -163,7 +164,7 @@ class GeneralizedRCNN(nn.Module):
             return  # captured just now (with warm-up runs); the regular call replays it
         cur = torch.cuda.current_stream(x.device)
         if self._side is None:
-            self._side = torch.cuda.Stream(device=x.device)
+            self._side = torch.cuda.Stream(device=x.device, priority=self.side_priority)
         self._side.wait_stream(cur)
         g.launch_forward([x], self._side)
         self._pending[site] = (g, first.data_ptr(), tuple(x.shape), x)
@@ -180,7 +181,7 @@ class GeneralizedRCNN(nn.Module):
         g, _ = self._graph_for("stu", x, 1)
         cur = torch.cuda.current_stream(x.device)
         if self._side is None:
-            self._side = torch.cuda.Stream(device=x.device)
+            self._side = torch.cuda.Stream(device=x.device, priority=self.side_priority)
         self._side.wait_stream(cur)
         g.launch_forward([x], self._side)
         self._pending["stu"] = (g, images.data_ptr(), views[0].data_ptr(), x)

@@ -98,7 +98,8 @@ class MTtrainer(object):
         # them (profiles/r02_profile_step_d.md).  On two threads / two streams one pass enqueues while the other waits.
         # Only with CUDA graphs on (the production / bench configuration); parity tests run the passes in order.
         self.teacher_thread = os.environ.get("MMT_TEACHER_THREAD", "1") == "1"
-        self.teacher_first = os.environ.get("MMT_TEACHER_FIRST", "1") == "1"
+        # (measured: no effect on the step time, profiles/r02_ab_teacher_first.log — kept as a knob, off by default)
+        self.teacher_first = os.environ.get("MMT_TEACHER_FIRST", "0") == "1"
         if self.teacher_first:
             self.teacher.side_priority = -1
         self._t_stream, self._t_pool = None, None

@@ -56,7 +56,7 @@ KNOBS = {
     "unfused": dict(pdl=1, cg=0, fused=False),
     "nothread": dict(pdl=1, cg=0, fused=True, thread=False),
     "nolevels": dict(pdl=1, cg=0, fused=True, levels=False),
-    "studentfirst": dict(pdl=1, cg=0, fused=True, teacher_first=False),
+    "teacherfirst": dict(pdl=1, cg=0, fused=True, teacher_first=True),
 }
 it = [2000]
 
@@ -84,7 +84,7 @@ for visit in range(2):
         BottleneckWithFixedBatchNorm.fused_backward = k["fused"]
         trainer.teacher_thread = k.get("thread", True)
         streams.set_enabled(k.get("levels", True))
-        tf = k.get("teacher_first", True)
+        tf = k.get("teacher_first", False)
         trainer.teacher_first = tf
         teacher.side_priority = -1 if tf else 0
         teacher._side = None              # re-created with the configuration's priority

@@ -95,7 +95,7 @@ class MTtrainer(object):
         # Second host thread for the (no-grad, independent) teacher pass: the supervised pass and the teacher pass are each
         # a string of ~300 small launches separated by ~8 device read-backs (data-dependent ROI counts); run one after the
         # other the host sits in cudaStreamSynchronize ~10 ms per iteration with an empty device queue behind every one of
-        # them (profiles/r02_profile_step_d.md).  On two threads / two streams one pass enqueues while the other waits.
+        # them (profiles/r02_timeline.md).  On two threads / two streams one pass enqueues while the other waits.
         # Only with CUDA graphs on (the production / bench configuration); parity tests run the passes in order.
         self.teacher_thread = os.environ.get("MMT_TEACHER_THREAD", "1") == "1"
         # (measured: no effect on the step time, profiles/r02_ab_teacher_first.log — kept as a knob, off by default)

@@ -391,6 +391,10 @@ int mmt_conv_force_cta_group(int cta_group);
 /* Programmatic dependent launch of the tcgen05 kernels (default on): their prologue (barrier init, TMEM allocation,
  * descriptor prefetch) overlaps the tail of the previous kernel of the stream; 0 = plain stream serialisation. */
 int mmt_conv_set_pdl(int on);
+/* Operand pipeline of the tcgen05 fprop / dgrad kernel: `stages` caps the shared-memory ring depth (0 = as deep as shared
+ * memory allows: the default), `prefetch_kblocks` = how many 32-channel K blocks ahead of its loads the TMA producer issues
+ * L2 prefetches of the activation tiles (0 = off). */
+int mmt_conv_set_pipeline(int stages, int prefetch_kblocks);
 size_t mmt_conv_workspace_bytes(const mmt_conv_shape* shape);
 int mmt_conv_fprop_f32(const float* x_nhwc, const float* w_ohwi, const float* scale /*nullable*/,
                        const float* bias /*nullable*/, const float* residual_nhwc /*nullable*/,

@@ -75,6 +75,8 @@ struct FpropParams {
   int relu;
   int total_tiles;  // work units: (pixel tile, column tile) pairs; with CTA pairs a unit covers TWO consecutive pixel tiles
   int m_tiles;      // pixel tiles
+  int stages;       // ring slots actually used (<= the kernel's compile-time STAGES)
+  int prefetch;     // K blocks the producer runs its L2 prefetch ahead of its loads (0 = off)
   int sub_w;  // per-warp store box: 32 pixels = sub_w x (32 / sub_w) of the TW x TH patch
 };
 
@@ -212,14 +214,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t full_base = CG == 2 ? mapa_shared(L.full[0], 0) : L.full[0];
       int stage = 0;
       uint32_t phase = 0;
+      const int n_stage = p.stages;
       for (int t = unit0; t < p.total_tiles; t += n_units) {
         int nt, b, h0, w0;
         bool dup;
         locate(t, nt, b, h0, w0, dup);
+        // L2 prefetch runs `p.prefetch` K blocks ahead of the loads (the A operand streams from HBM once per tile and tap;
+        // the load that follows finds it in L2): prologue here, steady state inside the loop
+        const int taps_w = p.kw, cbs = p.cblocks;
+        auto prefetch_kb = [&](int q) {
+          const int cb = q % cbs, tap = q / cbs;
+          const int r = tap / taps_w, s2 = tap % taps_w;
+          tma_prefetch_4d(&tmA, cb * 32, w0 + s2 - p.pad_w, h0 + r - p.pad_h, b);
+        };
+        if (p.prefetch > 0)
+          for (int q = 0; q < min(p.prefetch, kblocks); ++q) prefetch_kb(q);
         int kb = 0;
         for (int r = 0; r < p.kh; ++r)
           for (int s = 0; s < p.kw; ++s)
             for (int cb = 0; cb < p.cblocks; ++cb, ++kb) {
+              if (p.prefetch > 0 && kb + p.prefetch < kblocks) prefetch_kb(kb + p.prefetch);
               mbar_wait(L.empty[stage], phase ^ 1u);
               if constexpr (CG == 2) {
                 const uint32_t full = full_base + 8u * (uint32_t)stage;
@@ -231,7 +245,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 tma_load_4d(L.a[stage], &tmA, L.full[stage], cb * 32, w0 + s - p.pad_w, h0 + r - p.pad_h, b);
                 tma_load_2d(L.b[stage], &tmB, L.full[stage], kb * 32, nt * BN);
               }
-              if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+              if (++stage == n_stage) { stage = 0; phase ^= 1u; }
             }
       }
     }
@@ -260,7 +274,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           if constexpr (CG == 2) mma_commit_cg2(L.empty[stage], 3);  // frees the stage in BOTH CTAs
           else mma_commit(L.empty[stage]);
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
         if constexpr (CG == 2) mma_commit_cg2(L.tfull[acc], 3);
         else mma_commit(L.tfull[acc]);
@@ -759,6 +773,8 @@ inline double gemm_bytes(const GemmProblem& g) {
 // Launch attributes of the tcgen05 kernels: the CTA pair (cluster of 2 = the two SMs of a TPC) and programmatic dependent
 // launch (the kernel's prologue overlaps the tail of the previous kernel of the stream; see tc_ptx.cuh pdl_wait).
 std::atomic<int> g_pdl{1};
+std::atomic<int> g_dbg_stages{0};   // experiments: cap the ring depth (0 = all the shared memory allows)
+std::atomic<int> g_prefetch{0};     // K blocks of L2 prefetch ahead of the loads
 void fill_launch(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, int grid, int threads, size_t smem, cudaStream_t stream,
                  int cluster) {
   cfg.gridDim = dim3((unsigned)grid);
@@ -810,6 +826,11 @@ int launch_gemm(const GemmProblem& g, cudaStream_t stream) {
   if (m_tiles * p.n_tiles > 0x7fffffffll) return mmt::fail(MMT_ERR_UNSUPPORTED, "conv: too many tiles");
   p.m_tiles = (int)m_tiles;
   p.total_tiles = (int)total;
+  {
+    const int dbg_stages = g_dbg_stages.load(std::memory_order_relaxed);
+    p.stages = dbg_stages > 0 ? std::min(dbg_stages, C::kStages) : C::kStages;
+    p.prefetch = g_prefetch.load(std::memory_order_relaxed);
+  }
   p.sub_w = sub_w;
   static bool attr_set = false;
   if (!attr_set) {
@@ -904,6 +925,14 @@ int launch_wgrad(const CUtensorMap& tmDY, const CUtensorMap& tmX, const CUtensor
 }
 
 }  // namespace
+
+extern "C" int mmt_conv_set_pipeline(int stages, int prefetch_kblocks) {
+  if (stages < 0 || stages > 8 || prefetch_kblocks < 0 || prefetch_kblocks > 64)
+    return mmt::fail(MMT_ERR_INVALID_ARGUMENT, "conv_set_pipeline: stages in [0, 8], prefetch in [0, 64]");
+  g_dbg_stages.store(stages);
+  g_prefetch.store(prefetch_kblocks);
+  return MMT_OK;
+}
 
 extern "C" int mmt_conv_set_pdl(int on) {
   g_pdl.store(on ? 1 : 0);

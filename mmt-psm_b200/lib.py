@@ -86,6 +86,7 @@ _PROTOS = {
     "mmt_conv_set_max_ctas": (c_int, [c_int]),
     "mmt_conv_force_cta_group": (c_int, [c_int]),
     "mmt_conv_set_pdl": (c_int, [c_int]),
+    "mmt_conv_set_pipeline": (c_int, [c_int, c_int]),
     "mmt_conv_dgrad_fused_f32": (c_int, [P, P, P, P, c_int, P, POINTER(ConvShape), P, c_size_t, P]),
     "mmt_conv_wgrad_scaled_f32": (c_int, [P, P, P, P, POINTER(ConvShape), c_int, P]),
     "mmt_conv_workspace_bytes": (c_size_t, [POINTER(ConvShape)]),
@@ -129,6 +130,8 @@ def lib():
         # experiment knobs of the conv engine (benchmarks / bisecting): MMT_CONV_PDL=0, MMT_CONV_CTA_GROUP=1|2
         if os.environ.get("MMT_CONV_PDL") in ("0", "1"):
             handle.mmt_conv_set_pdl(int(os.environ["MMT_CONV_PDL"]))
+        if os.environ.get("MMT_CONV_PREFETCH"):
+            handle.mmt_conv_set_pipeline(0, int(os.environ["MMT_CONV_PREFETCH"]))
         if os.environ.get("MMT_CONV_CTA_GROUP") in ("0", "1", "2"):
             handle.mmt_conv_force_cta_group(int(os.environ["MMT_CONV_CTA_GROUP"]))
     return _lib

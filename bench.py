@@ -284,15 +284,15 @@ def run_ours(args):
     e2e_warm = True
     stage_next = os.environ.get("MMT_BENCH_STAGE", "1") == "1"
 
-    def step(j, e2e):
+    def step(j, e2e, last=False):
         it = it_counter[0]
         it_counter[0] += 1
         if e2e:
             images, targets, views = pool[j % len(pool)]
             ld, total = trainer.train_step(it, images, fresh_targets(targets), views if mt else None)
-            if stage_next:                   # the NEXT step's H2D copies start now, under this step's compute (a data
+            if stage_next and not last:      # the NEXT step's H2D copies start now, under this step's compute (a data
                 nxt = pool[(j + 1) % len(pool)]        # loader's prefetch); they are still inside the timed region
-                trainer.stage(nxt[0], nxt[2] if mt else None)
+                trainer.stage(nxt[0], nxt[2] if mt else None, iteration=it + 1)
             return float(total)              # D2H of the step's loss (one fp32 scalar) = host sync
         images, targets, views = resident[j % len(resident)]
         ld, total = trainer.train_step(it, images, targets, views if mt else None)
@@ -326,7 +326,7 @@ def run_ours(args):
                 torch.cuda.synchronize()
                 a0 = alloc_counters()
             ts = time.perf_counter()
-            last = step(j, e2e)
+            last = step(j, e2e, last=(j == k - 1))
             marks[j + 1].record()             # no sync: per-step device time is read back after the region
             host_ms.append((time.perf_counter() - ts) * 1e3)
             if trace:

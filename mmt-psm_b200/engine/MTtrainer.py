@@ -103,7 +103,7 @@ class MTtrainer(object):
         if self.teacher_first:
             self.teacher.side_priority = -1
         self._t_stream, self._t_pool = None, None
-        self._copy_stream, self._staged, self._pregrow_copy = None, None, False
+        self._copy_stream, self._staged, self._pregrow_copy, self._prefetched = None, None, False, None
         self.pool_gb = tuple(float(v) for v in os.environ.get("MMT_POOL_GB", "6,4,0.5").split(","))   # main, teacher, copy stream
         self._pregrown_for, self._pregrow_teacher = 0, False
         self.loss_keys = ["loss_classifier", "loss_box_reg", "loss_seg", "loss_objectness", "loss_rpn_box_reg"]
@@ -152,7 +152,7 @@ class MTtrainer(object):
                 return None
 
     # ---- input staging ------------------------------------------------------------------------
-    def stage(self, data_s=None, data_u_list=None):
+    def stage(self, data_s=None, data_u_list=None, iteration=None):
         """Start the host -> device copies of the NEXT iteration's image tensors (pinned host memory) on a dedicated copy
         stream and return at once: called right after `train_step` has enqueued the current iteration, the uploads
         (61 MB per iteration on the bench workload: ~2.4 ms of PCIe time) run under that iteration's compute instead of in
@@ -181,12 +181,32 @@ class MTtrainer(object):
             done = torch.cuda.Event()
             done.record(self._copy_stream)
         self._staged = (staged, done)
+        # With the iteration number at hand the NEXT iteration's conv trunks are enqueued as well (they only need the
+        # staged inputs and this iteration's SGD + EMA, already in the main stream's queue): a caller that now blocks on this
+        # iteration's loss finds the device busy with them when it comes back, instead of idle until `train_step` has
+        # re-filled the queue.
+        if (iteration is not None and self.cuda_graphs and data_s is not None and data_u_list is not None
+                and self.n_step_unlabel == 1 and iteration > self.start_mt and self.lambda_value > 0
+                and bool(self.cfg.DATASETS.NO_LABEL) and getattr(self.student, "_graphs", None)
+                and getattr(self.teacher, "_graphs", None)):
+            views = list(data_u_list)
+            if all(isinstance(v, torch.Tensor) for v in views):
+                host_img = data_s.tensors if (hasattr(data_s, "tensors") and not isinstance(data_s, torch.Tensor)) else data_s
+                img_t = self._take(host_img)
+                dev_views = [self._take(v) for v in views]
+                self._prefetched = {id(host_img): img_t}
+                self._prefetched.update({id(h): d for h, d in zip(views, dev_views)})
+                if self.student.prefetch_student(img_t, dev_views[len(views) - self.student_bs:]):
+                    with torch.no_grad():
+                        self.teacher.prefetch_trunk("aug", dev_views[:self.teacher_bs])
 
     def _take(self, t):
         """The device copy of host tensor / ImageList `t`: the staged one if `stage` uploaded it, else a copy enqueued now."""
         if hasattr(t, "tensors") and not isinstance(t, torch.Tensor):
             from ..structures.image_list import ImageList
             return ImageList(self._take(t.tensors), t.image_sizes)
+        if self._prefetched and id(t) in self._prefetched:
+            return self._prefetched.pop(id(t))          # uploaded AND its trunk already enqueued by `stage`
         st = self._staged
         if st is not None and id(t) in st[0]:
             host, dev_t = st[0].pop(id(t))

@@ -35,6 +35,20 @@ class LinearParam(nn.Module):
         return Fk.linear(x, self.weight, self.bias, relu)
 
 
+def split_nonzero(masks):
+    """[mask.nonzero().squeeze(1) for mask in masks] with one `nonzero` over the concatenation (the only point where the host
+    waits for the device) and one read-back of the per-mask counts, which finds the queue already drained."""
+    if len(masks) == 1:
+        return [masks[0].nonzero().squeeze(1)]
+    sizes = [int(m.numel()) for m in masks]
+    idx = torch.cat(list(masks)).nonzero().squeeze(1)
+    starts = [0]
+    for n in sizes:
+        starts.append(starts[-1] + n)
+    cuts = torch.searchsorted(idx, torch.tensor(starts, dtype=idx.dtype, device=idx.device)).tolist()
+    return [idx[cuts[i]:cuts[i + 1]] - starts[i] for i in range(len(masks))]
+
+
 class MaskRCNNFPNAdaptor(nn.Module):
     """MGD 1x1 adaptors 256 -> 128 per level (reference roi_box_feature_extractors.py:45-75)."""
 
@@ -236,8 +250,9 @@ class FastRCNNLossComputation(object):
         for lab, reg, p in zip(labels, regression_targets, proposals):
             p.add_field("labels", lab)
             p.add_field("regression_targets", reg)
-        for i, (pi, ni) in enumerate(zip(pos, neg)):
-            proposals[i] = proposals[i][torch.nonzero(pi | ni).squeeze(1)]
+        # the sampled rows of every image with ONE device drain (the reference: a nonzero = a host sync per image)
+        for i, idx in enumerate(split_nonzero([pi | ni for pi, ni in zip(pos, neg)])):
+            proposals[i] = proposals[i][idx]
         self._proposals = proposals
         return proposals
 

@@ -152,6 +152,10 @@ class GeneralizedRCNN(nn.Module):
         of the next instead of serialising with it.  No-op without CUDA graphs."""
         if not self._graphs_on:
             return
+        head = tensors if site == "sup" else tensors[0]
+        pend = self._pending.get(site)
+        if pend is not None and pend[1] == head.data_ptr():
+            return      # already enqueued for exactly these tensors (MTtrainer.stage launched it ahead of the iteration)
         if site == "sup":
             x, n_views, first = tensors, 1, tensors
         else:
@@ -177,6 +181,9 @@ class GeneralizedRCNN(nn.Module):
         if not (self._graphs_on and self.training and images.is_cuda and len(views) == 1
                 and tuple(views[0].shape) == tuple(images.shape)):
             return False
+        pend = self._pending.get("stu")
+        if pend is not None and pend[1] == images.data_ptr() and pend[2] == views[0].data_ptr():
+            return True   # already enqueued for exactly these tensors (MTtrainer.stage launched it ahead of the iteration)
         x = torch.cat([images, views[0]], 0)
         g, _ = self._graph_for("stu", x, 1)
         cur = torch.cuda.current_stream(x.device)

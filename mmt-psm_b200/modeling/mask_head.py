@@ -24,11 +24,9 @@ from .utils import cat
 
 def keep_only_positive_boxes(boxes):
     assert isinstance(boxes, (list, tuple)) and isinstance(boxes[0], BoxList)
-    positive_boxes, positive_inds = [], []
-    for b in boxes:
-        mask = b.get_field("labels") > 0
-        positive_boxes.append(b[mask.nonzero().squeeze(1)])
-        positive_inds.append(mask)
+    from .box_head import split_nonzero
+    positive_inds = [b.get_field("labels") > 0 for b in boxes]
+    positive_boxes = [b[idx] for b, idx in zip(boxes, split_nonzero(positive_inds))]   # one device drain for the batch
     return positive_boxes, positive_inds
 
 

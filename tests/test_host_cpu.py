@@ -330,3 +330,17 @@ def test_run_logger_contract(tmp_path, capsys):
     quiet = setup_logger("mmt_test_rank1", str(tmp_path / "r1"), 1)
     quiet.info("nothing")
     assert not (tmp_path / "r1").exists()
+
+
+def test_split_nonzero_equals_per_mask_nonzero():
+    """modeling.box_head.split_nonzero: one `nonzero` over the concatenated masks == a `nonzero` per mask (what the reference
+    runs, one host sync per image: box_head/loss.py:107-111, mask_head/mask_head.py:24-31)."""
+    import torch
+    import mmt_psm_b200  # noqa: F401
+    from mmt_psm_b200.modeling.box_head import split_nonzero
+    g = torch.Generator().manual_seed(0)
+    masks = [torch.rand(n, generator=g) > 0.7 for n in (17, 1, 40, 0, 5, 512)]
+    out = split_nonzero(masks)
+    assert all(torch.equal(o, m.nonzero().squeeze(1)) for o, m in zip(out, masks))
+    assert torch.equal(split_nonzero(masks[:1])[0], masks[0].nonzero().squeeze(1))
+    assert [len(o) for o in split_nonzero([torch.zeros(4, dtype=torch.bool)] * 2)] == [0, 0]

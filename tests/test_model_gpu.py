@@ -315,3 +315,38 @@ def test_teacher_thread_matches_sequential(cuda, restore):
     for a, b in zip(l0[1:], l1[1:]):          # later iterations: 1e-7 weight differences may flip a discrete decision
         for k in a:
             assert abs(a[k] - b[k]) <= 2e-2 * max(abs(a[k]), 1e-2), (k, a[k], b[k])
+
+
+def test_staged_inputs_and_prefetched_trunks_match_plain_steps(cuda, restore):
+    """`MTtrainer.stage(next batch, iteration)` — uploads on the copy stream and the next iteration's conv trunks enqueued
+    ahead of `train_step` — changes when work is enqueued, not what is computed: three iterations from pinned host batches
+    with staging give the losses of three plain iterations on the same data."""
+    from mmt_psm_b200.engine import MTtrainer
+    from mmt_psm_b200.modeling.balanced_positive_negative_sampler import BalancedPositiveNegativeSampler
+    from mmt_psm_b200.solver import make_lr_scheduler, make_optimizer
+    results = []
+    for staged in (False, True):
+        cfg, student, teacher, sd, images, targets, views, g = _build(cuda)
+        BalancedPositiveNegativeSampler.rng_device = None
+        for m, (o1, o2) in ((student, (1, 2)), (teacher, (3, 4))):
+            m.rpn.loss_evaluator.fg_bg_sampler._calls = m.box_heads.box.loss_evaluator.fg_bg_sampler._calls = 0
+            m.rpn.loss_evaluator.fg_bg_sampler._ordinal, m.box_heads.box.loss_evaluator.fg_bg_sampler._ordinal = o1, o2
+        opt = make_optimizer(cfg, student, teacher)
+        trainer = MTtrainer(student, teacher, None, opt, make_lr_scheduler(cfg, opt), None, None, 10 ** 9, cfg, cuda_graphs=True)
+        torch.manual_seed(7)
+        himg, hviews = images.pin_memory(), [v.pin_memory() for v in views]
+        losses = []
+        for it in (5, 6, 7):
+            ld, total = trainer.train_step(it, himg, targets, hviews)
+            if staged and it < 7:
+                trainer.stage(himg, hviews, iteration=it + 1)
+                if it == 6:
+                    assert "stu" in student._pending and "aug" in teacher._pending     # next trunks already in flight
+            losses.append({k: float(v) for k, v in ld.items()})
+        results.append(losses)
+    for a, b in zip(results[0][:1], results[1][:1]):
+        for k in a:
+            assert abs(a[k] - b[k]) <= 1e-5 * max(abs(a[k]), 1e-2), (k, a[k], b[k])
+    for a, b in zip(results[0][1:], results[1][1:]):
+        for k in a:
+            assert abs(a[k] - b[k]) <= 2e-2 * max(abs(a[k]), 1e-2), (k, a[k], b[k])

@@ -282,7 +282,8 @@ def run_ours(args):
 
     it_counter = [2000]
     e2e_warm = True
-    stage_next = os.environ.get("MMT_BENCH_STAGE", "1") == "1"
+    stage_next = os.environ.get("MMT_BENCH_STAGE", "1") != "0"      # "2": uploads only, trunks not enqueued ahead
+    stage_trunks = os.environ.get("MMT_BENCH_STAGE", "1") == "1"
 
     def step(j, e2e, last=False):
         it = it_counter[0]
@@ -292,7 +293,7 @@ def run_ours(args):
             ld, total = trainer.train_step(it, images, fresh_targets(targets), views if mt else None)
             if stage_next and not last:      # the NEXT step's H2D copies start now, under this step's compute (a data
                 nxt = pool[(j + 1) % len(pool)]        # loader's prefetch); they are still inside the timed region
-                trainer.stage(nxt[0], nxt[2] if mt else None, iteration=it + 1)
+                trainer.stage(nxt[0], nxt[2] if mt else None, iteration=(it + 1) if stage_trunks else None)
             return float(total)              # D2H of the step's loss (one fp32 scalar) = host sync
         images, targets, views = resident[j % len(resident)]
         ld, total = trainer.train_step(it, images, targets, views if mt else None)

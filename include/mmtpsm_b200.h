@@ -5,6 +5,12 @@
  * path.  Every entry point takes raw DEVICE pointers, sizes and a CUDA stream (passed as void*,
  * i.e. a cudaStream_t), returns an int status (0 = ok) and never allocates, frees or synchronises:
  * the caller owns every output and workspace buffer.  No torch types appear in this file.
+ * The ONLY host-memory arguments are the small tables whose parameter names end in `_host` (segment offsets, per-level
+ * pointer / size tables): they are read during the call and become kernel arguments.
+ *
+ * Process-wide state is limited to instrumentation and tuning knobs, none of which changes a result: the launch counter
+ * and the profiling switch below (bench.py only), and the conv engine's mmt_conv_set_max_ctas / mmt_conv_force_cta_group /
+ * mmt_conv_set_pdl / mmt_conv_set_pipeline.  Errors are reported through a thread-local string.
  *
  * Each block cites the reference interface it replaces (paths relative to the reference root).
  * The reference-side binding a maintainer adds is shown in INTEGRATION.md.

@@ -24,15 +24,15 @@ ncu)
 full)
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:conv_tc_kernel -s 600 -c 6 -f -o $OUT/prof_conv \
       python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-roofline --no-graphs > $OUT/ncu_full_conv.log 2>&1
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:"roi_align_fpn|sgd_ema|mgd_level|psm_kernel|wgrad_tc" -s 30 -c 10 -f -o $OUT/prof_bw \
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:"roi_align_fpn|sgd_ema|mgd_level|psm_kernel|rpn_topk|balanced_sample|greedy_scan" -s 8 -c 14 -f -o $OUT/prof_bw \
       python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-roofline --no-graphs > $OUT/ncu_full_bw.log 2>&1
   ;;
 sanitize)
   timeout 1200 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_ops_gpu.py -m gpu -q -x \
-      -k "nms or roi_align or psm or mgd or conv_fprop or cta_pair or fused_backward_ops or rasterize or paste" > $OUT/sanitizer_memcheck.log 2>&1
+      -k "nms or roi_align or psm or mgd or conv_fprop or cta_pair or fused_backward_ops or rasterize or paste or topk or balanced_sample or padded_heads" > $OUT/sanitizer_memcheck.log 2>&1
   echo "memcheck exit code $?" >> $OUT/sanitizer_memcheck.log
   timeout 1200 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_ops_gpu.py -m gpu -q -x \
-      -k "nms_golden or roi_align_forward_golden or roi_align_fpn or psm or mgd or sigmoid_focal" > $OUT/sanitizer_racecheck.log 2>&1
+      -k "nms_golden or roi_align_forward_golden or roi_align_fpn or psm or mgd or sigmoid_focal or topk or balanced_sample" > $OUT/sanitizer_racecheck.log 2>&1
   echo "racecheck exit code $?" >> $OUT/sanitizer_racecheck.log
   ;;
 esac; done

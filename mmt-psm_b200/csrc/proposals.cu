@@ -334,7 +334,7 @@ constexpr int kSampleCap = 8192;   // candidate keys held in shared memory durin
 // list; only if the prefilter caught too few / too many (probability ~0) does the search stream the whole image.
 __device__ unsigned int select_threshold(const float* __restrict__ labels, int n, int cls_pos, unsigned long long seed,
                                          unsigned int img, int want, int cls_size, int* s_part, int* s_bcast,
-                                         unsigned int* s_keys, int* s_hist) {
+                                         unsigned int* s_keys, int* s_hist, int* need_at_threshold) {
   // a class that fits in the list is collected whole (T0 = max key); a larger one is prefiltered to ~4 x want keys
   const unsigned long long target = (unsigned long long)want * 4ull + 64ull;
   const bool whole = cls_size <= kSampleCap;
@@ -345,13 +345,26 @@ __device__ unsigned int select_threshold(const float* __restrict__ labels, int n
     if (!whole) T0 = (unsigned int)((target << 32) / (unsigned long long)cls_size);
     if (threadIdx.x == 0) *s_bcast = 0;
     __syncthreads();
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-      const float l = labels[i];
-      const bool in_cls = cls_pos ? (l >= 1.f) : (l == 0.f);
-      if (in_cls) {
-        const unsigned int k = hash_key(seed, img, (unsigned int)i);
-        if (k <= T0) {
-          const int slot = atomicAdd(s_bcast, 1);
+    const int lane = threadIdx.x & 31;
+    for (int base0 = 0; base0 < n; base0 += blockDim.x) {      // uniform trip count: the ballots below need whole warps
+      const int i = base0 + threadIdx.x;
+      bool hit = false;
+      unsigned int k = 0u;
+      if (i < n) {
+        const float l = labels[i];
+        if (cls_pos ? (l >= 1.f) : (l == 0.f)) {
+          k = hash_key(seed, img, (unsigned int)i);
+          hit = k <= T0;
+        }
+      }
+      const unsigned int mask = __ballot_sync(0xffffffffu, hit);   // one slot reservation per warp, not per candidate
+      if (mask) {
+        const int leader = __ffs(mask) - 1;
+        int slot0 = 0;
+        if (lane == leader) slot0 = atomicAdd(s_bcast, __popc(mask));
+        slot0 = __shfl_sync(0xffffffffu, slot0, leader);
+        if (hit) {
+          const int slot = slot0 + __popc(mask & ((1u << lane) - 1u));
           if (slot < kSampleCap) s_keys[slot] = k;
         }
       }
@@ -397,6 +410,7 @@ __device__ unsigned int select_threshold(const float* __restrict__ labels, int n
     need = s_part[0];
     __syncthreads();
   }
+  *need_at_threshold = need;   // how many of the keys EQUAL to the threshold are still wanted (the rest, want - need, lie below it)
   return prefix;
 }
 
@@ -433,24 +447,14 @@ __global__ void __launch_bounds__(1024) balanced_sample_kernel(const float* __re
   const int num_neg = min(cn, batch_per_image - num_pos);
   const bool all_pos = num_pos == cp, all_neg = num_neg == cn;
   unsigned int tp = 0xffffffffu, tn = 0xffffffffu;
-  if (!all_pos && num_pos > 0) tp = select_threshold(lab, n, 1, seed, img, num_pos, cp, s_part, &s_bcast, s_keys, s_hist);
-  if (!all_neg && num_neg > 0) tn = select_threshold(lab, n, 0, seed, img, num_neg, cn, s_part, &s_bcast, s_keys, s_hist);
-  // keys strictly below the threshold are in; the keys equal to it (the threshold element itself, plus ties — a 2^-32
-  // event per pair) are admitted by ticket until the quota is met
+  int need_p = 0, need_n = 0;
+  if (!all_pos && num_pos > 0) tp = select_threshold(lab, n, 1, seed, img, num_pos, cp, s_part, &s_bcast, s_keys, s_hist, &need_p);
+  if (!all_neg && num_neg > 0) tn = select_threshold(lab, n, 0, seed, img, num_neg, cn, s_part, &s_bcast, s_keys, s_hist, &need_n);
+  // keys strictly below the threshold are in; of the keys equal to it (the threshold element itself, plus ties — a 2^-32
+  // event per pair) the select wants need_p / need_n more: admitted by ticket
   __shared__ int s_tie_p, s_tie_n;
-  int below_p = 0, below_n = 0;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const float l = lab[i];
-    const unsigned int k = hash_key(seed, img, (unsigned int)i);
-    below_p += (l >= 1.f) && num_pos > 0 && (all_pos || k < tp);
-    below_n += (l == 0.f) && num_neg > 0 && (all_neg || k < tn);
-  }
-  below_p = block_count(below_p, s_part);
-  __syncthreads();
-  below_n = block_count(below_n, s_part);
   if (threadIdx.x == 0) { s_tie_p = 0; s_tie_n = 0; }
   __syncthreads();
-  const int need_p = num_pos - below_p, need_n = num_neg - below_n;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const float l = lab[i];
     const unsigned int k = hash_key(seed, img, (unsigned int)i);
@@ -581,9 +585,18 @@ __global__ void __launch_bounds__(kTopkThreads) rpn_topk_gather_kernel(TopkTab t
       __syncthreads();
       const uint32_t prefix = s_prefix;
       const uint32_t hi_mask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
-      for (int i = tid; i < n; i += kTopkThreads) {
-        const uint32_t key = ordered_key(__ldg(s + i));
-        if ((key & hi_mask) == prefix) atomicAdd(&hist[warp >> 1][(key >> shift) & 255u], 1);
+      // sigmoid scores share a handful of exponents, so in the first passes almost every element of a warp lands in the
+      // same few bins: the lanes with equal digits elect one of them to add their count (one shared-memory atomic per
+      // distinct digit per warp instead of 32 serialised ones on the same address)
+      for (int base = 0; base < n; base += kTopkThreads) {
+        const int i = base + tid;
+        uint32_t digit = 0x100u;                           // "not counted": its own match group
+        if (i < n) {
+          const uint32_t key = ordered_key(__ldg(s + i));
+          if ((key & hi_mask) == prefix) digit = (key >> shift) & 255u;
+        }
+        const unsigned peers = __match_any_sync(0xffffffffu, digit);
+        if (digit < 256u && lane == __ffs(peers) - 1) atomicAdd(&hist[warp >> 1][digit], __popc(peers));
       }
       __syncthreads();
       if (tid < 256) {

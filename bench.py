@@ -282,6 +282,7 @@ def run_ours(args):
 
     it_counter = [2000]
     e2e_warm = True
+    staged_targets = []
     stage_next = os.environ.get("MMT_BENCH_STAGE", "1") != "0"      # "2": uploads only, trunks not enqueued ahead
     stage_trunks = os.environ.get("MMT_BENCH_STAGE", "1") == "1"
 
@@ -290,10 +291,12 @@ def run_ours(args):
         it_counter[0] += 1
         if e2e:
             images, targets, views = pool[j % len(pool)]
-            ld, total = trainer.train_step(it, images, fresh_targets(targets), views if mt else None)
+            tg = staged_targets.pop() if staged_targets else fresh_targets(targets)
+            ld, total = trainer.train_step(it, images, tg, views if mt else None)
             if stage_next and not last:      # the NEXT step's H2D copies start now, under this step's compute (a data
                 nxt = pool[(j + 1) % len(pool)]        # loader's prefetch); they are still inside the timed region
-                trainer.stage(nxt[0], nxt[2] if mt else None, iteration=(it + 1) if stage_trunks else None)
+                staged_targets.append(trainer.stage(nxt[0], nxt[2] if mt else None, iteration=(it + 1) if stage_trunks else None,
+                                                    targets=fresh_targets(nxt[1])))
             return float(total)              # D2H of the step's loss (one fp32 scalar) = host sync
         images, targets, views = resident[j % len(resident)]
         ld, total = trainer.train_step(it, images, targets, views if mt else None)
@@ -318,7 +321,8 @@ def run_ours(args):
         t0 = time.perf_counter()
         marks[0].record()
         if e2e and stage_next:                # step 0's uploads: inside the timed region like every other step's
-            trainer.stage(pool[0][0], pool[0][2] if mt else None)
+            del staged_targets[:]
+            staged_targets.append(trainer.stage(pool[0][0], pool[0][2] if mt else None, targets=fresh_targets(pool[0][1])))
         last = None
         trace = os.environ.get("MMT_BENCH_TRACE") == "1"
         host_ms = []

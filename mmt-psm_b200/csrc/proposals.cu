@@ -585,18 +585,23 @@ __global__ void __launch_bounds__(kTopkThreads) rpn_topk_gather_kernel(TopkTab t
       __syncthreads();
       const uint32_t prefix = s_prefix;
       const uint32_t hi_mask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
-      // sigmoid scores share a handful of exponents, so in the first passes almost every element of a warp lands in the
-      // same few bins: the lanes with equal digits elect one of them to add their count (one shared-memory atomic per
-      // distinct digit per warp instead of 32 serialised ones on the same address)
+      // Pass 0 looks at the sign and the top 7 exponent bits: sigmoid scores share a handful of exponents, so almost every
+      // element of a warp lands in the same 3-4 bins — the lanes with equal digits elect one of them to add their count
+      // (__match_any_sync costs one step per DISTINCT value in the warp: cheap here, expensive in the later passes, whose
+      // digits are spread over all 256 bins and whose plain shared-memory atomics do not collide).
       for (int base = 0; base < n; base += kTopkThreads) {
         const int i = base + tid;
-        uint32_t digit = 0x100u;                           // "not counted": its own match group
+        uint32_t digit = 0x100u;                           // "not counted"
         if (i < n) {
           const uint32_t key = ordered_key(__ldg(s + i));
           if ((key & hi_mask) == prefix) digit = (key >> shift) & 255u;
         }
-        const unsigned peers = __match_any_sync(0xffffffffu, digit);
-        if (digit < 256u && lane == __ffs(peers) - 1) atomicAdd(&hist[warp >> 1][digit], __popc(peers));
+        if (pass == 0) {
+          const unsigned peers = __match_any_sync(0xffffffffu, digit);
+          if (digit < 256u && lane == __ffs(peers) - 1) atomicAdd(&hist[warp >> 1][digit], __popc(peers));
+        } else if (digit < 256u) {
+          atomicAdd(&hist[warp >> 1][digit], 1);
+        }
       }
       __syncthreads();
       if (tid < 256) {

@@ -152,7 +152,7 @@ class MTtrainer(object):
                 return None
 
     # ---- input staging ------------------------------------------------------------------------
-    def stage(self, data_s=None, data_u_list=None, iteration=None):
+    def stage(self, data_s=None, data_u_list=None, iteration=None, targets=None):
         """Start the host -> device copies of the NEXT iteration's image tensors (pinned host memory) on a dedicated copy
         stream and return at once: called right after `train_step` has enqueued the current iteration, the uploads
         (61 MB per iteration on the bench workload: ~2.4 ms of PCIe time) run under that iteration's compute instead of in
@@ -160,7 +160,15 @@ class MTtrainer(object):
         it is later handed; anything not staged is copied the usual way.  Upload order = use order: labeled batch, the
         student's unlabeled view, the teacher's views."""
         if self.device.type != "cuda":
-            return
+            return targets
+        dev_targets = None
+        if targets is not None:
+            # the next iteration's ground truth: boxes / labels uploaded and the polygons packed into their device arrays
+            # now, while the host would otherwise wait for this iteration's loss; hand the returned list to `train_step`
+            dev_targets = [t.to(self.device) for t in targets]
+            for t in dev_targets:
+                if t.has_field("masks") and hasattr(t.get_field("masks"), "packed"):
+                    t.get_field("masks").packed(self.device)
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(device=self.device)
             self._pregrow_copy = True
@@ -199,6 +207,7 @@ class MTtrainer(object):
                 if self.student.prefetch_student(img_t, dev_views[len(views) - self.student_bs:]):
                     with torch.no_grad():
                         self.teacher.prefetch_trunk("aug", dev_views[:self.teacher_bs])
+        return dev_targets
 
     def _take(self, t):
         """The device copy of host tensor / ImageList `t`: the staged one if `stage` uploaded it, else a copy enqueued now."""

@@ -11,10 +11,11 @@ from mmt_psm_b200 import kernels as kn
 
 dev = torch.device("cuda:0")
 A, Cp, N = 3, 16, 2
-hw = [200 * 200, 100 * 100, 50 * 50, 25 * 25, 13 * 13]
+side = [200, 100, 50, 25, 13]
+hw = [x * x for x in side]
 g = torch.Generator(device="cuda").manual_seed(1)
 scores = [torch.sigmoid(torch.randn(N, p * A, device=dev, generator=g) * 1.5 - 4.0) for p in hw]
-fused = [torch.randn(N, p, Cp, device=dev, generator=g) for p in hw]
+fused = [torch.randn(N, x, x, Cp, device=dev, generator=g) for x in side]
 anchors = [torch.rand(p * A, 4, device=dev, generator=g) for p in hw]
 ks = [min(2000, p * A) for p in hw]
 K_ = sum(ks)

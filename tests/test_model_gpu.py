@@ -336,10 +336,12 @@ def test_staged_inputs_and_prefetched_trunks_match_plain_steps(cuda, restore):
         torch.manual_seed(7)
         himg, hviews = images.pin_memory(), [v.pin_memory() for v in views]
         losses = []
+        tg = targets
         for it in (5, 6, 7):
-            ld, total = trainer.train_step(it, himg, targets, hviews)
+            ld, total = trainer.train_step(it, himg, tg, hviews)
             if staged and it < 7:
-                trainer.stage(himg, hviews, iteration=it + 1)
+                tg = trainer.stage(himg, hviews, iteration=it + 1, targets=targets)   # next targets uploaded / packed ahead
+                assert all(t.bbox.is_cuda for t in tg)
                 if it == 6:
                     assert "stu" in student._pending and "aug" in teacher._pending     # next trunks already in flight
             losses.append({k: float(v) for k, v in ld.items()})

@@ -430,6 +430,29 @@ def test_balanced_sample_counts_and_uniformity(cuda):
     assert abs(float(f.mean()) - exp) < 1e-6 and float((f - exp).abs().max()) < 4.5 * sigma, (float(f.min()), float(f.max()), exp, sigma)
 
 
+def test_balanced_sample_matches_restated_draw(cuda):
+    """The benchmarked sampler path, pinned draw for draw: `mmt_balanced_sample_f32` == oracle.ops_ref.balanced_sample_ref
+    (the same counter-based keys, the n smallest of each class) on RPN-sized (160 K anchors, prefiltered key list), box-head
+    sized (2 K proposals, whole class in shared memory), under-full and empty classes, for several seeds."""
+    kn = K()
+    gen = torch.Generator().manual_seed(10)
+    labs = [torch.where(torch.rand(159882, generator=gen) < 0.002, 1.0, 0.0),     # ~320 pos > quota, ~159 K neg
+            torch.where(torch.rand(2040, generator=gen) < 0.4, 2.0, 0.0),         # box head: 816 pos > 128, 1224 neg > 384
+            torch.tensor([1.0] * 5 + [0.0] * 20 + [-1.0] * 12),                   # fewer than either quota
+            torch.full((300,), -1.0)]                                            # nothing eligible
+    labs[0][torch.randperm(159882, generator=gen)[:4000]] = -1.0
+    sizes = [int(l.numel()) for l in labs]
+    offsets = np.concatenate([[0], np.cumsum(sizes)])
+    labels = torch.cat(labs)
+    offs = torch.tensor(offsets, dtype=torch.int32, device=cuda)
+    for seed, batch, quota in ((1234, 256, 128), (0x9E3779B97F4A7C15, 512, 128), (7, 512, 128)):
+        pos, neg = kn.balanced_sample(labels.to(cuda), offs, len(labs), batch, quota, seed=seed)
+        rp, rn, unique = R.balanced_sample_ref(labels.numpy(), offsets, batch, quota, seed)
+        assert unique          # no exactly-equal keys at a cut in these draws (a 2^-32 event per pair)
+        assert np.array_equal(pos.cpu().numpy(), rp), (seed, int(pos.sum()), int(rp.sum()))
+        assert np.array_equal(neg.cpu().numpy(), rn), (seed, int(neg.sum()), int(rn.sum()))
+
+
 # --------------------------------------------------------------------- encode / FPN ROI table
 def test_encode_boxes_and_fpn_rois_golden(cuda):
     kn = K()

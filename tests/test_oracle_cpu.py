@@ -330,3 +330,29 @@ def test_polygon_oracle_bit_exact_reference_mask_targets():
     bad = [i for i in range(len(which)) if not np.array_equal(got[i].astype(np.uint8), masks[i])]
     assert not bad, bad
     assert masks.any(axis=(1, 2)).mean() > 0.9 and 0.2 < masks.mean() < 0.9     # the fixture is not trivially empty / full
+
+
+def test_balanced_sample_restatement_properties():
+    """oracle.ops_ref.balanced_sample_ref (the restated draw the shipped device sampler is pinned to on the GPU): exact class
+    sizes of the reference's sampler (balanced_positive_negative_sampler.py:41-54), only eligible rows, per-image keys,
+    seed-dependent, and uniform over seeds."""
+    rng = np.random.default_rng(3)
+    lab = np.where(rng.random(4000) < 0.12, 1.0, 0.0).astype(np.float32)
+    lab[rng.integers(0, 4000, 300)] = -1.0
+    small = np.array([1.0] * 5 + [0.0] * 20 + [-1.0] * 12, dtype=np.float32)
+    labels = np.concatenate([lab, small, lab])
+    offs = [0, 4000, 4037, 8037]
+    p, n, unique = R.balanced_sample_ref(labels, offs, 512, 128, 42)
+    assert unique and not (p & (labels < 1)).any() and not (n & (labels != 0)).any()
+    for a, b in zip(offs[:-1], offs[1:]):
+        want_p = min(int((labels[a:b] >= 1).sum()), 128)
+        assert int(p[a:b].sum()) == want_p and int(n[a:b].sum()) == min(int((labels[a:b] == 0).sum()), 512 - want_p)
+    assert not np.array_equal(p[:4000], p[4037:])                      # same labels, different image index: different draw
+    p2, _, _ = R.balanced_sample_ref(labels, offs, 512, 128, 43)
+    assert not np.array_equal(p, p2)
+    hits = np.zeros(4000)
+    for s in range(300):
+        hits += R.balanced_sample_ref(lab, [0, 4000], 512, 128, 1000 + s)[0]
+    f = hits[lab >= 1] / 300.0
+    exp = 128.0 / float((lab >= 1).sum())
+    assert abs(f.mean() - exp) < 1e-9 and np.abs(f - exp).max() < 4.5 * (exp * (1 - exp) / 300.0) ** 0.5

@@ -355,6 +355,13 @@ class GeneralizedRCNN(nn.Module):
             raise NotImplementedError("forward_teacher with ground-truth targets (PLTRAIN) is out of scope")
         images = [to_image_list(im) for im in images]
         view0 = ImageList(images[0].tensors, images[0].image_sizes)  # un-flipped handle on colour view 0
+        self.rpn.candidate_sharing(True)     # the coarse inference and the proposal pass post-process the same RPN output
+        try:
+            return self._forward_teacher(images, view0)
+        finally:
+            self.rpn.candidate_sharing(False)
+
+    def _forward_teacher(self, images, view0):
         aug_features = self.extract_aug_feat(images)
         # coarse inference on view 0 (eval-mode heads) re-using its backbone features
         self.set_module_mode("test")

@@ -87,6 +87,66 @@ class RPNPostProcessor(nn.Module):
             out.append(cat_boxlist((p, gt)))
         return out
 
+    def _candidates(self, anchors, scores_l, fused, A_, sizes, image_shapes, device):
+        """Per (image, level) the `sizes[l]` best-scoring anchors decoded to boxes, their scores, and the keep flags of the
+        per-(image, level) NMS (min-size filter folded in): (boxes [N*K_, 4], flat_scores [N*K_], flags [N*K_]).
+
+        `self.shared` (set by RPNModule to one dict for its train- and test-mode selectors): the teacher post-processes the
+        SAME head output twice — with the test-mode numbers for its coarse inference, then with the train-mode numbers for
+        the proposals the student is trained on (reference generalized_rcnn.py:127-139).  The candidates of a level are
+        sorted by score and greedy NMS decides every box from the higher-scored ones only, so the smaller selection's boxes,
+        scores and keep flags are exactly the leading rows of the larger one's: the first call computes the larger set,
+        the second reads its answer out of it — one top-k, one decode and one NMS chain per teacher pass instead of two."""
+        N, num_levels = scores_l[0].shape[0], len(scores_l)
+        shared = getattr(self, "shared", None)
+        if shared is not None and not shared.get("active"):
+            shared = None     # sharing is scoped to ONE teacher pass (RPNModule.candidate_sharing): the head maps of a CUDA-graph
+                              # trunk keep their addresses from one iteration to the next, so a key alone cannot tell passes apart
+        key = tuple(t.data_ptr() for t in scores_l) + (N,)
+        if shared is not None and shared.get("key") == key:
+            big = shared["sizes"]
+            if all(a <= b for a, b in zip(sizes, big)):
+                if list(sizes) == list(big):
+                    return shared["boxes"], shared["scores"], shared["flags"].clone()   # callers edit their flags in place
+                cols = shared["cols"].get(tuple(sizes))
+                if cols is None:
+                    off, parts = 0, []
+                    for a, b in zip(sizes, big):
+                        parts.append(torch.arange(off, off + a, device=device))
+                        off += b
+                    cols = shared["cols"][tuple(sizes)] = torch.cat(parts)
+                Kb = sum(big)
+                rows = (torch.arange(N, device=device)[:, None] * Kb + cols[None, :]).reshape(-1)
+                return shared["boxes"][rows], shared["scores"][rows], shared["flags"][rows]
+        want = sizes
+        if shared is not None and shared.get("max_sizes") is not None:
+            want = [max(a, min(b, s.shape[1])) for a, b, s in zip(sizes, shared["max_sizes"], scores_l)]
+        K_ = sum(want)
+        offs, image_wh = self._segments(N, tuple(want), image_shapes, device)
+        deltas = torch.empty((N, K_, 4), dtype=torch.float32, device=device)
+        anch = torch.empty((N, K_, 4), dtype=torch.float32, device=device)
+        cand_scores = torch.empty((N, K_), dtype=torch.float32, device=device)
+        level_anchors = [anchors[0][l].bbox for l in range(num_levels)]
+        if not (device.type == "cuda" and K.rpn_topk_gather(scores_l, fused, A_, level_anchors, want, deltas, anch, cand_scores)):
+            col = 0   # pre_nms_top_n beyond the fused kernel's capacity: torch's top-k + the gather kernel, per level
+            for l, (s_l, k) in enumerate(zip(scores_l, want)):
+                vals, idx = s_l.topk(k, dim=1, sorted=True)
+                K.rpn_gather(fused[l], A_, idx, vals, level_anchors[l], deltas, anch, cand_scores, col)
+                col += k
+        flat_scores = cand_scores.reshape(-1)                 # image-major: row = j * K_ + (level offset + rank)
+        boxes, scores_nms, valid = K.decode_clip_boxes(deltas.reshape(-1, 4), anch.reshape(-1, 4), self.box_coder.weights,
+                                                       self.box_coder.bbox_xform_clip, image_wh, K_, flat_scores,
+                                                       self.min_size)
+        # filtered (too small) boxes carry score -1: they sort behind, and so can never suppress, a valid box
+        flags = K.nms_segmented_flags(boxes, scores_nms, offs, self.nms_thresh)
+        if valid is not None:
+            flags &= valid
+        if shared is not None:
+            shared.update(key=key, sizes=list(want), boxes=boxes, scores=flat_scores, flags=flags.clone())
+            if list(want) != list(sizes):
+                return self._candidates(anchors, scores_l, fused, A_, sizes, image_shapes, device)   # the smaller view of it
+        return boxes, flat_scores, flags
+
     def _segments(self, N, sizes, image_shapes, device):
         """Static description of the (image, level) NMS problems of a pass, cached per shape: segment offsets (a
         ctypes int array, image-major) and the per-image (width, height) table on the device."""
@@ -124,25 +184,7 @@ class RPNPostProcessor(nn.Module):
             A_ = objectness[0].shape[-1]
         sizes = [min(self.pre_nms_top_n, s.shape[1]) for s in scores_l]
         K_ = sum(sizes)
-        offs, image_wh = self._segments(N, tuple(sizes), image_shapes, device)
-        deltas = torch.empty((N, K_, 4), dtype=torch.float32, device=device)
-        anch = torch.empty((N, K_, 4), dtype=torch.float32, device=device)
-        cand_scores = torch.empty((N, K_), dtype=torch.float32, device=device)
-        level_anchors = [anchors[0][l].bbox for l in range(num_levels)]
-        if not (device.type == "cuda" and K.rpn_topk_gather(scores_l, fused, A_, level_anchors, sizes, deltas, anch, cand_scores)):
-            col = 0   # pre_nms_top_n beyond the fused kernel's capacity: torch's top-k + the gather kernel, per level
-            for l, (s_l, k) in enumerate(zip(scores_l, sizes)):
-                vals, idx = s_l.topk(k, dim=1, sorted=True)
-                K.rpn_gather(fused[l], A_, idx, vals, level_anchors[l], deltas, anch, cand_scores, col)
-                col += k
-        flat_scores = cand_scores.reshape(-1)                 # image-major: row = j * K_ + (level offset + rank)
-        boxes, scores_nms, valid = K.decode_clip_boxes(deltas.reshape(-1, 4), anch.reshape(-1, 4), self.box_coder.weights,
-                                                       self.box_coder.bbox_xform_clip, image_wh, K_, flat_scores,
-                                                       self.min_size)
-        # filtered (too small) boxes carry score -1: they sort behind, and so can never suppress, a valid box
-        flags = K.nms_segmented_flags(boxes, scores_nms, offs, self.nms_thresh)
-        if valid is not None:
-            flags &= valid
+        boxes, flat_scores, flags = self._candidates(anchors, scores_l, fused, A_, sizes, image_shapes, device)
         if self.post_nms_top_n > 0 and max(sizes) > self.post_nms_top_n:   # keep[:post_nms_top_n] per (image, level)
             f2, a = flags.view(N, K_), 0
             for k in sizes:
@@ -314,10 +356,25 @@ class RPNModule(nn.Module):
         coder = BoxCoder(weights=(1.0, 1.0, 1.0, 1.0))
         self.box_selector_train = make_rpn_postprocessor(cfg, coder, is_train=True, is_teacher=is_teacher)
         self.box_selector_test = make_rpn_postprocessor(cfg, coder, is_train=False, is_teacher=is_teacher)
+        if is_teacher and (self.box_selector_train.nms_thresh, self.box_selector_train.min_size) == (
+                self.box_selector_test.nms_thresh, self.box_selector_test.min_size):
+            # the teacher runs both selectors on one head output (RPNPostProcessor._candidates): shared candidate tables
+            shared = {"cols": {}, "max_sizes": [max(self.box_selector_train.pre_nms_top_n, self.box_selector_test.pre_nms_top_n)] * 8}
+            self.box_selector_train.shared = self.box_selector_test.shared = shared
         self.loss_evaluator = make_rpn_loss_evaluator(cfg, coder)
 
     def set_teacher_mode(self, mode):
         self.mode = mode
+
+    def candidate_sharing(self, on):
+        """Scope of the teacher's shared candidate tables: switched on for the duration of ONE `forward_teacher` pass."""
+        shared = getattr(self.box_selector_train, "shared", None)
+        if shared is not None:
+            shared["active"] = bool(on) and shared.get("enabled", True)
+            shared["key"] = None
+            if not on:
+                for k in ("boxes", "scores", "flags"):
+                    shared.pop(k, None)
 
     def _head_and_anchors(self, images, features, head_out=None):
         if isinstance(features, list):

@@ -57,6 +57,7 @@ KNOBS = {
     "nothread": dict(pdl=1, cg=0, fused=True, thread=False),
     "nolevels": dict(pdl=1, cg=0, fused=True, levels=False),
     "teacherfirst": dict(pdl=1, cg=0, fused=True, teacher_first=True),
+    "noshare": dict(pdl=1, cg=0, fused=True, rpn_share=False),
 }
 it = [2000]
 
@@ -84,6 +85,7 @@ for visit in range(2):
         BottleneckWithFixedBatchNorm.fused_backward = k["fused"]
         trainer.teacher_thread = k.get("thread", True)
         streams.set_enabled(k.get("levels", True))
+        teacher.rpn.box_selector_train.shared["enabled"] = k.get("rpn_share", True)
         tf = k.get("teacher_first", False)
         trainer.teacher_first = tf
         teacher.side_priority = -1 if tf else 0

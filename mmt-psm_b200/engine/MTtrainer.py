@@ -272,6 +272,12 @@ class MTtrainer(object):
         keys = unlabel[0].keys()
         return {k: sum(d[k] for d in unlabel) / len(unlabel) for k in keys}
 
+    def close(self):
+        """Stop the teacher thread (idempotent).  `train()` calls it; callers that drive `train_step` themselves may."""
+        pool, self._t_pool = self._t_pool, None
+        if pool is not None:
+            pool.shutdown(wait=True)
+
     def update_teacher(self, step):
         alpha = min(1 - 1 / (step + 1), self.alpha)
         self.optimizer.ema_only(alpha)
@@ -420,6 +426,7 @@ class MTtrainer(object):
             if iteration % 1000 == 999:
                 gc.collect()          # full collection (generation 2) at a point where a pause costs nothing measurable
         self.save_model(iteration + 1, final=True)
+        self.close()
         if self.gc_every > 0:
             gc.enable()
         total = time.time() - t0

@@ -98,6 +98,8 @@ class MTtrainer(object):
         # them (profiles/r02_timeline.md).  On two threads / two streams one pass enqueues while the other waits.
         # Only with CUDA graphs on (the production / bench configuration); parity tests run the passes in order.
         self.teacher_thread = os.environ.get("MMT_TEACHER_THREAD", "1") == "1"
+        self.backward_thread = os.environ.get("MMT_BACKWARD_THREAD", "1") == "1"
+        self._bw_pool = None
         # (measured: no effect on the step time, profiles/r02_ab_teacher_first.log — kept as a knob, off by default)
         self.teacher_first = os.environ.get("MMT_TEACHER_FIRST", "0") == "1"
         if self.teacher_first:
@@ -237,6 +239,11 @@ class MTtrainer(object):
         small = [torch.empty(256 << 10, dtype=torch.uint8, device=self.device) for _ in range(small_blocks)]
         del big, small
 
+    def _backward_job(self, loss, main_stream):
+        torch.cuda.set_device(self.device)
+        with torch.cuda.stream(main_stream):
+            loss.backward()
+
     def _teacher_job(self, teacher_list, main_stream):
         """Body of the second host thread: the teacher pass on its own CUDA stream (ordered after everything the main
         stream had enqueued when the job was submitted: the previous iteration's SGD + EMA, this iteration's uploads)."""
@@ -274,9 +281,11 @@ class MTtrainer(object):
 
     def close(self):
         """Stop the teacher thread (idempotent).  `train()` calls it; callers that drive `train_step` themselves may."""
-        pool, self._t_pool = self._t_pool, None
-        if pool is not None:
-            pool.shutdown(wait=True)
+        for attr in ("_t_pool", "_bw_pool"):
+            pool = getattr(self, attr, None)
+            setattr(self, attr, None)
+            if pool is not None:
+                pool.shutdown(wait=True)
 
     def update_teacher(self, step):
         alpha = min(1 - 1 / (step + 1), self.alpha)
@@ -363,8 +372,21 @@ class MTtrainer(object):
         sup_weighted = self.weight_sum_loss(loss_dict, iteration)
         sup_total = sum(v for v in sup_weighted.values())
         if mt_on:
-            sup_total.backward()
+            bw_future = None
+            if teacher_future is not None and self.backward_thread:
+                # The main thread is the iteration's longest host path (it reaches this point ~21.5 ms into a 24 ms
+                # iteration with the teacher's results long waiting, profiles/r02_join_probe.log): the supervised heads'
+                # backward — ~2 ms of enqueueing — moves to a worker while this thread starts on the unlabeled pass.
+                # Autograd runs the backward kernels on the streams of the forward ops whichever thread calls it; the
+                # worker is joined before the consistency terms' backward touches the same parameters' gradients.
+                if self._bw_pool is None:
+                    self._bw_pool = ThreadPoolExecutor(max_workers=1, thread_name_prefix="mmt-backward")
+                bw_future = self._bw_pool.submit(self._backward_job, sup_total, torch.cuda.current_stream(self.device))
+            else:
+                sup_total.backward()
             mt_dict = self.forward_unlabel(data_u_list, teacher_future)
+            if bw_future is not None:
+                bw_future.result()
             mt_weighted = self.weight_sum_loss(mt_dict, iteration)
             losses_dict = dict(sup_weighted)
             losses_dict.update(mt_weighted)

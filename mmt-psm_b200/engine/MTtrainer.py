@@ -98,7 +98,9 @@ class MTtrainer(object):
         # them (profiles/r02_timeline.md).  On two threads / two streams one pass enqueues while the other waits.
         # Only with CUDA graphs on (the production / bench configuration); parity tests run the passes in order.
         self.teacher_thread = os.environ.get("MMT_TEACHER_THREAD", "1") == "1"
-        self.backward_thread = os.environ.get("MMT_BACKWARD_THREAD", "1") == "1"
+        # (measured: no gain — 24.6 vs 24.3 ms, profiles/r02_ab_backward_thread.log: the backward's Python-level nodes contend
+        # for the GIL with the unlabeled pass — kept as a knob, off by default)
+        self.backward_thread = os.environ.get("MMT_BACKWARD_THREAD", "0") == "1"
         self._bw_pool = None
         # (measured: no effect on the step time, profiles/r02_ab_teacher_first.log — kept as a knob, off by default)
         self.teacher_first = os.environ.get("MMT_TEACHER_FIRST", "0") == "1"

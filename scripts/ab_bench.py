@@ -58,7 +58,7 @@ KNOBS = {
     "nolevels": dict(pdl=1, cg=0, fused=True, levels=False),
     "teacherfirst": dict(pdl=1, cg=0, fused=True, teacher_first=True),
     "noshare": dict(pdl=1, cg=0, fused=True, rpn_share=False),
-    "nobwthread": dict(pdl=1, cg=0, fused=True, bw_thread=False),
+    "bwthread": dict(pdl=1, cg=0, fused=True, bw_thread=True),
 }
 it = [2000]
 
@@ -85,7 +85,7 @@ for visit in range(2):
         L.mmt_conv_force_cta_group(k["cg"])
         BottleneckWithFixedBatchNorm.fused_backward = k["fused"]
         trainer.teacher_thread = k.get("thread", True)
-        trainer.backward_thread = k.get("bw_thread", True)
+        trainer.backward_thread = k.get("bw_thread", False)
         streams.set_enabled(k.get("levels", True))
         teacher.rpn.box_selector_train.shared["enabled"] = k.get("rpn_share", True)
         tf = k.get("teacher_first", False)

@@ -101,6 +101,7 @@ class MTtrainer(object):
         # (measured: no gain — 24.6 vs 24.3 ms, profiles/r02_ab_backward_thread.log: the backward's Python-level nodes contend
         # for the GIL with the unlabeled pass — kept as a knob, off by default)
         self.backward_thread = os.environ.get("MMT_BACKWARD_THREAD", "0") == "1"
+        self.early_rpn_targets = os.environ.get("MMT_EARLY_RPN_TARGETS", "1") == "1"
         self._bw_pool = None
         # (measured: no effect on the step time, profiles/r02_ab_teacher_first.log — kept as a knob, off by default)
         self.teacher_first = os.environ.get("MMT_TEACHER_FIRST", "0") == "1"
@@ -355,6 +356,9 @@ class MTtrainer(object):
                         self.student.prefetch_trunk("unl", data_u_list[-self.student_bs:])
             else:
                 self.student.prefetch_trunk("sup", img_s)
+        if self.cuda_graphs and self.early_rpn_targets and getattr(self.student, "_pending", None):
+            target_s = [t.to(self.device) for t in target_s]
+            self.student.precompute_rpn_targets(data_s, target_s)
         self.scheduler.step()
         self.optimizer.zero_grad()
         teacher_future = None

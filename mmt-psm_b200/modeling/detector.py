@@ -195,6 +195,16 @@ class GeneralizedRCNN(nn.Module):
         self._stu, self._deferred = None, []
         return True
 
+    def precompute_rpn_targets(self, images, targets):
+        """RPN loss targets of the supervised pass whose trunk has just been enqueued (rpn.RPNLossComputation.precompute):
+        the grid sizes come from the trunk graph's static outputs, nothing waits for the device."""
+        pend = self._pending.get("stu") or self._pending.get("sup")
+        if pend is None or not self.training:
+            return
+        feats = pend[0].static_out[:len(self.rpn.anchor_generator.strides)]
+        anchors = self.rpn.anchor_generator(to_image_list(images), [f.shape[1:3] for f in feats])
+        self.rpn.loss_evaluator.precompute(anchors, targets)
+
     def _stu_outputs(self):
         if self._stu is None:
             g, _, _, x = self._pending.pop("stu")

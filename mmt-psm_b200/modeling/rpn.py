@@ -294,6 +294,18 @@ class RPNLossComputation(object):
         pos, neg = self.fg_bg_sampler(labels)
         return labels, regression_targets, torch.cat(pos, dim=0), torch.cat(neg, dim=0)
 
+    @staticmethod
+    def _targets_key(targets):
+        return tuple((t.bbox.data_ptr(), len(t)) for t in targets)
+
+    @torch.no_grad()
+    def precompute(self, anchors, targets):
+        """Everything of the RPN loss that does not depend on the network's output — anchor / ground-truth matching, box
+        encoding, the sampler's draw — for the pass that is about to run; `__call__` picks it up if it is then handed the
+        same targets.  The trainer calls this right after it has enqueued the trunks, while the device is still busy with
+        the previous iteration: ~60 small launches leave the window between the trunk's completion and the heads."""
+        self._pre = (self._targets_key(targets), self._sample(anchors, targets))
+
     def teacher_sample_selection(self, anchors, objectness, box_regression, targets):
         """Reference rpn/loss.py:85-136.  Its outputs are never used downstream; the only observable
         effect is the sampler's draw from the random stream.  When the sampler draws on the host (parity mode,
@@ -315,7 +327,11 @@ class RPNLossComputation(object):
         `nonzero`s = two host syncs) and reduces over them; here the same sums run over all anchors under the
         sampling masks — with the fused head maps at hand, in ONE kernel (functional.rpn_loss) that reads the five
         per-level maps in place, instead of flattening / concatenating them and ~35 elementwise launches."""
-        labels, regression_targets, pos, neg = self._sample(anchors, targets)
+        pre, self._pre = getattr(self, "_pre", None), None
+        if pre is not None and pre[0] == self._targets_key(targets):
+            labels, regression_targets, pos, neg = pre[1]
+        else:
+            labels, regression_targets, pos, neg = self._sample(anchors, targets)
         labels = torch.cat(labels, dim=0)
         regression_targets = torch.cat(regression_targets, dim=0)
         if fused is not None and all(f.is_cuda and f.is_contiguous() for f in fused):

@@ -59,6 +59,7 @@ KNOBS = {
     "teacherfirst": dict(pdl=1, cg=0, fused=True, teacher_first=True),
     "noshare": dict(pdl=1, cg=0, fused=True, rpn_share=False),
     "bwthread": dict(pdl=1, cg=0, fused=True, bw_thread=True),
+    "lateTargets": dict(pdl=1, cg=0, fused=True, early_rpn=False),
 }
 it = [2000]
 
@@ -86,6 +87,7 @@ for visit in range(2):
         BottleneckWithFixedBatchNorm.fused_backward = k["fused"]
         trainer.teacher_thread = k.get("thread", True)
         trainer.backward_thread = k.get("bw_thread", False)
+        trainer.early_rpn_targets = k.get("early_rpn", True)
         streams.set_enabled(k.get("levels", True))
         teacher.rpn.box_selector_train.shared["enabled"] = k.get("rpn_share", True)
         tf = k.get("teacher_first", False)

@@ -445,6 +445,7 @@ def run_ours(args):
                "data": "synthetic",
                "config": {"workload": workload_name(args), "global_batch_labeled": BATCH * world,
                           "global_batch_unlabeled": BATCH * world if mt else 0, "parallelism": "dp%d" % world, "cuda_graphs": not args.no_graphs,
+                          "head_stream_priority": trainer.head_priority, "teacher_trunk_ctas": trainer.teacher_trunk_ctas,
                           "l2": "no explicit flush: one iteration streams >10 GB of activations through the 126 MB L2",
                           "final_loss": final_loss},
                "e2e": {"value": imgs / (ms_e2e * 1e-3), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,

@@ -107,6 +107,16 @@ class MTtrainer(object):
         self.teacher_first = os.environ.get("MMT_TEACHER_FIRST", "0") == "1"
         if self.teacher_first:
             self.teacher.side_priority = -1
+        # Head / glue work of both host threads on HIGH-priority streams, and the teacher's trunk graph captured with a few SMs
+        # left free (`teacher_trunk_ctas` of 148).  The trunk graphs are chains of persistent conv launches that own every SM
+        # for 50-500 us at a time; their kernel nodes keep the capture stream's priority 0.  A small head kernel of the OTHER
+        # pass (they run concurrently with the teacher's trunk for most of the heads phase) is then picked first at every
+        # kernel boundary, or starts at once on a free SM, instead of queueing behind the next conv wave — and every one of
+        # the ~10 read-backs of a pass waits for such a kernel.  Measured together 24.0 -> 23.4 ms per iteration (either one
+        # alone: within noise; profiles/r02_ab_head_priority.log).  Only with CUDA graphs on.
+        self.head_priority = int(os.environ.get("MMT_HEAD_PRIORITY", "-1"))
+        self.teacher_trunk_ctas = int(os.environ.get("MMT_TEACHER_TRUNK_CTAS", "132"))
+        self._head_stream = None
         self._t_stream, self._t_pool = None, None
         self._copy_stream, self._staged, self._pregrow_copy, self._prefetched = None, None, False, None
         self.pool_gb = tuple(float(v) for v in os.environ.get("MMT_POOL_GB", "6,4,0.5").split(","))   # main, teacher, copy stream
@@ -123,6 +133,7 @@ class MTtrainer(object):
         self.cuda_graphs = bool(on)
         self.student.enable_cuda_graphs(on, getattr(self.optimizer, "mark_touched", None))
         self.teacher.enable_cuda_graphs(on)
+        self.teacher.trunk_max_ctas = self.teacher_trunk_ctas if (on and 0 < self.teacher_trunk_ctas < 148) else None
 
     def weight_sum_loss(self, loss_dict, step):
         return weight_sum_losses(loss_dict, step, self.rampup_step, self.rampdown_step, self.max_iter,
@@ -252,7 +263,7 @@ class MTtrainer(object):
         stream had enqueued when the job was submitted: the previous iteration's SGD + EMA, this iteration's uploads)."""
         torch.cuda.set_device(self.device)
         if self._t_stream is None:
-            self._t_stream = torch.cuda.Stream(device=self.device, priority=-1 if self.teacher_first else 0)
+            self._t_stream = torch.cuda.Stream(device=self.device, priority=-1 if self.teacher_first else min(self.head_priority, 0))
         self._t_stream.wait_stream(main_stream)
         with torch.cuda.stream(self._t_stream):
             if self._pregrow_teacher:
@@ -296,6 +307,24 @@ class MTtrainer(object):
 
     # ---- one iteration ------------------------------------------------------------------------
     def train_step(self, iteration, data_s, target_s, data_u_list=None):
+        """One training iteration; returns (weighted loss dict, total loss).  With CUDA graphs on and `head_priority` < 0 the
+        iteration is enqueued from a high-priority stream that starts after everything on the caller's current stream and
+        that the caller's stream waits for on return (the trunk graphs run on their own side streams either way)."""
+        if not (self.cuda_graphs and self.head_priority < 0 and self.device.type == "cuda"):
+            return self._train_step(iteration, data_s, target_s, data_u_list)
+        ambient = torch.cuda.current_stream(self.device)
+        if self._head_stream is None:
+            self._head_stream = torch.cuda.Stream(device=self.device, priority=self.head_priority)
+        self._head_stream.wait_stream(ambient)
+        with torch.cuda.stream(self._head_stream):
+            losses_dict, losses = self._train_step(iteration, data_s, target_s, data_u_list)
+        ambient.wait_stream(self._head_stream)
+        for t in [losses] + list(losses_dict.values()):      # allocated on the head stream, read by the caller on its own
+            if isinstance(t, torch.Tensor) and t.is_cuda:
+                t.record_stream(ambient)
+        return losses_dict, losses
+
+    def _train_step(self, iteration, data_s, target_s, data_u_list=None):
         if self.gc_every > 0:
             if self._gc_steps == 0:
                 gc.collect()

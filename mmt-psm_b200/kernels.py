@@ -33,6 +33,20 @@ def get_conv_math():
     return "tf32" if _conv_impl == CONV_AUTO else "fp32"
 
 
+_conv_max_ctas = None   # None = the library's default (one CTA per SM)
+
+
+def set_conv_max_ctas(n):
+    """Size of the conv engine's persistent grids from now on (None = all 148 SMs); returns the previous setting.  A CUDA
+    graph captured under a smaller setting keeps it: the trainer captures the TEACHER's trunk with a few SMs left free, so
+    that the small head / glue kernels of the other pass never queue behind a full wave of persistent conv CTAs."""
+    global _conv_max_ctas
+    prev = _conv_max_ctas
+    check(_l.lib().mmt_conv_set_max_ctas(int(n) if n else 148), "conv_set_max_ctas")
+    _conv_max_ctas = int(n) if n else None
+    return prev
+
+
 def _need_cuda(*tensors):
     for t in tensors:
         if t is not None and not t.is_cuda:

@@ -74,6 +74,7 @@ class GeneralizedRCNN(nn.Module):
         self._graphs, self._graphs_on, self._graph_on_backward = {}, False, None
         self._pending, self._side = {}, None
         self.side_priority = 0     # CUDA priority of the trunk-prefetch stream (-1 = high; the trainer raises the teacher's)
+        self.trunk_max_ctas = None  # persistent-grid size the trunk graphs are captured with (None = every SM)
         self._stu, self._stu_ptrs, self._deferred = None, {}, []
 
     # ------------------------------------------------------------------------------ CUDA graphs
@@ -129,7 +130,13 @@ class GeneralizedRCNN(nn.Module):
         if len(self._graphs) >= 8:
             raise RuntimeError("more than 8 distinct (call site, input shape) trunks captured; CUDA graphs are meant "
                                "for fixed-size crops — call enable_cuda_graphs(False) for variable-size input")
-        g = GraphedCallable(fn, [x], backward=need_grad, on_backward=self._graph_on_backward)
+        from .. import kernels as K
+        prev = K.set_conv_max_ctas(self.trunk_max_ctas) if self.trunk_max_ctas else None
+        try:
+            g = GraphedCallable(fn, [x], backward=need_grad, on_backward=self._graph_on_backward)
+        finally:
+            if self.trunk_max_ctas:
+                K.set_conv_max_ctas(prev)
         self._graphs[key] = g
         return g, True
 

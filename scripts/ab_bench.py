@@ -60,15 +60,13 @@ KNOBS = {
     "noshare": dict(pdl=1, cg=0, fused=True, rpn_share=False),
     "bwthread": dict(pdl=1, cg=0, fused=True, bw_thread=True),
     "lateTargets": dict(pdl=1, cg=0, fused=True, early_rpn=False),
-    # eager head / glue work of both host threads on HIGH-priority streams (the trunk graphs' kernel nodes keep the
-    # priority 0 of the capture stream): a small head kernel queued next to a chain of persistent conv launches is
-    # picked first at every kernel boundary instead of in arrival order
-    "hiprio": dict(pdl=1, cg=0, fused=True, head_prio=-1),
-    "hiprio5": dict(pdl=1, cg=0, fused=True, head_prio=-5),
-    # teacher trunk captured with a persistent grid of 132 / 116 CTAs: 16 / 32 SMs stay free for the head kernels
-    "tcap132": dict(pdl=1, cg=0, fused=True, tcap=132),
+    # head / glue work of both host threads on high-priority streams + teacher trunk captured with 132 of 148 CTAs are the
+    # shipped defaults (MTtrainer.head_priority / teacher_trunk_ctas); these switch them off / vary them
+    "noprio": dict(pdl=1, cg=0, fused=True, head_prio=0, tcap=148),
+    "prio_only": dict(pdl=1, cg=0, fused=True, tcap=148),
+    "tcap_only": dict(pdl=1, cg=0, fused=True, head_prio=0),
     "tcap116": dict(pdl=1, cg=0, fused=True, tcap=116),
-    "hiprio_tcap132": dict(pdl=1, cg=0, fused=True, head_prio=-1, tcap=132),
+    "tcap100": dict(pdl=1, cg=0, fused=True, tcap=100),
     # interpreter's thread switch interval (two host threads share the GIL): default 5 ms
     "sw1e4": dict(pdl=1, cg=0, fused=True, switch=1e-4),
 }
@@ -88,33 +86,14 @@ def run(n):
     return [marks[j].elapsed_time(marks[j + 1]) for j in range(n)]
 
 
-_orig_graph_for = teacher._graph_for
-_tcap = [0]
-_hi_streams = {}
-
-
-def _capped_graph_for(site, x, n_views):
-    if _tcap[0]:
-        lib.check(L.mmt_conv_set_max_ctas(_tcap[0]))
-    try:
-        return _orig_graph_for(site, x, n_views)
-    finally:
-        lib.check(L.mmt_conv_set_max_ctas(148))
-
-
-teacher._graph_for = _capped_graph_for
 names = [c for c in args.configs.split(",") if c in KNOBS]
 for visit in range(2):
     for name in names:
         k = KNOBS[name]
-        _tcap[0] = k.get("tcap", 0)
         sys.setswitchinterval(k.get("switch", 0.005))
-        prio = k.get("head_prio", 0)
-        if prio and prio not in _hi_streams:      # one (ambient, teacher-thread) pair per priority: their allocator pools are reused
-            _hi_streams[prio] = (torch.cuda.Stream(device=dev, priority=prio), torch.cuda.Stream(device=dev, priority=prio))
-        ambient = _hi_streams[prio][0] if prio else torch.cuda.default_stream(dev)
         torch.cuda.synchronize()
-        torch.cuda.set_stream(ambient)
+        trainer.head_priority = k.get("head_prio", -1)          # shipped default: -1 / 132 (MTtrainer.__init__)
+        trainer.teacher_trunk_ctas = k.get("tcap", 132)
         trainer._pregrown_for = 0         # the per-stream allocator pools are grown again after this configuration's capture
         trainer.set_cuda_graphs(False)
         L.mmt_conv_set_pdl(k["pdl"])
@@ -129,7 +108,7 @@ for visit in range(2):
         trainer.teacher_first = tf
         teacher.side_priority = -1 if tf else 0
         teacher._side = None              # re-created with the configuration's priority
-        trainer._t_stream = _hi_streams[prio][1] if prio else None
+        trainer._t_stream = None
         trainer.set_cuda_graphs(True)
         run(4)
         t = run(args.steps)

@@ -117,6 +117,7 @@ class MTtrainer(object):
         self.head_priority = int(os.environ.get("MMT_HEAD_PRIORITY", "-1"))
         self.teacher_trunk_ctas = int(os.environ.get("MMT_TEACHER_TRUNK_CTAS", "132"))
         self._head_stream = None
+        self._loss_slot, self._loss_host, self._loss_event = None, None, None
         self._t_stream, self._t_pool = None, None
         self._copy_stream, self._staged, self._pregrow_copy, self._prefetched = None, None, False, None
         self.pool_gb = tuple(float(v) for v in os.environ.get("MMT_POOL_GB", "6,4,0.5").split(","))   # main, teacher, copy stream
@@ -426,6 +427,8 @@ class MTtrainer(object):
             losses_dict = dict(sup_weighted)
             losses_dict.update(mt_weighted)
             mt_total = sum(v for v in mt_weighted.values()) if mt_weighted else None
+            losses = sup_total.detach() + (mt_total.detach() if mt_total is not None else 0)
+            self._publish_loss(losses)         # the iteration's result exists now: its read-back need not wait for the backward
             if stacked:
                 # heads first; their gradient bucket (fc6 alone is 51 MB of the 185 MB arena) is then final and its
                 # all-reduce runs on NCCL's stream UNDER the trunk's backward graph; the trunk bucket follows it
@@ -442,9 +445,9 @@ class MTtrainer(object):
                     reduced = True
             elif mt_total is not None:
                 mt_total.backward()
-            losses = sup_total.detach() + (mt_total.detach() if mt_total is not None else 0)
         else:
             losses_dict, losses = sup_weighted, sup_total
+            self._publish_loss(losses)
             losses.backward()
         if self.world > 1 and not reduced:
             # one NCCL all-reduce: the whole student gradient arena + the per-tensor "touched" flags behind it
@@ -455,6 +458,30 @@ class MTtrainer(object):
         self.optimizer.step(ema_alpha=ema, grad_scale=1.0 / self.world)
         self.last_losses = {k: v.detach() for k, v in losses_dict.items()}
         return losses_dict, losses
+
+    def _publish_loss(self, total):
+        """Enqueue the 4-byte device -> host copy of the iteration's total loss into a pinned slot, right behind the kernels
+        that produce it (the forward passes and the loss sums) and AHEAD of the backward / all-reduce / optimizer launches."""
+        if self.device.type != "cuda":
+            self._loss_host, self._loss_event = total.detach().reshape(()).clone(), None
+            return
+        if self._loss_slot is None:
+            self._loss_slot = torch.empty((), dtype=torch.float32).pin_memory()
+        self._loss_slot.copy_(total.detach().reshape(()), non_blocking=True)
+        self._loss_event = torch.cuda.Event()
+        self._loss_event.record(torch.cuda.current_stream(self.device))
+        self._loss_host = self._loss_slot
+
+    def loss_value(self):
+        """The last `train_step`'s total loss as a Python float.  Waits for the copy `_publish_loss` enqueued — i.e. for the
+        iteration's forward passes — not for its backward and optimizer step, so a caller that reads every iteration's loss
+        (bench.py's end-to-end loop, a logger) does not drain the device at every iteration boundary.  Call it before the
+        next `train_step` (one pinned slot)."""
+        if self._loss_host is None:
+            raise RuntimeError("loss_value() before the first train_step()")
+        if self._loss_event is not None:
+            self._loss_event.synchronize()
+        return float(self._loss_host)
 
     def train(self):
         from ..utils.metric_logger import MetricLogger

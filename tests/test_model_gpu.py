@@ -256,6 +256,8 @@ def test_cuda_graph_trunks_match_eager(cuda, restore):
         torch.manual_seed(7)
         lib.reset_launch_count()
         ld, total = trainer.train_step(5, images, targets, views)
+        early = trainer.loss_value()           # the pinned-slot read-back enqueued ahead of the backward: same number
+        assert early == float(total), (early, float(total))
         first = {k: float(v) for k, v in ld.items()}
         p1, t1 = opt.flat_p.clone(), opt.flat_t.clone()
         lib.reset_launch_count()

@@ -281,6 +281,7 @@ def run_ours(args):
         h2d += sum(p.numel() * 4 for inst in t.get_field("masks").polygons for p in inst.polygons)
 
     it_counter = [2000]
+    e2e_probe = []
     e2e_warm = True
     staged_targets = []
     stage_next = os.environ.get("MMT_BENCH_STAGE", "1") != "0"      # "2": uploads only, trunks not enqueued ahead
@@ -292,11 +293,16 @@ def run_ours(args):
         if e2e:
             images, targets, views = pool[j % len(pool)]
             tg = staged_targets.pop() if staged_targets else fresh_targets(targets)
+            tp = [time.perf_counter()]
             ld, total = trainer.train_step(it, images, tg, views if mt else None)
+            tp.append(time.perf_counter())
             if stage_next and not last:      # the NEXT step's H2D copies start now, under this step's compute (a data
                 nxt = pool[(j + 1) % len(pool)]        # loader's prefetch); they are still inside the timed region
+                ft = fresh_targets(nxt[1])
+                tp.append(time.perf_counter())
                 staged_targets.append(trainer.stage(nxt[0], nxt[2] if mt else None, iteration=(it + 1) if stage_trunks else None,
-                                                    targets=fresh_targets(nxt[1])))
+                                                    targets=ft))
+            tp.append(time.perf_counter())
             # D2H of the step's loss (one fp32 scalar) + host sync on it, every step: the copy is enqueued behind the forward
             # passes that produce the loss (MTtrainer._publish_loss), so the host waits for the RESULT, not for the backward
             # and optimizer step behind it — those are waited for by the next step's first read-back and by the barrier
@@ -304,6 +310,9 @@ def run_ours(args):
             v = trainer.loss_value()
             if os.environ.get("MMT_BENCH_LOSS_DRAIN") == "1":     # the round-1 behaviour: drain the device at every step
                 v = float(total)
+            tp.append(time.perf_counter())
+            if len(tp) == 5:
+                e2e_probe.append([(b - a) * 1e3 for a, b in zip(tp, tp[1:])])   # train_step | fresh targets | stage | loss wait
             return v
         images, targets, views = resident[j % len(resident)]
         ld, total = trainer.train_step(it, images, targets, views if mt else None)
@@ -371,7 +380,20 @@ def run_ours(args):
     ms_dev, last = timed(args.steps, False)
     launches = lib.launch_count()
     final_loss = float(last)
+    del e2e_probe[:]
+    if os.environ.get("MMT_BENCH_TRACE") == "2":
+        trainer._stage_probe = []
     ms_e2e, last_e2e = timed(args.steps, True)
+    if trainer._stage_probe:
+        rows = [[(b - a) * 1e3 for a, b in zip(r, r[1:])] for r in trainer._stage_probe if len(r) == 5]
+        if rows:
+            print("stage() host phases, median ms: targets %.2f | uploads %.2f | take + student trunk %.2f | teacher trunk %.2f" % tuple(
+                sorted(c)[len(c) // 2] for c in zip(*rows)), file=sys.stderr, flush=True)
+        trainer._stage_probe = None
+    if e2e_probe and os.environ.get("MMT_BENCH_TRACE") in ("1", "2"):
+        cols = list(zip(*e2e_probe))
+        print("e2e host phases, median ms: train_step %.2f | fresh targets %.2f | stage %.2f | loss wait %.2f" % tuple(
+            sorted(c)[len(c) // 2] for c in cols), file=sys.stderr, flush=True)
     if sampler:
         sampler.window(t_window, time.perf_counter())
     clocks = sampler.stop() if sampler else None

@@ -118,6 +118,7 @@ class MTtrainer(object):
         self.teacher_trunk_ctas = int(os.environ.get("MMT_TEACHER_TRUNK_CTAS", "132"))
         self._head_stream = None
         self._loss_slot, self._loss_host, self._loss_event = None, None, None
+        self._stage_probe = None     # list: host timestamps of stage()'s phases are appended (bench.py, MMT_BENCH_TRACE=2)
         self._t_stream, self._t_pool = None, None
         self._copy_stream, self._staged, self._pregrow_copy, self._prefetched = None, None, False, None
         self.pool_gb = tuple(float(v) for v in os.environ.get("MMT_POOL_GB", "6,4,0.5").split(","))   # main, teacher, copy stream
@@ -178,6 +179,9 @@ class MTtrainer(object):
         student's unlabeled view, the teacher's views."""
         if self.device.type != "cuda":
             return targets
+        probe = self._stage_probe
+        if probe is not None:
+            probe.append([time.perf_counter()])
         dev_targets = None
         if targets is not None:
             # the next iteration's ground truth: boxes / labels uploaded and the polygons packed into their device arrays
@@ -186,6 +190,8 @@ class MTtrainer(object):
             for t in dev_targets:
                 if t.has_field("masks") and hasattr(t.get_field("masks"), "packed"):
                     t.get_field("masks").packed(self.device)
+        if probe is not None:
+            probe[-1].append(time.perf_counter())
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(device=self.device)
             self._pregrow_copy = True
@@ -206,6 +212,8 @@ class MTtrainer(object):
             done = torch.cuda.Event()
             done.record(self._copy_stream)
         self._staged = (staged, done)
+        if probe is not None:
+            probe[-1].append(time.perf_counter())
         # With the iteration number at hand the NEXT iteration's conv trunks are enqueued as well (they only need the
         # staged inputs and this iteration's SGD + EMA, already in the main stream's queue): a caller that now blocks on this
         # iteration's loss finds the device busy with them when it comes back, instead of idle until `train_step` has
@@ -222,8 +230,12 @@ class MTtrainer(object):
                 self._prefetched = {id(host_img): img_t}
                 self._prefetched.update({id(h): d for h, d in zip(views, dev_views)})
                 if self.student.prefetch_student(img_t, dev_views[len(views) - self.student_bs:]):
+                    if probe is not None:
+                        probe[-1].append(time.perf_counter())
                     with torch.no_grad():
                         self.teacher.prefetch_trunk("aug", dev_views[:self.teacher_bs])
+        if probe is not None:
+            probe[-1].append(time.perf_counter())
         return dev_targets
 
     def _take(self, t):

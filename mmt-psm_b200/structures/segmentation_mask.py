@@ -109,9 +109,12 @@ class SegmentationMask(object):
                     poly_off.append(poly_off[-1] + p.numel() // 2)
                 inst_off.append(len(poly_off) - 1)
             flat = torch.cat(xy) if xy else torch.zeros(0)
-            self._packed[key] = (flat.to(device, non_blocking=True),
-                                 torch.tensor(poly_off, dtype=torch.int32).to(device, non_blocking=True),
-                                 torch.tensor(inst_off, dtype=torch.int32).to(device, non_blocking=True))
+            host = (flat, torch.tensor(poly_off, dtype=torch.int32), torch.tensor(inst_off, dtype=torch.int32))
+            if torch.device(device).type == "cuda":
+                # through pinned staging: a host -> device copy from PAGEABLE memory first synchronises the stream it is
+                # enqueued on — the caller (MTtrainer.stage) would sit out the rest of the running iteration here
+                host = tuple(t.pin_memory() if (t.device.type == "cpu" and t.numel()) else t for t in host)
+            self._packed[key] = tuple(t.to(device, non_blocking=True) for t in host)
         return self._packed[key]
 
     def __repr__(self):

@@ -608,7 +608,9 @@ def make_segments(entries, device):
         arr[i].begin, arr[i].end, arr[i].lr, arr[i].weight_decay, arr[i].trainable = b, e, lr, wd, int(tr)
     raw = bytes(arr)
     t = torch.frombuffer(bytearray(raw), dtype=torch.uint8).clone()
-    return t.to(device)
+    if torch.device(device).type == "cuda":    # pinned staging: a pageable H2D copy would synchronise the stream (the table is
+        t = t.pin_memory()                     # rebuilt whenever the learning rate changes: every iteration during warm-up)
+    return t.to(device, non_blocking=True)
 
 
 # ------------------------------------------------------------------------------------ convs

@@ -81,11 +81,20 @@ class FusedSGDEMA(object):
         self._agreed = False
         self.touched = [False] * len(self.entries)
 
+    def _write_flags(self):
+        """This rank's touched flags -> the slot behind the gradient arena.  On CUDA through pinned staging: a copy from
+        pageable memory synchronises the stream first — here that is the trunk's backward graph, enqueued a moment ago, and
+        the host would lose its whole lead over the device at every iteration of a data-parallel run."""
+        host = torch.tensor(self.touched, dtype=torch.float32)
+        if self._flags.is_cuda:
+            host = host.pin_memory()
+        self._flags.copy_(host, non_blocking=True)
+        self._agreed = True
+
     def reduce_buffer(self):
         """The tensor a data-parallel trainer all-reduces (SUM): the gradient arena followed by this rank's per-tensor
         touched flags.  After the reduction `step` updates every tensor ANY rank accumulated a gradient into."""
-        self._flags.copy_(torch.tensor(self.touched, dtype=torch.float32), non_blocking=True)
-        self._agreed = True
+        self._write_flags()
         return self._g_full
 
     def _segments(self, touched):
@@ -118,8 +127,7 @@ class FusedSGDEMA(object):
 
     def publish_touched(self):
         """Write this rank's touched flags behind the gradient arena (they ride in the LAST bucket's all-reduce)."""
-        self._flags.copy_(torch.tensor(self.touched, dtype=torch.float32), non_blocking=True)
-        self._agreed = True
+        self._write_flags()
 
     def _agreed_segments(self):
         """Segment table whose update mask comes from the all-reduced flags: built on the device, no read-back."""

@@ -1,7 +1,7 @@
 #!/bin/bash
 # where the end-to-end loop's extra 1.7 ms per step goes: host phases of the e2e step (train_step | fresh targets | stage | loss wait)
 mkdir -p gpurun_out
-for st in 1 2; do
+for st in 1; do
   MMT_BENCH_STAGE=$st MMT_BENCH_TRACE=2 timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/u_bench_$st.json 2> gpurun_out/u_bench_$st.log
   grep "host phases" gpurun_out/u_bench_$st.log
   python -c "

@@ -311,11 +311,17 @@ def run_ours(args):
             if os.environ.get("MMT_BENCH_LOSS_DRAIN") == "1":     # the round-1 behaviour: drain the device at every step
                 v = float(total)
             tp.append(time.perf_counter())
+            if os.environ.get("MMT_BENCH_LOSS_TRACE") == "1":     # diagnostic: every term of every step (synchronises)
+                print("e2e step %d it %d loss %.5f | %s" % (j, it, v, " ".join("%s=%.4f" % (k, float(x)) for k, x in ld.items())),
+                      file=sys.stderr, flush=True)
             if len(tp) == 5:
                 e2e_probe.append([(b - a) * 1e3 for a, b in zip(tp, tp[1:])])   # train_step | fresh targets | stage | loss wait
             return v
         images, targets, views = resident[j % len(resident)]
         ld, total = trainer.train_step(it, images, targets, views if mt else None)
+        if os.environ.get("MMT_BENCH_LOSS_TRACE") == "1":
+            print("dev step %d it %d loss %.5f | %s" % (j, it, float(total), " ".join("%s=%.4f" % (k, float(x)) for k, x in ld.items())),
+                  file=sys.stderr, flush=True)
         return total
 
     def barrier():
